@@ -158,6 +158,9 @@ _DEFAULTS: Dict[str, Any] = {
         'heavy_outputs': True,
         # cache the decoded motion-weight volume across eval frames
         'cache_eval_volume': False,
+        # stratified-jitter noise: 'reference' = CPU default generator like network.py:468
+        # (same random stream as the reference), 'device' = torch.rand on the GPU
+        'jitter_rng': 'reference',
     },
 }
 

@@ -1,0 +1,273 @@
+"""`Network`: drop-in replacement of reference `core/nets/human_nerf/network.py` whose per-ray
+path runs on the hand-written sm_100a kernels (humannerf_b200/csrc via the C ABI).
+
+Same constructor (no arguments, reads the global cfg), same `forward` keyword arguments, same
+11-key output dict, same parameter names (`mweight_vol_decoder.*`, `non_rigid_mlp.module.*`,
+`cnl_mlp.module.*`, `pose_decoder.*`), so the reference's `train.py` / `run.py`, optimizer
+(per-name learning rates) and checkpoints keep working when `cfg.network_module` points here.
+
+Per forward (reference network.py:647-789):
+  per frame, PyTorch (batch 1):  pose refinement, motion bases, motion-weight volume decode
+  per chunk of cfg.chunk rays, CUDA kernels:
+      ops.sample_z -> ops.motion_field -> ops.canonical_field -> ops.composite
+There is no CPU fallback: tensors must live on a CUDA device and the shared library must load.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from humannerf_b200 import _lib, ops
+from humannerf_b200.config import get_cfg
+from humannerf_b200.embedders.hannw_fourier import hann_window_weights
+from humannerf_b200.nn_util import MotionBasisComputer
+
+
+def _load_symbol(module_name: str, symbol: str):
+    """cfg.<component>.module -> python symbol.  Dotted module names resolve through the normal
+    import system first (package installs), then - like the reference's `imp.load_source`
+    (component_factory.py:3-36) - as a file path relative to the current directory."""
+    try:
+        return getattr(importlib.import_module(module_name), symbol)
+    except ModuleNotFoundError:
+        path = module_name.replace('.', '/') + '.py'
+        if not os.path.isfile(path):
+            raise
+        spec = importlib.util.spec_from_file_location(module_name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return getattr(mod, symbol)
+
+
+class _SingleDeviceParallel(nn.Module):
+    """Keeps the `.module.` level that `nn.DataParallel` puts into the reference's parameter names
+    (network.py:68-72,115-119).  One process drives one GPU here, so nothing is replicated."""
+
+    def __init__(self, module: nn.Module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+_UNSUPPORTED = (
+    ('non_rigid_motion_model', lambda c: c.get('non_rigid_motion_model', 'mlp') != 'mlp'),
+    ('multihead.head_num', lambda c: c.get('multihead', {}).get('head_num', 1) != 1),
+    ('rgb_history.last_num', lambda c: c.get('rgb_history', {}).get('last_num', 0) != 0),
+    ('canonical_mlp.view_dir', lambda c: bool(c.canonical_mlp.get('view_dir', False))),
+    ('canonical_mlp.time_input', lambda c: bool(c.canonical_mlp.get('time_input', False))),
+    ('canonical_mlp.input_encoder.enable', lambda c: bool(c.canonical_mlp.get('input_encoder', {}).get('enable', False))),
+    ('canonical_mlp.condition_code_dim', lambda c: c.canonical_mlp.get('condition_code_dim', 0) != 0),
+    ('canonical_mlp.pose_color', lambda c: c.canonical_mlp.get('pose_color', 'wo') != 'wo'),
+    ('non_rigid_motion_mlp.time_input', lambda c: bool(c.non_rigid_motion_mlp.get('time_input', False))),
+    ('non_rigid_motion_mlp.pose_input', lambda c: not c.non_rigid_motion_mlp.get('pose_input', True)),
+    ('condition_code.type', lambda c: c.get('condition_code', {}).get('type', 'global') != 'global'),
+    ('posevec.type', lambda c: c.get('posevec', {}).get('type', 'axis_angle') != 'axis_angle'),
+)
+
+
+class Network(nn.Module):
+    def __init__(self):
+        super().__init__()
+        cfg = get_cfg()
+        for key, bad in _UNSUPPORTED:
+            if bad(cfg):
+                raise NotImplementedError(
+                    f'humannerf_b200.Network: config option `{key}` selects a research variant of the fork '
+                    f'that the B200 hot path does not implement (SURVEY.md section 2, row 22)')
+
+        self.motion_basis_computer = MotionBasisComputer(total_bones=cfg.total_bones)
+
+        self.mweight_vol_decoder = _load_symbol(cfg.mweight_volume.module, 'MotionWeightVolumeDecoder')(
+            embedding_size=cfg.mweight_volume.embedding_size,
+            volume_size=cfg.mweight_volume.volume_size,
+            total_bones=cfg.total_bones)
+
+        self.get_non_rigid_embedder = _load_symbol(cfg.non_rigid_embedder.module, 'get_embedder')
+        if cfg.non_rigid_motion_mlp.i_embed != 0 or cfg.canonical_mlp.i_embed != 0:
+            raise NotImplementedError('humannerf_b200.Network: identity embedders (i_embed = -1) are not supported')
+        nr_pe = 3 * 2 * cfg.non_rigid_motion_mlp.multires
+        nr_cfg = cfg.non_rigid_motion_mlp
+        self.non_rigid_mlp = _SingleDeviceParallel(
+            _load_symbol(nr_cfg.module, 'NonRigidMotionMLP')(
+                pos_embed_size=nr_pe,
+                condition_code_size=nr_cfg.condition_code_size,
+                mlp_width=nr_cfg.mlp_width,
+                mlp_depth=nr_cfg.mlp_depth,
+                skips=nr_cfg.skips,
+                multihead_enable=nr_cfg.multihead.enable,
+                multihead_depth=nr_cfg.multihead.head_depth,
+                multihead_num=cfg.multihead.head_num,
+                last_linear_scale=nr_cfg.last_linear_scale,
+                mlp_depth_plus=nr_cfg.mlp_depth_plus))
+
+        get_embedder = _load_symbol(cfg.embedder.module, 'get_embedder')
+        self.pos_embed_fn, cnl_pe = get_embedder(cfg.canonical_mlp.multires, cfg.canonical_mlp.i_embed)
+        self.dir_embed_fn = None
+        cn_cfg = cfg.canonical_mlp
+        self.cnl_mlp = _SingleDeviceParallel(
+            _load_symbol(cn_cfg.module, 'CanonicalMLP')(
+                input_ch=cnl_pe,
+                mlp_depth=cn_cfg.mlp_depth,
+                mlp_width=cn_cfg.mlp_width,
+                view_dir=cn_cfg.view_dir,
+                input_ch_dir=-1,
+                pose_color=cn_cfg.pose_color,
+                pose_ch=cn_cfg.pose_ch,
+                skips=[4],
+                multihead_enable=cn_cfg.multihead.enable,
+                multihead_depth=cn_cfg.multihead.head_depth,
+                multihead_num=cfg.multihead.head_num,
+                last_linear_scale=cn_cfg.last_linear_scale,
+                mlp_depth_plus=cn_cfg.mlp_depth_plus,
+                rgb_dynamic_features_ch=0))
+
+        if not cfg.pose_decoder_off:
+            self.pose_decoder = _load_symbol(cfg.pose_decoder.module, 'BodyPoseRefiner')(
+                embedding_size=cfg.pose_decoder.embedding_size,
+                mlp_width=cfg.pose_decoder.mlp_width,
+                mlp_depth=cfg.pose_decoder.mlp_depth)
+
+        nr, cn = self.non_rigid_mlp.module, self.cnl_mlp.module
+        self._spec = ops.FieldSpec(
+            nr_layers=len(nr.linear_layers()), nr_width=nr_cfg.mlp_width, nr_skip=nr.skip_layer_index(),
+            nr_freqs=nr_cfg.multires, cond_dim=nr_cfg.condition_code_size,
+            cn_layers=len(cn.linear_layers()), cn_width=cn_cfg.mlp_width, cn_skip=cn.skip_layer_index(),
+            cn_freqs=cn_cfg.multires)
+        self._vol_cache = None
+        self.motion_weights_vol = None
+        self.boundary_tensors = {}
+
+    # -- reference API -------------------------------------------------------------------
+    def deploy_mlps_to_secondary_gpus(self):
+        """The reference scatters MLP chunks over secondary GPUs with nn.DataParallel
+        (network.py:161-166).  Here every rank owns one GPU and shards rays instead
+        (humannerf_b200/parallel.py), so there is nothing to deploy."""
+        return self
+
+    # -- helpers ------------------------------------------------------------------------
+    def _field_weights(self):
+        nr = self.non_rigid_mlp.module.linear_layers()
+        cn = self.cnl_mlp.module.linear_layers()
+        return ([l.weight for l in nr], [l.bias for l in nr], [l.weight for l in cn], [l.bias for l in cn])
+
+    @staticmethod
+    def _multiply_corrected_Rs(Rs, correct_Rs):
+        total = Rs.shape[1]
+        return torch.matmul(Rs.reshape(-1, 3, 3), correct_Rs.reshape(-1, 3, 3)).reshape(-1, total, 3, 3)
+
+    def _decode_volume(self, priors):
+        cfg = get_cfg()
+        cache_ok = (not self.training) and (not torch.is_grad_enabled()) and \
+            bool(cfg.get('b200', {}).get('cache_eval_volume', False))
+        if cache_ok and self._vol_cache is not None and self._vol_cache[0] is priors:
+            return self._vol_cache[1]
+        vol = self.mweight_vol_decoder(motion_weights_priors=priors)
+        if cache_ok:
+            self._vol_cache = (priors, vol)
+        return vol
+
+    def forward(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec=None,
+                near=None, far=None, iter_val=1e7, **kwargs) -> Dict[str, torch.Tensor]:
+        cfg = get_cfg()
+        b200 = cfg.get('b200', {})
+        dev = dst_Rs.device
+        if dev.type != 'cuda':
+            raise RuntimeError('humannerf_b200.Network runs on CUDA devices only (no CPU fallback)')
+        it = float(torch.as_tensor(iter_val).reshape(-1)[0])
+
+        dst_Rs, dst_Ts = dst_Rs[None, ...].float(), dst_Ts[None, ...].float()
+        dst_posevec = dst_posevec[None, ...].float()
+        cnl_gtfms = cnl_gtfms[None, ...].float()
+        priors = motion_weights_priors[None, ...] if motion_weights_priors.dim() == 4 else motion_weights_priors
+
+        # 1. pose refinement (network.py:667-695)
+        if (not cfg.pose_decoder_off) and it >= cfg.pose_decoder.get('kick_in_iter', 0):
+            refined = self.pose_decoder(dst_posevec)['Rs']
+            dst_Rs = torch.cat([dst_Rs[:, 0:1], self._multiply_corrected_Rs(dst_Rs[:, 1:], refined)], dim=1)
+
+        # 2. condition code and hann window (network.py:697-738)
+        nr_cfg = cfg.non_rigid_motion_mlp
+        cond = dst_posevec[0]
+        if it < nr_cfg.kick_in_iter:
+            cond = torch.zeros_like(cond)
+        hann = hann_window_weights(it, nr_cfg.multires, nr_cfg.kick_in_iter, nr_cfg.full_band_iter).to(dev)
+
+        # 3. motion bases and blend-weight volume (network.py:757-763)
+        scale_Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts, cnl_gtfms)
+        vol = self._decode_volume(priors.float())[0]
+        self.motion_weights_vol = vol
+        # outputs of the replicated per-frame front end; the multi-GPU train step exchanges the
+        # gradients of these instead of the 63.6 M decoder parameters (parallel.CutBReducer)
+        self.boundary_tensors = {'motion_weights_vol': vol, 'motion_scale_Rs': scale_Rs, 'motion_Ts': Ts}
+        J = cfg.total_bones
+        vol_j = vol[:J]
+
+        # 4. rays (network.py:771-777)
+        rays_o = rays[0].reshape(-1, 3).float().contiguous()
+        rays_d = rays[1].reshape(-1, 3).float().contiguous()
+        lead_shape = list(rays[1].shape[:-1])
+        near = near.reshape(-1).float()
+        far = far.reshape(-1).float()
+        bbox_min = kwargs['cnl_bbox_min_xyz'].float()
+        bbox_scale = kwargs['cnl_bbox_scale_xyz'].float()
+        bgcolor = kwargs.get('bgcolor')
+        bgcolor = torch.zeros(3, device=dev) if bgcolor is None else bgcolor.float()
+        t_rand_all = kwargs.get('t_rand')
+
+        S = int(cfg.N_samples)
+        heavy = bool(b200.get('heavy_outputs', True))
+        ignore_nr = bool(cfg.ignore_non_rigid_motions)
+        precision = _lib.PRECISION_BF16 if str(b200.get('mlp_precision', 'fp32')).lower() == 'bf16' \
+            else _lib.PRECISION_FP32
+        nr_w, nr_b, cn_w, cn_b = self._field_weights()
+        packed = None
+        if precision == _lib.PRECISION_BF16:
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise RuntimeError('humannerf_b200: cfg.b200.mlp_precision="bf16" is a forward-only render path in '
+                                   'this build; wrap the call in torch.no_grad() or train with "fp32"')
+            packed = ops.pack_field_bf16(self._spec, nr_w, nr_b, cn_w, cn_b, cond)
+
+        outs = []
+        R = rays_o.shape[0]
+        chunk = int(cfg.chunk)
+        for a in range(0, R, chunk):
+            b = min(R, a + chunk)
+            o_c, d_c = rays_o[a:b], rays_d[a:b]
+            t_rand = None
+            if cfg.perturb > 0.:
+                if t_rand_all is not None:
+                    t_rand = t_rand_all[a:b]
+                elif str(b200.get('jitter_rng', 'reference')) == 'device':
+                    t_rand = torch.rand(b - a, S, device=dev)
+                else:   # the reference draws on the CPU default generator (network.py:468)
+                    t_rand = torch.rand(b - a, S).to(dev)
+            z = ops.sample_z(near[a:b], far[a:b], S, t_rand)
+            x_skel, mask, bw = ops.motion_field(scale_Rs[0], Ts[0], vol_j, bbox_min, bbox_scale,
+                                                rays_o=o_c, rays_d=d_c, z=z, want_weights=heavy)
+            raw, xyz, offs = ops.canonical_field(self._spec, x_skel.reshape(-1, 3), cond, hann, nr_w, nr_b,
+                                                 cn_w, cn_b, ignore_non_rigid=ignore_nr, precision=precision,
+                                                 packed=packed)
+            n = b - a
+            xyz = xyz.view(n, S, 3)
+            rgb, acc, depth, weights, cnl_xyz, cnl_rgb, w_max, rgbs = ops.composite(
+                raw.view(n, S, 4), mask, z, d_c, xyz, bgcolor, heavy=heavy)
+            res = {'rgb': rgb, 'alpha': acc, 'depth': depth, 'weights_on_rays': weights, 'xyz_on_rays': xyz,
+                   'cnl_xyz': cnl_xyz, 'cnl_rgb': cnl_rgb, 'cnl_weight': w_max, 'offsets': offs.view(n, S, 3)}
+            if heavy:
+                res['rgb_on_rays'] = rgbs
+                res['backward_motion_weights'] = bw
+            outs.append(res)
+
+        if not outs:
+            raise RuntimeError('humannerf_b200.Network.forward: no rays')
+        all_ret = {k: (outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs], dim=0)) for k in outs[0]}
+        for k in all_ret:
+            all_ret[k] = all_ret[k].reshape(lead_shape + list(all_ret[k].shape[1:]))
+        return all_ret

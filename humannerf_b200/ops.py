@@ -1,0 +1,408 @@
+"""Operators of the rendering hot path: thin `torch.autograd.Function` wrappers over
+the C ABI (`humannerf_b200/_lib.py`).  PyTorch allocates; the kernels compute.
+
+Operator <-> reference code (paths relative to the reference root)
+  gen_rays / rays_bbox / compact_rays   core/utils/camera_util.py:132-208, train.py:592-616
+  sample_z                              core/nets/human_nerf/network.py:455-471
+  motion_field                          network.py:392-444 (_sample_motion_fields) + :499
+  canonical_field                       network.py:233-327 (_apply_mlp_kernals) with the embedders,
+                                        mlp_offset.py:74-114 and mlp_rgb_sigma.py:132-206
+  composite                             network.py:355-388 (_raw2outputs)
+  scatter_rows / gather_rows            trainer.py:28-37 (_unpack_imgs), run.py:49-65
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FieldGrads, FieldParams, check, ptr, stream_ptr
+
+
+# ---------------------------------------------------------------------------
+# optional per-operator device timing (CUDA events on the launching stream; used by bench.py)
+# ---------------------------------------------------------------------------
+_TIMING = {'on': False, 'events': {}}
+
+
+class _timed:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING['on']:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMING['on']:
+            self.e.record()
+            _TIMING['events'].setdefault(self.name, []).append((self.s, self.e))
+        return False
+
+
+def timing_start() -> None:
+    _TIMING['on'] = True
+    _TIMING['events'] = {}
+
+
+def timing_stop():
+    """{op name: (total milliseconds, calls)}; synchronises the device."""
+    _TIMING['on'] = False
+    torch.cuda.synchronize()
+    out = {k: (sum(s.elapsed_time(e) for s, e in v), len(v)) for k, v in _TIMING['events'].items()}
+    _TIMING['events'] = {}
+    return out
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError('humannerf_b200: expected a CUDA tensor - the rendering hot path has no CPU fallback')
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------
+# ray set-up
+# ---------------------------------------------------------------------------
+def gen_rays(H: int, W: int, K: np.ndarray, E: np.ndarray, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Pixel rays in float64: rays_o, rays_d of shape (H*W, 3) on `device`."""
+    lib = _lib.load()
+    Kh = np.ascontiguousarray(K, dtype=np.float64)[:3, :3].copy()
+    Eh = np.ascontiguousarray(E, dtype=np.float64)
+    if Eh.shape == (3, 4):
+        Eh = np.concatenate([Eh, [[0, 0, 0, 1.0]]], 0)
+    Eh = np.ascontiguousarray(Eh)
+    o = torch.empty(H * W, 3, dtype=torch.float64, device=device)
+    d = torch.empty(H * W, 3, dtype=torch.float64, device=device)
+    with torch.cuda.device(o.device):
+        check(lib.hn_gen_rays(H, W, Kh.ctypes.data, Eh.ctypes.data, ptr(o), ptr(d), stream_ptr()), 'gen_rays')
+    return o, d
+
+
+def rays_bbox(bounds: np.ndarray, rays_o: torch.Tensor, rays_d: torch.Tensor):
+    """near, far (float64, dense) and mask (uint8) per ray; patches |d| < 1e-5 in `rays_d` IN PLACE."""
+    lib = _lib.load()
+    assert rays_o.dtype == torch.float64 and rays_d.dtype == torch.float64
+    n = rays_o.shape[0]
+    b = np.ascontiguousarray(np.asarray(bounds, dtype=np.float64).reshape(2, 3))
+    near = torch.empty(n, dtype=torch.float64, device=rays_o.device)
+    far = torch.empty(n, dtype=torch.float64, device=rays_o.device)
+    mask = torch.empty(n, dtype=torch.uint8, device=rays_o.device)
+    with torch.cuda.device(rays_o.device):
+        check(lib.hn_rays_bbox(n, b.ctypes.data, ptr(rays_o), ptr(rays_d), ptr(near), ptr(far), ptr(mask),
+                               stream_ptr()), 'rays_bbox')
+    return near, far, mask
+
+
+def compact_rays(mask, rays_o, rays_d, near, far):
+    """Keep the rays with mask = 1 in pixel order; returns float32 o, d, near (R,1), far (R,1), pixel_index (R)."""
+    lib = _lib.load()
+    n = mask.shape[0]
+    dev = mask.device
+    o = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    nr = torch.empty(n, dtype=torch.float32, device=dev)
+    fr = torch.empty(n, dtype=torch.float32, device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.hn_compact_rays_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.hn_compact_rays(n, ptr(mask), ptr(rays_o), ptr(rays_d), ptr(near), ptr(far), ptr(o), ptr(d),
+                                  ptr(nr), ptr(fr), ptr(idx), ptr(count), ptr(ws), stream_ptr()), 'compact_rays')
+    r = int(count.item())
+    return o[:r], d[:r], nr[:r, None], fr[:r, None], idx[:r]
+
+
+_T_TABLES = {}
+
+
+def _t_table(n_samples: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1, S) evaluated on the CPU (bit-exact with the reference's table) and cached."""
+    key = (n_samples, str(device))
+    if key not in _T_TABLES:
+        _T_TABLES[key] = torch.linspace(0.0, 1.0, steps=n_samples).to(device)
+    return _T_TABLES[key]
+
+
+def sample_z(near: torch.Tensor, far: torch.Tensor, n_samples: int,
+             t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    near, far = _f32c(near).reshape(-1), _f32c(far).reshape(-1)
+    r = near.shape[0]
+    z = torch.empty(r, n_samples, dtype=torch.float32, device=near.device)
+    if t_rand is not None:
+        t_rand = _f32c(t_rand)
+        assert t_rand.shape == (r, n_samples)
+    with torch.cuda.device(near.device), _timed('sample_z'):
+        check(lib.hn_sample_z(r, n_samples, ptr(near), ptr(far), ptr(_t_table(n_samples, near.device)),
+                              ptr(t_rand), ptr(z), stream_ptr()), 'sample_z')
+    return z
+
+
+# ---------------------------------------------------------------------------
+# motion field
+# ---------------------------------------------------------------------------
+class _MotionField(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale, want_weights):
+        lib = _lib.load()
+        J = Rs.shape[0]
+        V = vol.shape[-1]
+        if pts is not None:
+            n_rays, S = pts.shape[0], pts.shape[1]
+            dev = pts.device
+        else:
+            n_rays, S = z.shape
+            dev = z.device
+        x_skel = torch.empty(n_rays, S, 3, dtype=torch.float32, device=dev)
+        mask = torch.empty(n_rays, S, 1, dtype=torch.float32, device=dev)
+        weights = torch.empty(n_rays, S, J, dtype=torch.float32, device=dev) if want_weights else None
+        with torch.cuda.device(dev), _timed('motion_field_fwd'):
+            check(lib.hn_motion_field_fwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
+                                          ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(x_skel),
+                                          ptr(mask), ptr(weights), stream_ptr()), 'motion_field_fwd')
+        ctx.save_for_backward(rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale)
+        ctx.dims = (n_rays, S, J, V)
+        if weights is None:
+            weights = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(weights)
+        return x_skel, mask, weights
+
+    @staticmethod
+    def backward(ctx, g_x, g_m, g_w):
+        lib = _lib.load()
+        rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale = ctx.saved_tensors
+        n_rays, S, J, V = ctx.dims
+        dev = Rs.device
+        g_x = _f32c(g_x) if g_x is not None else None
+        g_m = _f32c(g_m) if g_m is not None else None
+        g_w = _f32c(g_w) if (g_w is not None and g_w.numel() > 0) else None
+        d_vol = torch.zeros_like(vol)
+        d_Rs = torch.zeros_like(Rs)
+        d_Ts = torch.zeros_like(Ts)
+        with torch.cuda.device(dev), _timed('motion_field_bwd'):
+            check(lib.hn_motion_field_bwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
+                                          ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(g_x), ptr(g_m),
+                                          ptr(g_w), ptr(d_vol), ptr(d_Rs), ptr(d_Ts), stream_ptr()),
+                  'motion_field_bwd')
+        return None, None, None, None, d_Rs, d_Ts, d_vol, None, None, None
+
+
+def motion_field(Rs, Ts, vol, bbox_min, bbox_scale, *, pts=None, rays_o=None, rays_d=None, z=None,
+                 want_weights=True):
+    """x_skel (R,S,3), mask (R,S,1), weights (R,S,J) [or None].  `vol` is the first J channels of the
+    motion-weight volume, (J,V,V,V) contiguous; Rs (J,3,3); Ts (J,3).  Differentiable in Rs, Ts, vol."""
+    Rs, Ts, vol = _f32c(Rs), _f32c(Ts), _f32c(vol)
+    bbox_min, bbox_scale = _f32c(bbox_min), _f32c(bbox_scale)
+    if pts is not None:
+        pts = _f32c(pts)
+        assert pts.dim() == 3 and pts.shape[-1] == 3
+    else:
+        rays_o, rays_d, z = _f32c(rays_o), _f32c(rays_d), _f32c(z)
+    x, m, w = _MotionField.apply(rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale, bool(want_weights))
+    return x, m, (w if want_weights else None)
+
+
+# ---------------------------------------------------------------------------
+# canonical field (hann-PE -> non-rigid MLP -> PE -> canonical MLP)
+# ---------------------------------------------------------------------------
+class FieldSpec:
+    """Static description of the two MLPs (layer counts, widths, skip positions, encodings)."""
+
+    def __init__(self, nr_layers=7, nr_width=128, nr_skip=4, nr_freqs=6, cond_dim=69,
+                 cn_layers=9, cn_width=256, cn_skip=5, cn_freqs=10):
+        self.nr_layers, self.nr_width, self.nr_skip, self.nr_freqs = nr_layers, nr_width, nr_skip, nr_freqs
+        self.cond_dim = cond_dim
+        self.cn_layers, self.cn_width, self.cn_skip, self.cn_freqs = cn_layers, cn_width, cn_skip, cn_freqs
+
+    def params(self, nr_w, nr_b, cn_w, cn_b) -> FieldParams:
+        fp = FieldParams()
+        fp.nr_layers, fp.nr_width, fp.nr_skip, fp.nr_freqs = self.nr_layers, self.nr_width, self.nr_skip, self.nr_freqs
+        fp.cond_dim = self.cond_dim
+        fp.cn_layers, fp.cn_width, fp.cn_skip, fp.cn_freqs = self.cn_layers, self.cn_width, self.cn_skip, self.cn_freqs
+        for i in range(self.nr_layers):
+            fp.nr_w[i], fp.nr_b[i] = ptr(nr_w[i]), ptr(nr_b[i])
+        for i in range(self.cn_layers):
+            fp.cn_w[i], fp.cn_b[i] = ptr(cn_w[i]), ptr(cn_b[i])
+        return fp
+
+
+def pack_field_bf16(spec: FieldSpec, nr_w, nr_b, cn_w, cn_b, cond: torch.Tensor) -> torch.Tensor:
+    """bf16 weight image for the tcgen05 kernel (re-pack whenever weights or the pose change)."""
+    lib = _lib.load()
+    ws = [_f32c(t.detach()) for t in list(nr_w) + list(nr_b) + list(cn_w) + list(cn_b)]
+    nl, cl = spec.nr_layers, spec.cn_layers
+    fp = spec.params(ws[:nl], ws[nl:2 * nl], ws[2 * nl:2 * nl + cl], ws[2 * nl + cl:])
+    nbytes = int(lib.hn_field_packed_bytes(C.byref(fp)))
+    if nbytes <= 0:
+        check(-1, 'field_packed_bytes')
+    cond = _f32c(cond.detach()).reshape(-1)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=cond.device)
+    with torch.cuda.device(cond.device):
+        check(lib.hn_field_pack_bf16(C.byref(fp), ptr(cond), ptr(packed), stream_ptr()), 'field_pack_bf16')
+    packed._hn_keepalive = ws   # the pack kernels read the fp32 weights asynchronously
+    return packed
+
+
+class _CanonicalField(torch.autograd.Function):
+    """inputs: x_skel (P,3), cond (cond_dim), hann_w (nr_freqs), then the flat parameter list
+    [nr_w..., nr_b..., cn_w..., cn_b...]."""
+
+    @staticmethod
+    def forward(ctx, spec: FieldSpec, ignore_non_rigid: bool, precision: int, packed, x_skel, cond, hann_w,
+                *flat):
+        lib = _lib.load()
+        nl, cl = spec.nr_layers, spec.cn_layers
+        flat = [_f32c(t) for t in flat]
+        nr_w, nr_b, cn_w, cn_b = flat[:nl], flat[nl:2 * nl], flat[2 * nl:2 * nl + cl], flat[2 * nl + cl:]
+        fp = spec.params(nr_w, nr_b, cn_w, cn_b)
+        x_skel = _f32c(x_skel)
+        P = x_skel.shape[0]
+        dev = x_skel.device
+        need_grad = any(ctx.needs_input_grad)
+        if need_grad and precision != _lib.PRECISION_FP32:
+            raise RuntimeError('humannerf_b200: the bf16 tensor-core field is forward-only in this build; '
+                               'set cfg.b200.mlp_precision = "fp32" for training')
+        raw = torch.empty(P, 4, dtype=torch.float32, device=dev)
+        xyz = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        off = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        wbytes = int(lib.hn_field_workspace_bytes(C.byref(fp), P, 1 if need_grad else 0, precision))
+        if wbytes < 0:
+            check(-1, 'field_workspace_bytes')
+        ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev), _timed('field_fwd_bf16' if precision == _lib.PRECISION_BF16 else 'field_fwd_fp32'):
+            check(lib.hn_field_fwd(C.byref(fp), P, ptr(x_skel), ptr(cond), ptr(hann_w), 1 if ignore_non_rigid else 0,
+                                   ptr(raw), ptr(xyz), ptr(off), ptr(ws), wbytes, 1 if need_grad else 0, precision,
+                                   ptr(packed), stream_ptr()), 'field_fwd')
+        if need_grad:
+            ctx.spec, ctx.ignore = spec, ignore_non_rigid
+            ctx.ws = ws
+            ctx.save_for_backward(x_skel, cond, hann_w, *flat)
+        return raw, xyz, off
+
+    @staticmethod
+    def backward(ctx, g_raw, g_xyz, g_off):
+        lib = _lib.load()
+        spec = ctx.spec
+        nl, cl = spec.nr_layers, spec.cn_layers
+        x_skel, cond, hann_w, *flat = ctx.saved_tensors
+        nr_w, nr_b, cn_w, cn_b = flat[:nl], flat[nl:2 * nl], flat[2 * nl:2 * nl + cl], flat[2 * nl + cl:]
+        fp = spec.params(nr_w, nr_b, cn_w, cn_b)
+        P = x_skel.shape[0]
+        dev = x_skel.device
+        grads = [torch.zeros_like(t) for t in flat]
+        fg = FieldGrads()
+        gn_w, gn_b, gc_w, gc_b = grads[:nl], grads[nl:2 * nl], grads[2 * nl:2 * nl + cl], grads[2 * nl + cl:]
+        for i in range(nl):
+            if not ctx.ignore:
+                fg.nr_w[i], fg.nr_b[i] = ptr(gn_w[i]), ptr(gn_b[i])
+        for i in range(cl):
+            fg.cn_w[i], fg.cn_b[i] = ptr(gc_w[i]), ptr(gc_b[i])
+        g_raw = _f32c(g_raw) if g_raw is not None else torch.zeros(P, 4, device=dev)
+        g_xyz = _f32c(g_xyz) if g_xyz is not None else None
+        g_off = _f32c(g_off) if g_off is not None else None
+        d_x = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        sbytes = int(lib.hn_field_bwd_scratch_bytes(C.byref(fp), P))
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev), _timed('field_bwd_fp32'):
+            check(lib.hn_field_bwd(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(cond), ptr(hann_w),
+                                   1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
+                                   ptr(ctx.ws), ctx.ws.numel(), ptr(scratch), sbytes, stream_ptr()), 'field_bwd')
+        ctx.ws = None
+        return (None, None, None, None, d_x, None, None, *grads)
+
+
+def canonical_field(spec: FieldSpec, x_skel, cond, hann_w, nr_w, nr_b, cn_w, cn_b, *,
+                    ignore_non_rigid=False, precision=_lib.PRECISION_FP32, packed=None):
+    """raw (P,4), xyz (P,3), offsets (P,3) for canonical-space samples x_skel (P,3)."""
+    flat = list(nr_w) + list(nr_b) + list(cn_w) + list(cn_b)
+    cond = _f32c(cond).reshape(-1)
+    hann_w = _f32c(hann_w).reshape(-1)
+    return _CanonicalField.apply(spec, bool(ignore_non_rigid), int(precision), packed, x_skel, cond, hann_w, *flat)
+
+
+# ---------------------------------------------------------------------------
+# compositing
+# ---------------------------------------------------------------------------
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, mask, z, rays_d, xyz, bgcolor, heavy):
+        lib = _lib.load()
+        R, S = z.shape
+        dev = raw.device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        rgb, acc, depth = new(R, 3), new(R), new(R)
+        weights = new(R, S)
+        cnl_xyz, cnl_rgb, w_max = new(R, 3), new(R, 3), new(R)
+        rgbs = new(R, S, 3) if heavy else None
+        with torch.cuda.device(dev), _timed('composite_fwd'):
+            check(lib.hn_composite_fwd(R, S, ptr(raw), ptr(mask), ptr(z), ptr(rays_d), ptr(xyz), ptr(bgcolor),
+                                       ptr(rgb), ptr(acc), ptr(depth), ptr(weights), ptr(cnl_xyz), ptr(cnl_rgb),
+                                       ptr(w_max), ptr(rgbs), stream_ptr()), 'composite_fwd')
+        ctx.save_for_backward(raw, mask, z, rays_d, bgcolor)
+        if rgbs is None:
+            rgbs = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(cnl_xyz, cnl_rgb, w_max, rgbs)
+        return rgb, acc, depth, weights, cnl_xyz, cnl_rgb, w_max, rgbs
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, g_depth, g_w, *_):
+        lib = _lib.load()
+        raw, mask, z, rays_d, bgcolor = ctx.saved_tensors
+        R, S = z.shape
+        dev = raw.device
+        c = lambda g: _f32c(g) if g is not None else None
+        d_raw = torch.empty(R, S, 4, dtype=torch.float32, device=dev)
+        d_mask = torch.empty(R, S, 1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _timed('composite_bwd'):
+            check(lib.hn_composite_bwd(R, S, ptr(raw), ptr(mask), ptr(z), ptr(rays_d), ptr(bgcolor), ptr(c(g_rgb)),
+                                       ptr(c(g_acc)), ptr(c(g_depth)), ptr(c(g_w)), ptr(d_raw), ptr(d_mask),
+                                       stream_ptr()), 'composite_bwd')
+        return d_raw, d_mask, None, None, None, None, None
+
+
+def composite(raw, mask, z, rays_d, xyz, bgcolor, heavy=True):
+    """rgb (R,3), alpha (R), depth (R), weights (R,S), cnl_xyz, cnl_rgb, cnl_weight, rgb_on_rays.
+    Differentiable in raw and mask (through rgb, alpha, depth, weights)."""
+    raw, mask, z = _f32c(raw), _f32c(mask), _f32c(z)
+    rays_d, xyz, bgcolor = _f32c(rays_d), _f32c(xyz), _f32c(bgcolor)
+    return _Composite.apply(raw, mask, z, rays_d, xyz, bgcolor, bool(heavy))
+
+
+# ---------------------------------------------------------------------------
+# scatter / gather of rays into images or patches
+# ---------------------------------------------------------------------------
+class _ScatterRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, index, base):
+        lib = _lib.load()
+        out = base.clone()
+        n, c = src.shape
+        with torch.cuda.device(src.device):
+            check(lib.hn_scatter_rows(n, c, ptr(src), ptr(index), ptr(out), stream_ptr()), 'scatter_rows')
+        ctx.save_for_backward(index)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (index,) = ctx.saved_tensors
+        g = _f32c(g)
+        n = index.shape[0]
+        c = g.shape[-1]
+        out = torch.empty(n, c, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib.hn_gather_rows(n, c, ptr(g.reshape(-1, c)), ptr(index), ptr(out), stream_ptr()), 'gather_rows')
+        return out, None, None
+
+
+def scatter_rows(src: torch.Tensor, index: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
+    """Copy of `base` (..., C) with row index[r] of its flattened (N, C) view replaced by src[r]."""
+    return _ScatterRows.apply(_f32c(src), index.to(torch.int64).contiguous(), _f32c(base))

@@ -1,0 +1,201 @@
+/*
+ * humannerf_b200 - C ABI of the B200-native HumanNeRF per-ray rendering hot path.
+ *
+ * One shared library (libhumannerf_b200.so), extern "C", plain pointers and sizes only.
+ * The reference (ChenYutongTHU/humannerf) is pure Python and has no FFI of its own; each
+ * entry point below replaces one group of eager PyTorch / numpy calls of the reference and
+ * cites it (paths relative to the reference root).  A Python host binds these with ctypes
+ * (humannerf_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - the caller owns all memory (inputs, outputs, workspaces); nothing is allocated or freed here;
+ *    every op that needs scratch memory has a *_workspace_bytes query;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *  - return value: 0 = ok, < 0 = argument error, > 0 = cudaError_t; text via hn_last_error()
+ *    (thread local).  No entry point exits or aborts the process;
+ *  - float = IEEE fp32 row-major; "nullable" pointers may be NULL to skip that input / output;
+ *  - entry points keep no mutable global state (only function attributes set once per device).
+ */
+#ifndef HUMANNERF_B200_H
+#define HUMANNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_ABI_VERSION 1
+#define HN_MAX_LAYERS 16
+
+/* ABI version of the loaded library (compare with HN_ABI_VERSION). */
+int hn_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* hn_last_error(void);
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t hn_launch_count(void);
+/* 1 if the tcgen05/TMEM fused-MLP kernel was compiled in (sm_100a build). */
+int hn_has_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  core/utils/camera_util.py:132-159  get_rays_from_KRT
+ * Pixel (x, y, 1) -> K^-1 -> camera -> world; origin = -R^T T; d = pixel_world - origin (not
+ * normalised).  float64 arithmetic.  K_host: 9 doubles row-major; E_host: 16 doubles row-major
+ * (world->camera 4x4).  rays_o, rays_d: (H*W, 3) double, row-major pixel order.
+ */
+int hn_gen_rays(int H, int W, const double* K_host, const double* E_host,
+                double* rays_o, double* rays_d, void* stream);
+
+/* a2  core/utils/camera_util.py:162-208  rays_intersect_3d_bbox
+ * bounds_host: 6 doubles (min xyz, max xyz), padded by 0.01 inside.  |d| < 1e-5 components are
+ * overwritten with 1e-5 IN PLACE in rays_d (the reference mutates the array the network later
+ * consumes).  mask[i] = 1 iff exactly two of the six plane hits lie in the eps-grown box; near /
+ * far (double, dense, defined where mask = 1) = |p - o| / |d| min / max.  Bit-exact float64.
+ */
+int hn_rays_bbox(int64_t n_rays, const double* bounds_host, const double* rays_o, double* rays_d,
+                 double* near, double* far, uint8_t* mask, void* stream);
+
+/* Stream compaction of the rays selected by `mask`, keeping row-major pixel order
+ * (core/data/human_nerf/train.py:592-616: rays[ray_mask], near/far .astype(float32)).
+ * Outputs have capacity n_rays; *count (device int64) receives R.  pixel_index[r] = source pixel.
+ */
+int64_t hn_compact_rays_workspace_bytes(int64_t n_rays);
+int hn_compact_rays(int64_t n_rays, const uint8_t* mask, const double* rays_o, const double* rays_d,
+                    const double* near, const double* far,
+                    float* out_o, float* out_d, float* out_near, float* out_far,
+                    int32_t* pixel_index, int64_t* count, void* workspace, void* stream);
+
+/* a9  core/nets/human_nerf/network.py:455-471, 499
+ * z[r][s] = near*(1-t_s) + far*t_s with t = t_table (S floats, torch.linspace(0,1,S));
+ * if t_rand (R,S) != NULL: stratified jitter between neighbouring mid points.  Separate
+ * multiply / add roundings (no FMA contraction) -> bit-exact with the eager reference.
+ */
+int hn_sample_z(int64_t n_rays, int n_samples, const float* near, const float* far,
+                const float* t_table, const float* t_rand /*nullable*/, float* z, void* stream);
+
+/* a10  core/nets/human_nerf/network.py:392-444  _sample_motion_fields  (+ pts = o + d*z, :499)
+ * Either pts (P,3) is given, or pts == NULL and (rays_o, rays_d (R,3), z (R,S)) are.
+ * Rs (J,3,3), Ts (J,3): motion bases; vol (>=J, V, V, V) blend-weight volume indexed [z][y][x];
+ * bbox_min, bbox_scale: 3 floats each (device).  Trilinear, align_corners=True, zero padding.
+ * Outputs: x_skel (P,3), mask (P) = sum_j w_j, weights (P,J) nullable.  J <= 32.
+ */
+int hn_motion_field_fwd(int64_t n_rays, int n_samples, int n_joints, int vol_size,
+                        const float* pts, const float* rays_o, const float* rays_d, const float* z,
+                        const float* Rs, const float* Ts, const float* vol,
+                        const float* bbox_min, const float* bbox_scale,
+                        float* x_skel, float* mask, float* weights, void* stream);
+
+/* Backward of the above.  d_x_skel (P,3), d_mask (P), d_weights (P,J) are nullable upstream
+ * gradients.  Accumulates (+=) into d_vol (J,V,V,V), d_Rs (J,3,3), d_Ts (J,3): caller zeroes.
+ */
+int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_size,
+                        const float* pts, const float* rays_o, const float* rays_d, const float* z,
+                        const float* Rs, const float* Ts, const float* vol,
+                        const float* bbox_min, const float* bbox_scale,
+                        const float* d_x_skel, const float* d_mask, const float* d_weights,
+                        float* d_vol, float* d_Rs, float* d_Ts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11-a14  embedders/{hannw_fourier,fourier}.py, non_rigid_motion_mlps/mlp_offset.py:74-114,
+ *          canonical_mlps/mlp_rgb_sigma.py:132-206, network.py:233-327 (_apply_mlp_kernals)
+ *
+ * "Canonical field": x_skel -> hann-PE -> non-rigid MLP -> xyz = x_skel + offset -> PE ->
+ * canonical MLP -> raw (r,g,b,sigma).  Weights are the reference's nn.Linear tensors, (out,in)
+ * row-major fp32, in module order.  Layer layout (reference defaults in parentheses):
+ *   non-rigid: layer 0 takes [cond (69) | pe (36)]; layer nr_skip (4) takes [h | pe]; the last
+ *              layer (index nr_layers-1) maps width -> 3 without activation;
+ *   canonical: layer 0 takes pe (63); layer cn_skip (5) takes [pe | h]; the last layer maps
+ *              width -> 4 without activation.
+ */
+typedef struct hn_field_params {
+  int32_t nr_layers;   /* Linear layers of the non-rigid MLP incl. output (7) */
+  int32_t nr_width;    /* 128 */
+  int32_t nr_skip;     /* index of the layer that re-reads the encoding (4); -1 = none */
+  int32_t nr_freqs;    /* 6  -> 36-d hann-windowed encoding, no raw x */
+  int32_t cond_dim;    /* 69 */
+  int32_t cn_layers;   /* Linear layers of the canonical MLP incl. output (9) */
+  int32_t cn_width;    /* 256 */
+  int32_t cn_skip;     /* 5; -1 = none */
+  int32_t cn_freqs;    /* 10 -> 63-d encoding incl. raw x */
+  int32_t reserved;
+  const float* nr_w[HN_MAX_LAYERS];
+  const float* nr_b[HN_MAX_LAYERS];
+  const float* cn_w[HN_MAX_LAYERS];
+  const float* cn_b[HN_MAX_LAYERS];
+} hn_field_params;
+
+/* Gradient destinations, same shapes as the weights; accumulated (+=); caller zeroes. */
+typedef struct hn_field_grads {
+  float* nr_w[HN_MAX_LAYERS];
+  float* nr_b[HN_MAX_LAYERS];
+  float* cn_w[HN_MAX_LAYERS];
+  float* cn_b[HN_MAX_LAYERS];
+} hn_field_grads;
+
+#define HN_PRECISION_FP32 0   /* SIMT fp32 kernels, 1e-4 parity path                       */
+#define HN_PRECISION_BF16 1   /* tcgen05 / TMEM fused kernel, bf16 operands, fp32 accumulate */
+
+/* Bytes of workspace hn_field_fwd needs for n_samples.  save_for_backward != 0 keeps every
+ * activation hn_field_bwd needs (the same workspace must then be passed to it untouched). */
+int64_t hn_field_workspace_bytes(const hn_field_params* p, int64_t n_samples,
+                                 int save_for_backward, int precision);
+
+/* cond (cond_dim), hann_w (nr_freqs) are device vectors.  ignore_non_rigid != 0 skips the
+ * non-rigid MLP (cfg.ignore_non_rigid_motions, network.py:264,276-277): xyz = x_skel, offsets = 0.
+ * Outputs: raw (P,4), xyz (P,3), offsets (P,3).
+ * For HN_PRECISION_BF16, `packed` is the bf16 weight image made by hn_field_pack_bf16. */
+int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_skel,
+                 const float* cond, const float* hann_w, int ignore_non_rigid,
+                 float* raw, float* xyz, float* offsets,
+                 void* workspace, int64_t workspace_bytes, int save_for_backward,
+                 int precision, const void* packed, void* stream);
+
+/* Backward (HN_PRECISION_FP32 path).  d_raw (P,4), d_xyz (P,3) nullable, d_offsets (P,3) nullable.
+ * Writes d_x_skel (P,3) and accumulates parameter gradients into `g`. `scratch` must hold
+ * hn_field_bwd_scratch_bytes. */
+int64_t hn_field_bwd_scratch_bytes(const hn_field_params* p, int64_t n_samples);
+int hn_field_bwd(const hn_field_params* p, const hn_field_grads* g, int64_t n_samples,
+                 const float* x_skel, const float* cond, const float* hann_w, int ignore_non_rigid,
+                 const float* d_raw, const float* d_xyz, const float* d_offsets,
+                 float* d_x_skel, const void* workspace, int64_t workspace_bytes,
+                 void* scratch, int64_t scratch_bytes, void* stream);
+
+/* bf16 weight image for the tcgen05 kernel: weights re-tiled into the UMMA shared-memory
+ * core-matrix layout, in consumption order, with the condition code folded into the first
+ * non-rigid bias (W0[:, :cond_dim] . cond + b0 is constant per frame, mlp_offset.py:75-77). */
+int64_t hn_field_packed_bytes(const hn_field_params* p);
+int hn_field_pack_bf16(const hn_field_params* p, const float* cond, void* packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a15  core/nets/human_nerf/network.py:355-388  _raw2outputs
+ * raw (R,S,4), mask (R,S), z (R,S), rays_d (R,3), xyz (R,S,3), bgcolor (3, in 0..255).
+ * Outputs: rgb (R,3), acc (R), depth (R), weights (R,S) nullable, cnl_xyz (R,3), cnl_rgb (R,3),
+ * w_max (R), rgb_on_rays (R,S,3) nullable.  arg-max ties resolve to the first sample.
+ */
+int hn_composite_fwd(int64_t n_rays, int n_samples, const float* raw, const float* mask,
+                     const float* z, const float* rays_d, const float* xyz, const float* bgcolor,
+                     float* rgb, float* acc, float* depth, float* weights,
+                     float* cnl_xyz, float* cnl_rgb, float* w_max, float* rgb_on_rays, void* stream);
+
+/* Backward w.r.t. raw and mask.  Upstream grads d_rgb (R,3), d_acc (R), d_depth (R),
+ * d_weights (R,S) are nullable.  Writes d_raw (R,S,4) and d_mask (R,S). */
+int hn_composite_bwd(int64_t n_rays, int n_samples, const float* raw, const float* mask,
+                     const float* z, const float* rays_d, const float* bgcolor,
+                     const float* d_rgb, const float* d_acc, const float* d_depth,
+                     const float* d_weights, float* d_raw, float* d_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a16  core/train/trainers/human_nerf/trainer.py:28-37 _unpack_imgs and run.py:49-65
+ * Scatter per-ray values (R,C) into a dense image / patch stack pre-filled with `fill` (C floats,
+ * device): out[dst_index[r]*C + c] = src[r*C + c].  And the matching gather for the backward.
+ */
+int hn_scatter_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* dst_index,
+                    float* out, void* stream);
+int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* src_index,
+                   float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUMANNERF_B200_H */

@@ -1,0 +1,31 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, smoke, a short bench, then (only if the plain bench exited 0)
+# the ncu launch list.  Everything is logged under gpurun_out/.  Each stage has its own timeout so a
+# hung kernel cannot run into gpurun's limit.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+echo "== pytest (fp32 + rays + composite + motion field) =="
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -s -k "not bf16 and not full_size" > gpurun_out/pytest_fp32.log 2>&1
+echo "exit $?" >> gpurun_out/pytest_fp32.log
+tail -5 gpurun_out/pytest_fp32.log
+echo "== pytest (bf16 tcgen05) =="
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -s -k "bf16 or full_size" > gpurun_out/pytest_bf16.log 2>&1
+echo "exit $?" >> gpurun_out/pytest_bf16.log
+tail -5 gpurun_out/pytest_bf16.log
+echo "== smoke =="
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "exit $?" >> gpurun_out/smoke.log
+tail -3 gpurun_out/smoke.log
+echo "== bench =="
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
+rc=$?
+echo "bench exit $rc"
+tail -c 3000 gpurun_out/bench.log
+tail -5 gpurun_out/bench.err
+if [ $rc -eq 0 ] && [ "${HN_NCU:-1}" = "1" ]; then
+  echo "== ncu launch list =="
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+  echo "ncu exit $?"
+fi

@@ -1,0 +1,155 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol the header declares, the host
+mirror of the reference interface (config, Network construction, parameter names, init parity,
+patch sampling) behaves like the reference, and the product path fails loudly without CUDA."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from humannerf_b200 import _lib, synthetic as syn
+from humannerf_b200.config import CfgNode, get_cfg, make_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'humannerf_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(hn_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.isfile(_lib.lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.lib_path())
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/humannerf_b200.h but not exported'
+    assert sorted(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ set(declared)
+    loaded = _lib.load()
+    assert loaded.hn_version() == _lib.HN_ABI_VERSION
+    assert loaded.hn_has_tcgen05() == 1
+    assert loaded.hn_last_error() == b'' or isinstance(loaded.hn_last_error(), bytes)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    rc = lib.hn_sample_z(4, 0, None, None, None, None, None, None)
+    assert rc < 0 and b'hn_sample_z' in lib.hn_last_error()
+    rc = lib.hn_composite_fwd(1, 4096, *([None] * 15))
+    assert rc < 0 and b'n_samples' in lib.hn_last_error()
+    p = _lib.FieldParams()
+    assert lib.hn_field_workspace_bytes(ctypes.byref(p), 10, 0, 0) == -1      # zero layers
+
+
+def test_field_plan_sizes():
+    """Workspace / packed-image sizes for the reference architecture (no device work)."""
+    from humannerf_b200.ops import FieldSpec
+    lib = _lib.load()
+    fp = FieldSpec().params([None] * 7, [None] * 7, [None] * 9, [None] * 9)
+    per_sample = lib.hn_field_workspace_bytes(ctypes.byref(fp), 1000, 1, 0) - 256
+    # non-rigid 108+128*3+164+128*2+4, canonical 64+256*4+320+256*3+4 floats per sample
+    assert per_sample == 1000 * 4 * ((108 + 128 * 3 + 164 + 128 * 2 + 4) + (64 + 256 * 4 + 320 + 256 * 3 + 4))
+    packed = lib.hn_field_packed_bytes(ctypes.byref(fp))
+    # bf16 image: non-rigid (48*128 + 3*128*128 + 176*128 + 128*128 + 128*16) + canonical
+    # (64*256 + 4*256*256 + 320*256 + 2*256*256 + 256*16) elements, plus tables
+    elems = (48 * 128 + 3 * 128 * 128 + 176 * 128 + 128 * 128 + 128 * 16) + (64 * 256 + 4 * 256 * 256 + 320 * 256 + 2 * 256 * 256 + 256 * 16)
+    assert 2 * elems < packed < 2 * elems + 64 * 1024
+
+
+def test_ops_refuse_cpu_tensors():
+    from humannerf_b200 import ops
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.sample_z(torch.zeros(2, 1), torch.ones(2, 1), 8)
+
+
+def test_config_surface(tmp_path):
+    cfg = make_cfg()
+    assert cfg.N_samples == 128 and cfg.chunk == 32768 and cfg.canonical_mlp.mlp_width == 256
+    y = tmp_path / 'exp.yaml'
+    y.write_text("task: 'zju_mocap'\nsubject: 'p387'\npatch:\n  size: 20\nbrand_new_key: 3\n")
+    cfg = make_cfg([str(y)], ['N_samples', '64', 'train.lr', '0.001'])
+    assert cfg.patch.size == 20 and cfg.patch.N_patches == 6 and cfg.brand_new_key == 3
+    assert cfg.N_samples == 64 and cfg.train.lr == 0.001
+    with pytest.raises(KeyError):
+        make_cfg([], ['no.such.key', '1'])
+    assert get_cfg() is make_cfg()
+    assert isinstance(cfg.clone(), CfgNode)
+
+
+def test_network_parameters_and_init_match_reference():
+    from humannerf_b200.network import Network
+    make_cfg()
+    torch.manual_seed(0)
+    net = Network()
+    sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == syn.REFERENCE_PARAM_SHAPES
+    assert sum(p.numel() for p in net.parameters()) == 64417381
+    g = json.load(open(os.path.join(GOLD, 'init_stats_seed0.json')))
+    assert list(sd.keys()) == list(g.keys())
+    for k, v in sd.items():
+        assert abs(float(v.double().sum()) - g[k][0]) <= 1e-9 * max(1.0, abs(g[k][0])), k
+        assert [float(x) for x in v.reshape(-1)[:4]] == g[k][2], k
+    assert net.deploy_mlps_to_secondary_gpus() is net
+    with pytest.raises(RuntimeError, match='CUDA'):
+        fr = {k: torch.from_numpy(v) for k, v in syn.make_frame(0).items()}
+        net(rays=torch.zeros(3, 2, 3), near=torch.ones(2, 1), far=torch.ones(2, 1) * 2, dst_Rs=fr['dst_Rs'],
+            dst_Ts=fr['dst_Ts'], cnl_gtfms=fr['cnl_gtfms'], motion_weights_priors=fr['motion_weights_priors'],
+            dst_posevec=fr['dst_posevec'], cnl_bbox_min_xyz=fr['cnl_bbox_min_xyz'],
+            cnl_bbox_scale_xyz=fr['cnl_bbox_scale_xyz'])
+
+
+def test_unsupported_variants_raise():
+    from humannerf_b200.network import Network
+    cfg = make_cfg()
+    cfg.multihead.head_num = 4
+    with pytest.raises(NotImplementedError, match='multihead'):
+        Network()
+    cfg = make_cfg()
+    cfg.canonical_mlp.view_dir = True
+    with pytest.raises(NotImplementedError):
+        Network()
+    make_cfg()
+
+
+def test_host_patch_sampling_matches_reference():
+    from humannerf_b200.data import sample_patches
+    g = np.load(os.path.join(GOLD, 'patches.npz'))
+
+    class Replay:                       # feeds back the two host randoms the reference drew
+        def __init__(self):
+            self.i = 0
+
+        def rand(self, n):
+            return np.array([g['u_subject'][self.i]])
+
+        def choice(self, n, size=None, replace=True):
+            assert n == g['choice_n'][self.i]
+            v = np.array([g['choice_idx'][self.i]])
+            self.i += 1
+            return v
+    sel, masks, div, xy = sample_patches(g['ray_mask'], g['subject_mask'], int(g['H']), int(g['W']), 6,
+                                         int(g['patch_size']), Replay(), float(g['sample_subject_ratio']))
+    assert np.array_equal(sel, g['select_inds']) and np.array_equal(masks, g['patch_masks'])
+    assert np.array_equal(div, g['div_indices']) and np.array_equal(xy, g['xy_min'])
+
+
+def test_hann_window_weights():
+    from humannerf_b200.embedders.hannw_fourier import get_embedder, hann_window_weights
+    from oracle import humannerf_oracle as orc
+    make_cfg()
+    for it in (0, 10000, 23456, 30000, 50000, 10000000, torch.full((1,), 30000)):
+        assert torch.equal(hann_window_weights(it, 6), orc.hann_weights(it, 6, 10000, 50000))
+    fn, dim = get_embedder(6, 30000, 0)
+    x = torch.rand(5, 3)
+    assert dim == 36 and torch.allclose(fn(x), orc.fourier_pe(x, 6, orc.hann_weights(30000, 6, 10000, 50000), False))
+    from humannerf_b200.embedders.fourier import get_embedder as ge
+    fn, dim = ge(10, 0)
+    assert dim == 63 and torch.allclose(fn(x), orc.fourier_pe(x, 10))
