@@ -276,7 +276,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    it_val = torch.full((1,), 60000, device=dev)
+    it_val = 60000          # python int: no device->host sync per step (the trainer's (1,) tensor also works)
 
     # =========================== leg 1: device-resident inputs (`value`) ===========================
     dev_batches = [to_device(hb) for hb in host_batches]
