@@ -256,8 +256,8 @@ class _CanonicalField(torch.autograd.Function):
     [nr_w..., nr_b..., cn_w..., cn_b...]."""
 
     @staticmethod
-    def forward(ctx, spec: FieldSpec, ignore_non_rigid: bool, precision: int, packed, x_skel, cond, hann_w,
-                *flat):
+    def forward(ctx, spec: FieldSpec, ignore_non_rigid: bool, precision: int, packed, need_grad: bool, x_skel,
+                cond, hann_w, *flat):
         lib = _lib.load()
         nl, cl = spec.nr_layers, spec.cn_layers
         flat = [_f32c(t) for t in flat]
@@ -266,7 +266,6 @@ class _CanonicalField(torch.autograd.Function):
         x_skel = _f32c(x_skel)
         P = x_skel.shape[0]
         dev = x_skel.device
-        need_grad = any(ctx.needs_input_grad)
         if need_grad and precision != _lib.PRECISION_FP32:
             raise RuntimeError('humannerf_b200: the bf16 tensor-core field is forward-only in this build; '
                                'set cfg.b200.mlp_precision = "fp32" for training')
@@ -316,7 +315,7 @@ class _CanonicalField(torch.autograd.Function):
                                    1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
                                    ptr(ctx.ws), ctx.ws.numel(), ptr(scratch), sbytes, stream_ptr()), 'field_bwd')
         ctx.ws = None
-        return (None, None, None, None, d_x, None, None, *grads)
+        return (None, None, None, None, None, d_x, None, None, *grads)
 
 
 def canonical_field(spec: FieldSpec, x_skel, cond, hann_w, nr_w, nr_b, cn_w, cn_b, *,
@@ -325,7 +324,11 @@ def canonical_field(spec: FieldSpec, x_skel, cond, hann_w, nr_w, nr_b, cn_w, cn_
     flat = list(nr_w) + list(nr_b) + list(cn_w) + list(cn_b)
     cond = _f32c(cond).reshape(-1)
     hann_w = _f32c(hann_w).reshape(-1)
-    return _CanonicalField.apply(spec, bool(ignore_non_rigid), int(precision), packed, x_skel, cond, hann_w, *flat)
+    # Function.forward always runs with grad mode off, so the decision to keep activations for the
+    # backward pass is taken here
+    need_grad = torch.is_grad_enabled() and (x_skel.requires_grad or any(t.requires_grad for t in flat))
+    return _CanonicalField.apply(spec, bool(ignore_non_rigid), int(precision), packed, need_grad, x_skel, cond,
+                                 hann_w, *flat)
 
 
 # ---------------------------------------------------------------------------

@@ -244,10 +244,10 @@ def fixture_state_dict(shapes, dense: bool = True, scale: float = 1.0):
 
     Random-init HumanNeRF renders an almost empty image (alpha_max ~ 8e-3,
     offsets ~ 1e-4: SURVEY.md section 8c), which makes every tolerance vacuous.
-    `dense=True` therefore boosts the density row of the canonical output
+    `dense=True` therefore rescales the density row of the canonical output
     layer, the non-rigid output layer and the pose-decoder output layer so that
-    alpha spans (0,1), offsets reach centimetres and the pose refinement is
-    non-trivial.  The same dict is loaded into the reference (when generating
+    alpha spans (0,1), offsets are centimetres (as in a trained model) and the
+    pose refinement is non-trivial.  The same dict is loaded into the reference (when generating
     golden vectors), the oracle and the CUDA implementation."""
     import zlib
     import torch
@@ -271,11 +271,11 @@ def fixture_state_dict(shapes, dense: bool = True, scale: float = 1.0):
     if dense:
         k = 'cnl_mlp.module.output_linear.0'
         if k + '.weight' in out:
-            out[k + '.weight'][3] *= 60.0
-            out[k + '.bias'][3] += 8.0
+            out[k + '.weight'][3] *= 25.0
+            out[k + '.bias'][3] += 6.0
         k = 'non_rigid_mlp.module.block_mlps.12.weight'
         if k in out:
-            out[k] *= 0.15
+            out[k] *= 0.012
         k = 'pose_decoder.block_mlps.8.weight'
         if k in out:
             out[k] *= 0.1

@@ -99,7 +99,9 @@ def main():
     H = W = 48
     Ks = K.copy()
     Ks[:2] *= (W / 512.0)
-    ro, rd = camera_util.get_rays_from_KRT(H, W, Ks, E[:3, :3], E[:3, 3])
+    # float64 camera, like the training path (E comes out of apply_global_tfm_to_camera as float64)
+    ro, rd = camera_util.get_rays_from_KRT(H, W, Ks.astype(np.float64), E[:3, :3].astype(np.float64),
+                                           E[:3, 3].astype(np.float64))
     ro = ro.reshape(-1, 3).copy()
     rd = rd.reshape(-1, 3).copy()
     rd_in = rd.copy()

@@ -44,14 +44,19 @@ def report(name, got, want, atol, rtol=0.0):
     assert np.all(err <= lim) and not np.isnan(got).any(), msg
 
 
-def rel_max(name, got, want, rel):
+def rel_max(name, got, want, rel, outlier=10.0):
+    """Gradient check: relative L2 error <= rel and max-norm relative error <= outlier * rel.  The
+    max-norm bound is looser because a ReLU whose pre-activation is within rounding of zero may
+    switch between two fp32 evaluations, which moves single entries by far more than rounding."""
     got = got.detach().double().cpu().numpy()
     want = want.detach().double().cpu().numpy() if torch.is_tensor(want) else np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, f'{name}: shape {got.shape} vs {want.shape}'
     scale = np.abs(want).max() + 1e-20
     err = np.abs(got - want).max() / scale
-    print(f'[parity] {name}: max-norm relative err {err:.3e} (limit {rel:.1e}), |ref|max {scale:.3e}')
-    assert err <= rel and not np.isnan(got).any(), f'{name}: {err:.3e} > {rel:.1e}'
+    l2 = np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-20)
+    print(f'[parity] {name}: rel L2 err {l2:.3e} (limit {rel:.1e}), max-norm rel err {err:.3e} '
+          f'(limit {outlier * rel:.1e}), |ref|max {scale:.3e}')
+    assert l2 <= rel and err <= outlier * rel and not np.isnan(got).any(), f'{name}: L2 {l2:.3e} max {err:.3e} > {rel:.1e}'
 
 
 @pytest.fixture(scope='module')
@@ -78,7 +83,7 @@ def test_gen_rays_and_bbox(ops):
     H, W = int(g['H']), int(g['W'])
     o, d = ops.gen_rays(H, W, g['K'], g['E'], DEV)
     report('gen_rays.o', o, g['rays_o'], 1e-6)
-    report('gen_rays.d', d, g['rays_d_in'], 2e-7)           # golden is the float32 camera path
+    report('gen_rays.d', d, g['rays_d_in'], 1e-12)          # float64 camera; K^-1 / dot order differ from LAPACK/BLAS
     # a2 on identical float64 inputs: bit exact
     ro, rd = T(g['rays_o'], DEV), T(g['rays_d_in'], DEV).clone()
     near, far, mask = ops.rays_bbox(g['bounds'], ro, rd)
@@ -325,7 +330,9 @@ def test_field_fp32_forward(ops, sd, frame, P):
         raw, xyz, off = ops.canonical_field(spec, x.to(DEV), cond.to(DEV), hann.to(DEV), *w, ignore_non_rigid=ignore)
         report(f'field32.offsets[P={P},ignore={ignore}]', off, off_w, 2e-6, 1e-5)
         report(f'field32.xyz[P={P},ignore={ignore}]', xyz, xyz_w, 2e-6, 1e-5)
-        report(f'field32.raw[P={P},ignore={ignore}]', raw, raw_w, 5e-4, 2e-4)   # sigma row is scaled x60
+        # the density row of the fixture is scaled x25 and the 2^9 encoding frequency amplifies the
+        # 1e-7 differences in xyz; what has to hold to 1e-4 is the composited output (network tests)
+        report(f'field32.raw[P={P},ignore={ignore}]', raw, raw_w, 3e-3, 5e-4)
 
 
 def test_field_fp32_backward(ops, sd, frame):
