@@ -237,6 +237,7 @@ int hn_composite_fwd(int64_t n_rays, int n_samples, const float* raw, const floa
                      float* rgb_on_rays, void* stream) {
   if (n_rays < 0 || n_samples <= 0 || n_samples > 512)
     return fail_arg("hn_composite_fwd: n_samples=%d outside [1,512]", n_samples);
+  if (n_rays == 0) return 0;
   if (!raw || !mask || !z || !rays_d || !bgcolor || !rgb || !acc || !depth)
     return fail_arg("hn_composite_fwd: null required pointer");
   if (cnl_xyz && !xyz) return fail_arg("hn_composite_fwd: cnl_xyz requested without xyz");
@@ -259,6 +260,7 @@ int hn_composite_bwd(int64_t n_rays, int n_samples, const float* raw, const floa
                      void* stream) {
   if (n_rays < 0 || n_samples <= 0 || n_samples > 512)
     return fail_arg("hn_composite_bwd: n_samples=%d outside [1,512]", n_samples);
+  if (n_rays == 0) return 0;
   if (!raw || !mask || !z || !rays_d || !bgcolor || !d_raw)
     return fail_arg("hn_composite_bwd: null required pointer");
   if (n_rays == 0) return 0;

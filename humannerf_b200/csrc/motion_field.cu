@@ -259,6 +259,7 @@ static int check_common(const char* who, int64_t n_rays, int S, int J, int V, co
                         const float* rays_o, const float* rays_d, const float* z, const float* Rs,
                         const float* Ts, const float* vol, const float* bmin, const float* bscale) {
   if (n_rays < 0 || S <= 0) return fail_arg("%s: bad sizes (rays=%lld, samples=%d)", who, (long long)n_rays, S);
+  if (n_rays == 0) return 0;
   if (J <= 0 || J > kMaxJoints) return fail_arg("%s: n_joints=%d outside [1,%d]", who, J, kMaxJoints);
   if (V < 2 || V > 1024) return fail_arg("%s: vol_size=%d unsupported", who, V);
   if (!pts && (!rays_o || !rays_d || !z)) return fail_arg("%s: need pts or (rays_o, rays_d, z)", who);

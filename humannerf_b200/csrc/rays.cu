@@ -274,9 +274,9 @@ int hn_gen_rays(int H, int W, const double* K_host, const double* E_host, double
 
 int hn_rays_bbox(int64_t n_rays, const double* bounds_host, const double* rays_o, double* rays_d,
                  double* near, double* far, uint8_t* mask, void* stream) {
+  if (n_rays == 0) return 0;
   if (n_rays < 0 || !bounds_host || !rays_o || !rays_d || !near || !far || !mask)
     return fail_arg("hn_rays_bbox: bad argument");
-  if (n_rays == 0) return 0;
   BoundsF64 b;
   for (int a = 0; a < 3; ++a) {
     b.lo[a] = bounds_host[a] + (-0.01);
@@ -316,9 +316,9 @@ int hn_compact_rays(int64_t n_rays, const uint8_t* mask, const double* rays_o, c
 
 int hn_sample_z(int64_t n_rays, int n_samples, const float* near, const float* far,
                 const float* t_table, const float* t_rand, float* z, void* stream) {
+  if (n_rays == 0 && n_samples > 0) return 0;
   if (n_rays < 0 || n_samples <= 0 || !near || !far || !t_table || !z)
     return fail_arg("hn_sample_z: bad argument");
-  if (n_rays == 0) return 0;
   int64_t n = n_rays * n_samples;
   sample_z_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(
       n_rays, n_samples, near, far, t_table, t_rand, z);
@@ -327,8 +327,8 @@ int hn_sample_z(int64_t n_rays, int n_samples, const float* near, const float* f
 
 int hn_scatter_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* dst_index,
                     float* out, void* stream) {
+  if (n_rows == 0 && n_cols > 0) return 0;
   if (n_rows < 0 || n_cols <= 0 || !src || !dst_index || !out) return fail_arg("hn_scatter_rows: bad argument");
-  if (n_rows == 0) return 0;
   int64_t n = n_rows * n_cols;
   scatter_rows_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(n_rows, n_cols, src,
                                                                                          dst_index, out);
@@ -337,8 +337,8 @@ int hn_scatter_rows(int64_t n_rows, int n_cols, const float* src, const int64_t*
 
 int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* src_index,
                    float* out, void* stream) {
+  if (n_rows == 0 && n_cols > 0) return 0;
   if (n_rows < 0 || n_cols <= 0 || !src || !src_index || !out) return fail_arg("hn_gather_rows: bad argument");
-  if (n_rows == 0) return 0;
   int64_t n = n_rows * n_cols;
   gather_rows_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(n_rows, n_cols, src,
                                                                                         src_index, out);

@@ -24,8 +24,18 @@ echo "bench exit $rc"
 tail -c 3000 gpurun_out/bench.log
 tail -5 gpurun_out/bench.err
 if [ $rc -eq 0 ] && [ "${HN_NCU:-1}" = "1" ]; then
-  echo "== ncu launch list =="
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+  echo "== ncu launch list (bench) =="
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+  echo "ncu exit $?"
+  echo "== ncu full: tcgen05 field kernel =="
+  python scripts/profile_render.py --rays 32768 > gpurun_out/prof_plain_render.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:field_tc_kernel -s 1 -c 1 \
+      -o gpurun_out/prof_field_tc -f python scripts/profile_render.py --rays 32768 > gpurun_out/ncu_tc.log 2>&1
+  echo "ncu exit $?"
+  echo "== ncu full: motion field + sgemm (train) =="
+  python scripts/profile_render.py --rays 6144 --train > gpurun_out/prof_plain_train.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:motion_field|sgemm_kernel" -s 40 -c 12 \
+      -o gpurun_out/prof_train -f python scripts/profile_render.py --rays 6144 --train > gpurun_out/ncu_train.log 2>&1
   echo "ncu exit $?"
 fi
