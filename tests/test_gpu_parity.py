@@ -456,8 +456,8 @@ def test_network_eval_fp32(sd, frame):
     cfg.chunk = 7
     with torch.no_grad():
         out2 = net(**data, iter_val=cfg.eval_iter)
-    for k in KEYS:
-        assert torch.equal(out[k], out2[k]), k
+    for k in KEYS:      # (the cuDNN volume decoder is not bit-reproducible between calls, so no torch.equal here)
+        report('chunked ' + k, out2[k], out[k], 2e-6, 1e-5)
     # light-weight dict
     cfg.b200.heavy_outputs = False
     with torch.no_grad():
@@ -480,15 +480,66 @@ def test_network_train_fp32_with_grads(sd, frame):
     grads = {k: p.grad for k, p in net.named_parameters()}
     names = [str(n) for n in g['grad_names']]
     assert sorted(grads) == names
+    print('[parity] d(out bias) ours', grads['cnl_mlp.module.output_linear.0.bias'].cpu().numpy())
+    bad = []
     for n, ref_l2 in zip(names, g['grad_l2']):
         assert grads[n] is not None, n
         ours = float(grads[n].double().norm())
         rel = 2e-2 if n.startswith('pose_decoder') else 5e-3
-        print(f'[parity] grad L2 {n}: ours {ours:.6g} ref {ref_l2:.6g} rel {abs(ours - ref_l2) / max(ref_l2, 1e-12):.2e}')
-        assert abs(ours - ref_l2) <= rel * max(ref_l2, 1e-6) + 1e-7, (n, ours, ref_l2)
+        err = abs(ours - ref_l2) / max(ref_l2, 1e-12)
+        print(f'[parity] grad L2 {n}: ours {ours:.6g} ref {ref_l2:.6g} rel {err:.2e}')
+        if abs(ours - ref_l2) > rel * max(ref_l2, 1e-6) + 1e-7:
+            bad.append((n, ours, float(ref_l2)))
     for key in g.files:
         if key.startswith('grad/'):
-            rel_max(key, grads[key[5:]], g[key], 2e-2 if 'pose_decoder' in key else 5e-3)
+            try:
+                rel_max(key, grads[key[5:]], g[key], 2e-2 if 'pose_decoder' in key else 5e-3)
+            except AssertionError as e:
+                bad.append((key, str(e)))
+    assert not bad, bad
+
+
+def test_composite_backward_on_network_tensors(ops, sd, frame):
+    """Compositing backward on the tensors the network actually produces (zeros in the mask, large
+    densities, the 1e10 last interval), upstream gradient = the e2e test loss."""
+    g = gold('network_e2e.npz')
+    st = gold('stages.npz')
+    fr = {k: T(v) for k, v in frame.items()}
+    fr['bgcolor'] = T(g['bgcolor'])
+    with torch.no_grad():
+        tr = orc.network_forward(sd, T(st['rays']), T(st['near']), T(st['far']), fr, torch.full((1,), 30000),
+                                 t_rand=T(st['t_rand']), return_intermediates=True)
+    raw0, mask0, z, xyz = tr['raw'], tr['mask'], tr['z_vals'], tr['xyz_on_rays']
+    d = T(st['rays'])[1].float()
+    lw = T(g['train_loss_w'])
+    raw, mask = raw0.clone().requires_grad_(), mask0.clone().requires_grad_()
+    o = orc.composite(raw, mask, z, d, xyz, fr['bgcolor'])
+    ((o['rgb'] * lw).sum() + 0.3 * o['alpha'].sum() + 0.1 * o['depth'].sum()).backward()
+    rc, mc = raw0.to(DEV).requires_grad_(), mask0.to(DEV).requires_grad_()
+    out = ops.composite(rc, mc, z.to(DEV), d.to(DEV), xyz.to(DEV), fr['bgcolor'].to(DEV))
+    ((out[0] * lw.to(DEV)).sum() + 0.3 * out[1].sum() + 0.1 * out[2].sum()).backward()
+    print('[parity] sum d_raw per channel: ours', rc.grad.sum((0, 1)).cpu().numpy(), 'oracle', raw.grad.sum((0, 1)).numpy())
+    report('composite(e2e).d_raw', rc.grad, raw.grad, 1e-6, 1e-3)
+    report('composite(e2e).d_mask', mc.grad, mask.grad, 1e-6, 1e-3)
+    # and the canonical-field backward driven by exactly this d_raw
+    xs = tr['x_skel'].reshape(-1, 3)
+    cond, hann = fr['dst_posevec'], orc.hann_weights(30000, 6, 10000, 50000)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(('cnl_mlp', 'non_rigid'))}
+    x = xs.clone().requires_grad_()
+    raw_o, xyz_o, off_o = _field_oracle(sdo, x, cond, hann)
+    (raw_o * raw.grad.reshape(-1, 4)).sum().backward()
+    w = _field_weights(sd, DEV, requires_grad=True)
+    xc = xs.to(DEV).requires_grad_()
+    rawc, xyzc, offc = ops.canonical_field(ops.FieldSpec(), xc, cond.to(DEV), hann.to(DEV), *w)
+    (rawc * raw.grad.reshape(-1, 4).to(DEV)).sum().backward()
+    flat_names = ([f'non_rigid_mlp.module.block_mlps.{i}.weight' for i in range(0, 13, 2)]
+                  + [f'non_rigid_mlp.module.block_mlps.{i}.bias' for i in range(0, 13, 2)]
+                  + [f'cnl_mlp.module.pts_linears.{i}.weight' for i in range(0, 15, 2)] + ['cnl_mlp.module.output_linear.0.weight']
+                  + [f'cnl_mlp.module.pts_linears.{i}.bias' for i in range(0, 15, 2)] + ['cnl_mlp.module.output_linear.0.bias'])
+    flat = w[0] + w[1] + w[2] + w[3]
+    for n, p in zip(flat_names, flat):
+        rel_max(f'field32(e2e d_raw).grad {n}', p.grad, sdo[n].grad, 2e-3)
+    rel_max('field32(e2e d_raw).d_x', xc.grad, x.grad, 2e-3)
 
 
 def test_network_eval_bf16(sd, frame):
