@@ -361,12 +361,14 @@ class _Composite(torch.autograd.Function):
         raw, mask, z, rays_d, bgcolor = ctx.saved_tensors
         R, S = z.shape
         dev = raw.device
-        c = lambda g: _f32c(g) if g is not None else None
+        # the contiguous copies must stay referenced until the launch: a temporary freed inside the
+        # argument list hands its block straight to the next temporary (g_acc and g_depth would alias)
+        g_rgb, g_acc, g_depth, g_w = [(_f32c(g) if g is not None else None) for g in (g_rgb, g_acc, g_depth, g_w)]
         d_raw = torch.empty(R, S, 4, dtype=torch.float32, device=dev)
         d_mask = torch.empty(R, S, 1, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev), _timed('composite_bwd'):
-            check(lib.hn_composite_bwd(R, S, ptr(raw), ptr(mask), ptr(z), ptr(rays_d), ptr(bgcolor), ptr(c(g_rgb)),
-                                       ptr(c(g_acc)), ptr(c(g_depth)), ptr(c(g_w)), ptr(d_raw), ptr(d_mask),
+            check(lib.hn_composite_bwd(R, S, ptr(raw), ptr(mask), ptr(z), ptr(rays_d), ptr(bgcolor), ptr(g_rgb),
+                                       ptr(g_acc), ptr(g_depth), ptr(g_w), ptr(d_raw), ptr(d_mask),
                                        stream_ptr()), 'composite_bwd')
         return d_raw, d_mask, None, None, None, None, None
 

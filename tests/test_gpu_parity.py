@@ -457,7 +457,7 @@ def test_network_eval_fp32(sd, frame):
     with torch.no_grad():
         out2 = net(**data, iter_val=cfg.eval_iter)
     for k in KEYS:      # (the cuDNN volume decoder is not bit-reproducible between calls, so no torch.equal here)
-        report('chunked ' + k, out2[k], out[k], 2e-6, 1e-5)
+        report('chunked ' + k, out2[k], out[k], 2e-5, 1e-4)
     # light-weight dict
     cfg.b200.heavy_outputs = False
     with torch.no_grad():
