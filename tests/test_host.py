@@ -58,9 +58,10 @@ def test_field_plan_sizes():
     # non-rigid 108+128*3+164+128*2+4, canonical 64+256*4+320+256*3+4 floats per sample
     assert per_sample == 1000 * 4 * ((108 + 128 * 3 + 164 + 128 * 2 + 4) + (64 + 256 * 4 + 320 + 256 * 3 + 4))
     packed = lib.hn_field_packed_bytes(ctypes.byref(fp))
-    # bf16 image: non-rigid (48*128 + 3*128*128 + 176*128 + 128*128 + 128*16) + canonical
-    # (64*256 + 4*256*256 + 320*256 + 2*256*256 + 256*16) elements, plus tables
-    elems = (48 * 128 + 3 * 128 * 128 + 176 * 128 + 128 * 128 + 128 * 16) + (64 * 256 + 4 * 256 * 256 + 320 * 256 + 2 * 256 * 256 + 256 * 16)
+    # bf16 image (hidden layers carry one extra 16-row K step for the folded bias):
+    nr = 48 * 128 + 3 * (128 + 16) * 128 + (128 + 48) * 128 + (128 + 16) * 128 + (128 + 16) * 16
+    cn = 64 * 256 + 4 * (256 + 16) * 256 + (64 + 256) * 256 + 2 * (256 + 16) * 256 + (256 + 16) * 16
+    elems = nr + cn
     assert 2 * elems < packed < 2 * elems + 64 * 1024
 
 
