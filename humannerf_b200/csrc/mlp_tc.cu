@@ -14,8 +14,11 @@
 //   * the B operand (weights) is pre-tiled by hn_field_pack_bf16 into exactly the shared-memory
 //     image the MMA wants and streamed with 1-D TMA bulk copies (cp.async.bulk + mbarrier
 //     complete_tx) through a 4 x 16 KB ring - no tensor maps;
-//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue
-//     (two warps per TMEM lane quarter and tile, each owning half of the columns).
+//   * warp roles: warp 0 = TMA producer, warps 1 and 18 = MMA issuers (one per tile: a single thread
+//     issues ~1 MMA per 130 cycles, slower than the 128-cycle MMA itself), warps 2..17 = epilogue
+//     (two warps per TMEM lane quarter and tile, each owning half of the columns);
+//   * the two tiles have their own accumulator-full / operand-ready barriers, so they drift apart by
+//     up to the depth of the weight ring and one tile's epilogue overlaps the other tile's MMAs.
 //
 // Reference semantics: embedders/hannw_fourier.py:38-49, embedders/fourier.py:9-38,
 // non_rigid_motion_mlps/mlp_offset.py:74-114, canonical_mlps/mlp_rgb_sigma.py:132-206.
@@ -43,7 +46,8 @@ constexpr uint32_t kTableOff = kBarOff + 128;
 constexpr uint32_t kSmemTotal = kTableOff + kMaxChunks * 16;
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kThreads = (3 + kEpiWarps) * 32;   // producer, 2 MMA issuers (one per tile), epilogue
+constexpr int kMmaWarp0 = 1, kMmaWarp1 = 2 + kEpiWarps;
 constexpr uint32_t kMagic = 0x484e5432u;                // "HNT2"
 constexpr int kMaxTcLayers = 2 * HN_MAX_LAYERS;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
@@ -124,10 +128,11 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
   const uint32_t s_ring = s_base + kRingOff;
   const uint32_t s_full = s_base + kBarOff;                  // kStages x 8 B
   const uint32_t s_empty = s_full + kStages * 8;             // kStages x 8 B
-  const uint32_t s_acc_full = s_empty + kStages * 8;         // 8 B
-  const uint32_t s_a_ready = s_acc_full + 8;                 // 8 B
-  const uint32_t s_tmem_slot = s_a_ready + 8;                // 4 B
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + (2 * kStages + 2) * 8);
+  const uint32_t s_acc_full = s_empty + kStages * 8;         // kTiles x 8 B
+  const uint32_t s_a_ready = s_acc_full + kTiles * 8;        // kTiles x 8 B
+  const uint32_t s_tmem_slot = s_a_ready + kTiles * 8;       // 4 B
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem + kBarOff + (2 * kStages + 2 * kTiles) * 8);
   const TcChunk* table = reinterpret_cast<const TcChunk*>(smem + kTableOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,10 +151,12 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(s_full + s * 8, 1);
-      mbar_init(s_empty + s * 8, 1);
+      mbar_init(s_empty + s * 8, kTiles);          // one tcgen05.commit per MMA issuer
     }
-    mbar_init(s_acc_full, 1);
-    mbar_init(s_a_ready, kEpiWarps * 32);
+    for (int t = 0; t < kTiles; ++t) {
+      mbar_init(s_acc_full + t * 8, 1);
+      mbar_init(s_a_ready + t * 8, (kEpiWarps / kTiles) * 32);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -185,40 +192,44 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
+    // ===================== MMA issuers: warp 1 drives tile 0, warp 18 drives tile 1 =====================
     if (lane == 0) {
+      const uint32_t t = (warp == kMmaWarp0) ? 0u : 1u;
+      const uint32_t d_tmem = tmem_base + t * 256u;
+      const uint32_t bar_ready = s_a_ready + t * 8, bar_acc = s_acc_full + t * 8;
+      // descriptor halves: hi = SBO (128 B >> 4) | version 1 (bit 46 -> bit 14 of hi); lo = addr >> 4 | LBO >> 4 << 16
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_const = ((kLboA >> 4) << 16);
       uint32_t stage = 0, phase = 0, a_phase = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (uint32_t c = first_chunk; c < n_chunks; ++c) {
           const TcChunk ch = table[c];
           if (ch.flags & 1) {
-            // A operands of this layer are complete (and the previous accumulators drained)
-            mbar_wait(s_a_ready, a_phase, 2);
+            // the A operand of this layer is complete (and the previous accumulator drained)
+            mbar_wait(bar_ready, a_phase, 2);
             a_phase ^= 1;
             tc_fence_after();
           }
           mbar_wait(s_full + stage * 8, phase, 3);
           tc_fence_after();
           const uint32_t idesc = make_idesc(ch.n);
-          const uint32_t b_lbo = (uint32_t)ch.n * 16u;
-          const uint32_t b_base = s_ring + stage * kStageBytes;
           const bool in_pe = (ch.flags & 4) != 0;
-          const uint32_t a_base0 = (in_pe ? s_act_pe : s_base) + ch.a_off;
-          const uint32_t a_tile = in_pe ? kActPeTile : kActHTile;
-#pragma unroll
-          for (int t = 0; t < kTiles; ++t) {
-            const uint32_t a_base = a_base0 + (uint32_t)t * a_tile;
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-#pragma unroll 1
-            for (uint32_t k = 0; k < ch.ksteps; ++k) {
-              const uint64_t a_desc = make_desc(a_base + k * 2u * kLboA, kLboA, 128u);
-              const uint64_t b_desc = make_desc(b_base + k * 2u * b_lbo, b_lbo, 128u);
-              umma_bf16(d_tmem, a_desc, b_desc, idesc, ((ch.flags & 1) && k == 0) ? 0u : 1u);
-            }
+          const uint32_t a_addr = (in_pe ? s_act_pe + t * kActPeTile : s_base + t * kActHTile) + ch.a_off;
+          const uint32_t b_addr = s_ring + stage * kStageBytes;
+          uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | a_lo_const;
+          uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | ((uint32_t)ch.n << 16);      // LBO = n*16 bytes -> n
+          const uint32_t a_inc = (2u * kLboA) >> 4, b_inc = 2u * (uint32_t)ch.n;     // one K step = two core matrices
+          uint32_t acc = (ch.flags & 1) ? 0u : 1u;
+#pragma unroll 2
+          for (uint32_t k = 0; k < ch.ksteps; ++k) {
+            umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+            acc = 1u;
+            a_lo += a_inc;
+            b_lo += b_inc;
           }
-          umma_commit(s_empty + stage * 8);            // frees the ring slot when these MMAs retire
-          if (ch.flags & 2) umma_commit(s_acc_full);   // accumulators of the layer are complete
+          umma_commit(s_empty + stage * 8);            // ring slot is free once both issuers' MMAs retire
+          if (ch.flags & 2) umma_commit(bar_acc);      // accumulator of the layer is complete
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -233,6 +244,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
     const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)tile * 256u;
     const uint32_t a_h = s_base + (uint32_t)tile * kActHTile;
     const uint32_t a_pe = s_act_pe + (uint32_t)tile * kActPeTile;
+    const uint32_t bar_ready = s_a_ready + (uint32_t)tile * 8, bar_acc = s_acc_full + (uint32_t)tile * 8;
     uint32_t acc_phase = 0;
     float hw[10];
 #pragma unroll
@@ -250,7 +262,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
       if (!ignore_non_rigid) {
         write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad);
         fence_proxy_async();
-        mbar_arrive(s_a_ready);
+        mbar_arrive(bar_ready);
       }
 
       for (int layer = first_layer; layer < n_layers; ++layer) {
@@ -259,9 +271,9 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
         if (layer == nr_layers) {
           write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad);
           fence_proxy_async();
-          mbar_arrive(s_a_ready);
+          mbar_arrive(bar_ready);
         }
-        mbar_wait(s_acc_full, acc_phase, 4);
+        mbar_wait(bar_acc, acc_phase, 4);
         acc_phase ^= 1;
         tc_fence_after();
         if (!is_out) {
@@ -299,7 +311,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
           }
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(s_a_ready);
+          mbar_arrive(bar_ready);
         } else {
           uint32_t v[16];
           tmem_ld16(t_acc, v);
