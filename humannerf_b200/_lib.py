@@ -34,6 +34,12 @@ class FieldParams(C.Structure):
                 ('cn_w', _p * HN_MAX_LAYERS), ('cn_b', _p * HN_MAX_LAYERS)]
 
 
+class WgradJob(C.Structure):
+    _fields_ = [('dz', _p), ('x', _p), ('dw', _p), ('db', _p), ('f_dz', C.c_int32), ('f_x', C.c_int32),
+                ('m', C.c_int32), ('x_f0', C.c_int32), ('n', C.c_int32), ('n_valid', C.c_int32),
+                ('dw_ld', C.c_int32), ('dw_col0', C.c_int32), ('bias_col', C.c_int32), ('reserved', C.c_int32)]
+
+
 class FieldGrads(C.Structure):
     _fields_ = [('nr_w', _p * HN_MAX_LAYERS), ('nr_b', _p * HN_MAX_LAYERS),
                 ('cn_w', _p * HN_MAX_LAYERS), ('cn_b', _p * HN_MAX_LAYERS)]
@@ -61,6 +67,10 @@ SIGNATURES = {
     'hn_field_pack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
     'hn_composite_fwd': (_int, [_i64, _int] + [_p] * 15),
     'hn_composite_bwd': (_int, [_i64, _int] + [_p] * 12),
+    'hn_tile_image_bytes': (_i64, [_i64, _int]),
+    'hn_tile_pack': (_int, [_i64, _int, _int, _p, _i64, _p, _p]),
+    'hn_tile_unpack': (_int, [_i64, _int, _int, _p, _p, _i64, _p]),
+    'hn_tile_wgrad': (_int, [C.POINTER(WgradJob), _int, _i64, _p, _p]),
     'hn_scatter_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
     'hn_gather_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
 }

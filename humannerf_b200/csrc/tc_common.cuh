@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // Bounded wait: a protocol bug traps with a message instead of hanging the GPU (no legitimate
 // wait in this kernel lasts anywhere near a second).
 constexpr long long kWatchdogCycles = 4000000000LL;
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int who) {
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int who) {
   printf("humannerf_b200 tcgen05 kernel: mbarrier wait timed out (block %d thread %d role %d bar 0x%x parity %u)\n",
          (int)blockIdx.x, (int)threadIdx.x, who, bar, parity);
   __trap();

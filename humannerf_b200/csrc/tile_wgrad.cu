@@ -1,0 +1,285 @@
+// Weight gradients on the tensor cores: dW[n_out][k_in] += sum_samples dZ[s][n_out] * X[s][k_in]
+// with both operands read from "T16 tile images" in HBM (bf16), the layout the tcgen05 forward /
+// backward-data kernels write their activations and pre-activation gradients in:
+//
+//   image(X)[s][f] at  (s/128) * 128*F*2  +  ((s%128)/16) * 16*F*2  +  (f/8) * 256  +  (s%16) * 16  +  (f%8) * 2
+//
+// i.e. per 16 samples and 8 features one 256-byte block of 16 rows x 16 bytes.  A block of 16 samples
+// with all F features is contiguous (F*32 bytes), so a pipeline stage of 64 samples is one or a few
+// 1-D TMA bulk copies, and the same bytes are a valid UMMA *MN-major* no-swizzle operand for a K = 16
+// step (K = samples): 8 K rows of 16 bytes per core matrix, LBO (next 8 samples) = 128 B, SBO (next
+// 8 features) = 256 B.  D = dZ^T X accumulates in TMEM over a slab of samples; the epilogue adds it
+// into the fp32 gradient with atomics (split over samples across CTAs).
+//
+// Replaces the autograd of nn.Linear in reference non_rigid_motion_mlps/mlp_offset.py:74-84 and
+// canonical_mlps/mlp_rgb_sigma.py:163-166,198 on the bf16 path.
+#include <algorithm>
+#include <vector>
+
+#include "tc_common.cuh"
+#include "tiles.cuh"
+
+namespace hn {
+
+constexpr int kWgStages = 3;
+constexpr int kWgStageSamples = 64;
+constexpr uint32_t kWgOperandBytes = 256 * kWgStageSamples * 2;       // 32 KB: up to 256 features x 64 samples
+constexpr uint32_t kWgStageBytes = 2 * kWgOperandBytes;               // A (dZ) + B (X)
+constexpr uint32_t kWgBarOff = kWgStages * kWgStageBytes;
+constexpr uint32_t kWgSmem = kWgBarOff + 128;
+constexpr int kWgThreads = 6 * 32;                                    // producer, MMA, 4 epilogue warps
+
+// MN-major for both operands: bits 15 / 16 of the instruction descriptor
+__device__ __forceinline__ uint32_t make_idesc_mn(uint32_t n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+tile_wgrad_kernel(const WgradJob* __restrict__ jobs, int n_jobs, int n_tiles, int tiles_per_slab) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_full = s_base + kWgBarOff;
+  const uint32_t s_empty = s_full + kWgStages * 8;
+  const uint32_t s_acc = s_empty + kWgStages * 8;
+  const uint32_t s_drained = s_acc + 8;
+  const uint32_t s_tmem_slot = s_drained + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWgBarOff + (2 * kWgStages + 2) * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
+  const int n_items = n_jobs * n_slabs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(s_full + s * 8, 1);
+      mbar_init(s_empty + s * 8, 1);
+    }
+    mbar_init(s_acc, 1);
+    mbar_init(s_drained, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s_tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WgradJob job = jobs[item / n_slabs];
+        const int t0 = (item % n_slabs) * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        const uint32_t a_blk = (uint32_t)job.f_dz * 32u;       // bytes per 16-sample block of the dZ image
+        const uint32_t x_blk = (uint32_t)job.f_x * 32u;
+        const uint32_t b_blk = (uint32_t)job.n * 32u;          // bytes of the X window per 16-sample block
+        const bool x_whole = (job.x_f0 == 0 && job.n == job.f_x);
+        for (int t = t0; t < t1; ++t) {
+          const uint8_t* a_src = static_cast<const uint8_t*>(job.dz) + (size_t)t * 128 * job.f_dz * 2;
+          const uint8_t* x_src = static_cast<const uint8_t*>(job.x) + (size_t)t * 128 * job.f_x * 2 + (size_t)(job.x_f0 / 8) * 256;
+          for (int q = 0; q < 128 / kWgStageSamples; ++q) {
+            const uint32_t a_dst = s_base + stage * kWgStageBytes, b_dst = a_dst + kWgOperandBytes;
+            mbar_wait(s_empty + stage * 8, phase ^ 1, 1);
+            mbar_expect_tx(s_full + stage * 8, 4u * (a_blk + b_blk));
+            tma_bulk_g2s(a_dst, a_src + (size_t)q * 4 * a_blk, 4u * a_blk, s_full + stage * 8);
+            if (x_whole) {
+              tma_bulk_g2s(b_dst, x_src + (size_t)q * 4 * x_blk, 4u * b_blk, s_full + stage * 8);
+            } else {
+              for (int kb = 0; kb < 4; ++kb)
+                tma_bulk_g2s(b_dst + kb * b_blk, x_src + (size_t)(q * 4 + kb) * x_blk, b_blk, s_full + stage * 8);
+            }
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, drained_phase = 0;
+      const uint32_t desc_hi = (256u >> 4) | (1u << 14);      // SBO = 256 B (next 8 features), version 1
+      const uint32_t lo_const = ((128u >> 4) << 16);          // LBO = 128 B (next 8 samples)
+      bool first_item = true;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WgradJob job = jobs[item / n_slabs];
+        const int t0 = (item % n_slabs) * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        const int m_tiles = (job.m + 127) / 128;
+        const uint32_t idesc = make_idesc_mn((uint32_t)job.n);
+        const uint32_t a_blk = (uint32_t)job.f_dz * 32u, b_blk = (uint32_t)job.n * 32u;
+        if (!first_item) {
+          // the epilogue must have drained the previous item's accumulators
+          mbar_wait(s_drained, drained_phase, 2);
+          drained_phase ^= 1;
+          tc_fence_after();
+        }
+        first_item = false;
+        uint32_t acc = 0;
+        for (int t = t0; t < t1; ++t) {
+          for (int q = 0; q < 128 / kWgStageSamples; ++q) {
+            mbar_wait(s_full + stage * 8, phase, 3);
+            tc_fence_after();
+            const uint32_t a_addr = s_base + stage * kWgStageBytes, b_addr = a_addr + kWgOperandBytes;
+#pragma unroll 1
+            for (uint32_t kb = 0; kb < 4; ++kb) {
+              const uint32_t b_lo = (((b_addr + kb * b_blk) & 0x3FFFFu) >> 4) | lo_const;
+              for (int mt = 0; mt < m_tiles; ++mt) {
+                const uint32_t a_lo = (((a_addr + kb * a_blk + (uint32_t)mt * 16u * 256u) & 0x3FFFFu) >> 4) | lo_const;
+                umma_bf16(tmem_base + (uint32_t)mt * 256u, ((uint64_t)desc_hi << 32) | a_lo,
+                          ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+              }
+              acc = 1u;
+            }
+            umma_commit(s_empty + stage * 8);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(s_acc);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5): TMEM -> fp32 atomics =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const WgradJob job = jobs[item / n_slabs];
+      const int m_tiles = (job.m + 127) / 128;
+      mbar_wait(s_acc, acc_phase, 4);
+      acc_phase ^= 1;
+      tc_fence_after();
+      for (int mt = 0; mt < m_tiles; ++mt) {
+        const int r = mt * 128 + row;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)mt * 256u;
+        for (int c0 = 0; c0 < job.n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (r < job.m) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              const float val = __uint_as_float(v[j]);
+              if (c < job.n_valid) atomicAdd(job.dw + (int64_t)r * job.dw_ld + job.dw_col0 + c, val);
+              else if (c == job.bias_col && job.db) atomicAdd(job.db + r, val);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_drained);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 row-major <-> T16 tile image (tests, and the d_raw / d_xyz entry of the backward chain)
+// ------------------------------------------------------------------------------------------
+__global__ void tile_pack_kernel(int64_t n_samples, int n_feat, int f_pad, const float* __restrict__ src,
+                                 int64_t ld, uint8_t* __restrict__ image) {
+  const int64_t n_tiles = (n_samples + 127) / 128;
+  const int64_t units = n_tiles * 128 * (f_pad / 8);
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(u % (f_pad / 8));
+    const int64_t s = u / (f_pad / 8);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = g * 8 + i;
+      f[i] = (s < n_samples && c < n_feat) ? src[s * ld + c] : 0.0f;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(image + tile_offset(s, g * 8, f_pad)) = o;
+  }
+}
+
+__global__ void tile_unpack_kernel(int64_t n_samples, int n_feat, int f_pad, const uint8_t* __restrict__ image,
+                                   float* __restrict__ dst, int64_t ld) {
+  const int64_t total = n_samples * n_feat;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / n_feat;
+    const int c = (int)(i - s * n_feat);
+    const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(image + tile_offset(s, c, f_pad));
+    dst[s * ld + c] = __bfloat162float(v);
+  }
+}
+
+int launch_tile_wgrad(const WgradJob* jobs_dev, int n_jobs, int64_t n_samples, cudaStream_t st) {
+  if (n_jobs <= 0 || n_samples <= 0) return 0;
+  int dev = 0, sms = 0;
+  HN_TRY(check_cuda(cudaGetDevice(&dev), "tile_wgrad/device"));
+  HN_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "tile_wgrad/attr"));
+  HN_TRY(check_cuda(cudaFuncSetAttribute(tile_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kWgSmem), "tile_wgrad/smem attr"));
+  const int n_tiles = (int)ceil_div<int64_t>(n_samples, 128);
+  // ~3 work items per SM: enough to balance, few enough to keep the atomic traffic small
+  int n_slabs = std::max(1, std::min(n_tiles, (3 * sms + n_jobs - 1) / n_jobs));
+  const int tiles_per_slab = (n_tiles + n_slabs - 1) / n_slabs;
+  n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
+  const int grid = std::min(n_jobs * n_slabs, sms);
+  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(jobs_dev, n_jobs, n_tiles, tiles_per_slab);
+  return launched("tile_wgrad");
+}
+
+static int check_job(const hn_wgrad_job& j) {
+  if (!j.dz || !j.x || !j.dw) return fail_arg("hn_tile_wgrad: null pointer in job");
+  if (j.f_dz % 16 || j.f_dz < 16 || j.f_dz > 256) return fail_arg("hn_tile_wgrad: f_dz=%d must be a multiple of 16 in [16,256]", j.f_dz);
+  if (j.f_x % 16 || j.f_x < 16 || j.f_x > 256) return fail_arg("hn_tile_wgrad: f_x=%d must be a multiple of 16 in [16,256]", j.f_x);
+  if (j.n % 16 || j.n < 16 || j.n > 256 || j.x_f0 % 8 || j.x_f0 + j.n > j.f_x)
+    return fail_arg("hn_tile_wgrad: bad X window (x_f0=%d, n=%d, f_x=%d)", j.x_f0, j.n, j.f_x);
+  if (j.m < 1 || j.m > j.f_dz || j.n_valid < 0 || j.n_valid > j.n) return fail_arg("hn_tile_wgrad: bad m / n_valid");
+  return 0;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" {
+
+int64_t hn_tile_image_bytes(int64_t n_samples, int n_features_padded) {
+  if (n_samples < 0 || n_features_padded <= 0 || n_features_padded % 8) return -1;
+  return ceil_div<int64_t>(n_samples, 128) * 128 * n_features_padded * 2;
+}
+
+int hn_tile_pack(int64_t n_samples, int n_features, int n_features_padded, const float* src, int64_t ld,
+                 void* image, void* stream) {
+  if (n_samples == 0) return 0;
+  if (n_samples < 0 || n_features <= 0 || n_features_padded % 8 || n_features > n_features_padded || !src || !image)
+    return fail_arg("hn_tile_pack: bad argument");
+  tile_pack_kernel<<<1024, 256, 0, as_stream(stream)>>>(n_samples, n_features, n_features_padded, src, ld,
+                                                        static_cast<uint8_t*>(image));
+  return launched("hn_tile_pack");
+}
+
+int hn_tile_unpack(int64_t n_samples, int n_features, int n_features_padded, const void* image, float* dst,
+                   int64_t ld, void* stream) {
+  if (n_samples == 0) return 0;
+  if (n_samples < 0 || n_features <= 0 || n_features_padded % 8 || n_features > n_features_padded || !dst || !image)
+    return fail_arg("hn_tile_unpack: bad argument");
+  tile_unpack_kernel<<<1024, 256, 0, as_stream(stream)>>>(n_samples, n_features, n_features_padded,
+                                                          static_cast<const uint8_t*>(image), dst, ld);
+  return launched("hn_tile_unpack");
+}
+
+int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, void* jobs_scratch_dev,
+                  void* stream) {
+  if (n_jobs == 0 || n_samples == 0) return 0;
+  if (n_jobs < 0 || n_samples < 0 || !jobs_host || !jobs_scratch_dev) return fail_arg("hn_tile_wgrad: bad argument");
+  static_assert(sizeof(hn_wgrad_job) == sizeof(WgradJob), "job layouts must agree");
+  for (int i = 0; i < n_jobs; ++i) HN_TRY(check_job(jobs_host[i]));
+  cudaStream_t st = as_stream(stream);
+  HN_TRY(check_cuda(cudaMemcpyAsync(jobs_scratch_dev, jobs_host, (size_t)n_jobs * sizeof(hn_wgrad_job),
+                                    cudaMemcpyHostToDevice, st), "hn_tile_wgrad/jobs"));
+  return launch_tile_wgrad(static_cast<const WgradJob*>(jobs_scratch_dev), n_jobs, n_samples, st);
+}
+
+}  // extern "C"

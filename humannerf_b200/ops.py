@@ -411,3 +411,47 @@ class _ScatterRows(torch.autograd.Function):
 def scatter_rows(src: torch.Tensor, index: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
     """Copy of `base` (..., C) with row index[r] of its flattened (N, C) view replaced by src[r]."""
     return _ScatterRows.apply(_f32c(src), index.to(torch.int64).contiguous(), _f32c(base))
+
+
+# ---------------------------------------------------------------------------
+# T16 tile images and tensor-core weight gradients (building blocks of the bf16 training path)
+# ---------------------------------------------------------------------------
+def tile_image_bytes(n_samples: int, f_pad: int) -> int:
+    return int(_lib.load().hn_tile_image_bytes(n_samples, f_pad))
+
+
+def tile_pack(x: torch.Tensor, f_pad: int) -> torch.Tensor:
+    """fp32 (P, F) -> bf16 T16 tile image (uint8 tensor) with f_pad >= F features per sample."""
+    lib = _lib.load()
+    x = _f32c(x)
+    P, F = x.shape
+    img = torch.empty(tile_image_bytes(P, f_pad), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.hn_tile_pack(P, F, f_pad, ptr(x), F, ptr(img), stream_ptr()), 'tile_pack')
+    return img
+
+
+def tile_unpack(img: torch.Tensor, n_samples: int, n_features: int, f_pad: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(n_samples, n_features, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        check(lib.hn_tile_unpack(n_samples, n_features, f_pad, ptr(img), ptr(out), n_features, stream_ptr()),
+              'tile_unpack')
+    return out
+
+
+def tile_wgrad(jobs: Sequence[dict], n_samples: int) -> None:
+    """Run weight-gradient jobs (dicts with the fields of `_lib.WgradJob`; tensors for dz, x, dw, db)."""
+    lib = _lib.load()
+    arr = (_lib.WgradJob * len(jobs))()
+    dev = None
+    for a, j in zip(arr, jobs):
+        dev = j['dw'].device
+        a.dz, a.x, a.dw = ptr(j['dz']), ptr(j['x']), ptr(j['dw'])
+        a.db = ptr(j.get('db'))
+        for k in ('f_dz', 'f_x', 'm', 'x_f0', 'n', 'n_valid', 'dw_ld', 'dw_col0'):
+            setattr(a, k, int(j[k]))
+        a.bias_col = int(j.get('bias_col', -1))
+    scratch = torch.empty(len(jobs) * C.sizeof(_lib.WgradJob), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _timed('tile_wgrad'):
+        check(lib.hn_tile_wgrad(arr, len(jobs), n_samples, ptr(scratch), stream_ptr()), 'tile_wgrad')

@@ -195,6 +195,44 @@ int hn_scatter_rows(int64_t n_rows, int n_cols, const float* src, const int64_t*
 int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* src_index,
                    float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * T16 tile images (bf16) and tensor-core weight gradients
+ *
+ * The tcgen05 kernels keep activations H and pre-activation gradients dZ in HBM as "T16 tile
+ * images": element (sample s, feature f) of a (P x F) matrix, F a multiple of 8, lives at byte
+ *   (s/128)*128*F*2 + ((s%128)/16)*16*F*2 + (f/8)*256 + (s%16)*16 + (f%8)*2
+ * (per 16 samples x 8 features one 256-byte block; 16 samples x all features are contiguous).
+ * hn_tile_pack / hn_tile_unpack convert from / to fp32 row-major.
+ *
+ * hn_tile_wgrad runs a list of jobs  dW[0:m, col0:col0+n_valid] += dZ[:, 0:m]^T X[:, x_f0:x_f0+n]
+ * (nn.Linear weight gradients, reference mlp_offset.py:74-84, mlp_rgb_sigma.py:163-166,198) on the
+ * tensor cores; column `bias_col` of the X window (the constant-1 column of the encoding block)
+ * can be routed to a bias gradient db[0:m].  dW / db are accumulated with fp32 atomics.
+ */
+typedef struct hn_wgrad_job {
+  const void* dz;      /* tile image of dZ, f_dz features per sample */
+  const void* x;       /* tile image of the layer input, f_x features per sample */
+  float* dw;           /* (m, dw_ld) fp32, accumulated */
+  float* db;           /* nullable, (m) fp32, accumulated */
+  int32_t f_dz, f_x;   /* multiples of 16 in [16,256] */
+  int32_t m;           /* rows of dW = leading features of dZ used (<= f_dz) */
+  int32_t x_f0;        /* first feature of the X window (multiple of 8) */
+  int32_t n;           /* width of the X window = MMA N (multiple of 16, <= 256) */
+  int32_t n_valid;     /* columns of the window written to dW */
+  int32_t dw_ld, dw_col0;
+  int32_t bias_col;    /* window column routed to db, or -1 */
+  int32_t reserved;
+} hn_wgrad_job;
+
+int64_t hn_tile_image_bytes(int64_t n_samples, int n_features_padded);
+int hn_tile_pack(int64_t n_samples, int n_features, int n_features_padded, const float* src, int64_t ld,
+                 void* image, void* stream);
+int hn_tile_unpack(int64_t n_samples, int n_features, int n_features_padded, const void* image, float* dst,
+                   int64_t ld, void* stream);
+/* jobs_host: host array; jobs_scratch_dev: device scratch of n_jobs * sizeof(hn_wgrad_job) bytes. */
+int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, void* jobs_scratch_dev,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
