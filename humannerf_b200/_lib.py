@@ -63,6 +63,9 @@ SIGNATURES = {
     'hn_field_bwd_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),
     'hn_field_bwd': (_int, [C.POINTER(FieldParams), C.POINTER(FieldGrads), _i64, _p, _p, _p, _int, _p, _p, _p, _p,
                             _p, _i64, _p, _i64, _p]),
+    'hn_field_bwd_bf16_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),
+    'hn_field_bwd_bf16': (_int, [C.POINTER(FieldParams), C.POINTER(FieldGrads), _i64, _p, _p, _p, _p, _int, _p, _p, _p,
+                                 _p, _p, _i64, _p, _p, _i64, _p]),
     'hn_field_packed_bytes': (_i64, [C.POINTER(FieldParams)]),
     'hn_field_pack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
     'hn_composite_fwd': (_int, [_i64, _int] + [_p] * 15),

@@ -18,6 +18,8 @@ namespace hn {
 
 static inline int pad4(int v) { return (v + 3) & ~3; }
 
+int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples);   // mlp_tc.cu
+
 // ---------------------------------------------------------------------------------------
 // positional encodings
 // out[:, col0 + ...] = [x (if include_input), w_k sin(2^k x), w_k cos(2^k x)]_k ; per k the
@@ -139,7 +141,7 @@ static int pe_fwd(int64_t n, const float* x, int64_t ldx, int nf, const float* f
   });
 }
 
-static int pe_bwd(int64_t n, const float* x, int64_t ldx, int nf, const float* fw, bool incl,
+int pe_bwd(int64_t n, const float* x, int64_t ldx, int nf, const float* fw, bool incl,
                   const float* d_out, int64_t ldo, float* d_x, int64_t lddx, bool accumulate,
                   cudaStream_t st) {
   return launch_1d(n, st, "pe_bwd", [&](unsigned g, unsigned b, cudaStream_t s) {
@@ -147,14 +149,14 @@ static int pe_bwd(int64_t n, const float* x, int64_t ldx, int nf, const float* f
   });
 }
 
-static int copy_cols(int64_t n, int n_cols, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
+int copy_cols(int64_t n, int n_cols, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
                      cudaStream_t st) {
   return launch_1d(n * n_cols, st, "copy_cols", [&](unsigned g, unsigned b, cudaStream_t s) {
     copy_cols_kernel<<<g, b, 0, s>>>(n, n_cols, src, src_ld, dst, dst_ld);
   });
 }
 
-static int add3(int64_t n, const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
+int add3(int64_t n, const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
                 cudaStream_t st) {
   return launch_1d(n * 3, st, "add3", [&](unsigned g, unsigned bl, cudaStream_t s) {
     add3_kernel<<<g, bl, 0, s>>>(n, a, lda, b, ldb, out, ldo);
@@ -276,7 +278,8 @@ int64_t hn_field_workspace_bytes(const hn_field_params* p, int64_t n_samples, in
                                  int precision) {
   FieldPlan fp;
   if (make_plan(p, fp) != 0) return -1;
-  if (precision == HN_PRECISION_BF16) return 256;   // the tcgen05 kernel keeps activations on chip
+  if (precision == HN_PRECISION_BF16)                // forward-only: activations stay on chip
+    return save_for_backward ? tc_train_workspace_bytes(p, n_samples) : 256;
   int64_t rows = chunk_samples(n_samples, save_for_backward != 0);
   return fp.floats_per_sample * rows * (int64_t)sizeof(float) + 256;
 }

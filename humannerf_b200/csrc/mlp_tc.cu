@@ -22,67 +22,31 @@
 //
 // Reference semantics: embedders/hannw_fourier.py:38-49, embedders/fourier.py:9-38,
 // non_rigid_motion_mlps/mlp_offset.py:74-114, canonical_mlps/mlp_rgb_sigma.py:132-206.
-#include <algorithm>
-#include <cstring>
-#include <vector>
-
-#include "tc_common.cuh"
+#include "mlp_tc_plan.cuh"
 
 namespace hn {
-
-constexpr int kTileM = 128;
-constexpr int kTiles = 2;                               // tiles per CTA pass
-constexpr int kStages = 4;
-constexpr uint32_t kStageBytes = 16384;
-constexpr uint32_t kActHTile = kTileM * 256 * 2;        // 64 KB per tile: hidden activations, <= 256 wide
-constexpr uint32_t kActPeTile = kTileM * 64 * 2;        // 16 KB per tile: positional encoding, <= 64 wide
-constexpr uint32_t kActHBytes = kTiles * kActHTile;
-constexpr uint32_t kActPeBytes = kTiles * kActPeTile;
-constexpr uint32_t kLboA = kTileM * 16;                 // bytes between K-adjacent core matrices of A
-constexpr uint32_t kRingOff = kActHBytes + kActPeBytes;
-constexpr uint32_t kBarOff = kRingOff + kStages * kStageBytes;
-constexpr int kMaxChunks = 128;
-constexpr uint32_t kTableOff = kBarOff + 128;
-constexpr uint32_t kSmemTotal = kTableOff + kMaxChunks * 16;
-constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 16;
-constexpr int kThreads = (3 + kEpiWarps) * 32;   // producer, 2 MMA issuers (one per tile), epilogue
-constexpr int kMmaWarp0 = 1, kMmaWarp1 = 2 + kEpiWarps;
-constexpr uint32_t kMagic = 0x484e5432u;                // "HNT2"
-constexpr int kMaxTcLayers = 2 * HN_MAX_LAYERS;
-static_assert(kSmemTotal <= 232448, "shared memory budget");
-
-struct TcChunk {
-  uint32_t w_off;     // byte offset of the chunk inside the weight image
-  uint32_t bytes;     // multiple of 16, <= kStageBytes
-  uint32_t a_off;     // byte offset of the chunk's first A core matrix inside tile 0's region
-  uint16_t n;         // MMA N
-  uint8_t ksteps;     // K / 16
-  uint8_t flags;      // bit0 first chunk of its layer, bit1 last chunk, bit2 A operand in the PE block
-};
-static_assert(sizeof(TcChunk) == 16, "TcChunk must be 16 bytes");
-
-struct TcHeader {
-  uint32_t magic, n_chunks, table_off, image_off, total_bytes, reserved;
-  uint32_t nr_layers, cn_layers, nr_width, cn_width;
-  uint32_t nr_freqs, cn_freqs, nr_pe_pad, cn_pe_pad;
-  uint32_t layer_n[kMaxTcLayers];          // MMA N per layer (non-rigid layers first)
-};
 
 // ------------------------------------------------------------------------------------------
 // positional encodings written straight into the A operand block (bf16, 8 columns per store);
 // `half` selects which of the two threads of a row stores a given 16-byte chunk
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store8(uint32_t region, int row, int chunk, const float* v) {
+__device__ __forceinline__ void store8(uint32_t region, int row, int chunk, const float* v, uint8_t* img_row) {
   const uint32_t addr = region + (uint32_t)chunk * kLboA + (uint32_t)row * 16u;
-  st_shared_v4(addr, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  const uint32_t a = pack_bf16(v[0], v[1]), b = pack_bf16(v[2], v[3]), c = pack_bf16(v[4], v[5]), d = pack_bf16(v[6], v[7]);
+  st_shared_v4(addr, a, b, c, d);
+  if (img_row) *reinterpret_cast<uint4*>(img_row + (size_t)chunk * 256) = make_uint4(a, b, c, d);
+}
+
+// byte offset of (row r of tile t, feature 0) inside a T16 image with F features per sample
+__device__ __forceinline__ size_t image_row_offset(int64_t tile, int r, int F) {
+  return (size_t)tile * 128 * F * 2 + (size_t)(r >> 4) * 16 * F * 2 + (size_t)(r & 15) * 16;
 }
 
 // columns: [optional x (3)], then per frequency sin(x,y,z), cos(x,y,z); zero padding up to `pad`
 // columns with a constant 1 in the last one (the bias column).
 template <bool kIncludeInput>
 __device__ __forceinline__ void write_encoding(uint32_t region, int row, int half, const float x[3], int n_freqs,
-                                               const float* __restrict__ weights, int pad) {
+                                               const float* __restrict__ weights, int pad, uint8_t* img_row) {
   float pe[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) pe[i] = 0.0f;
@@ -107,7 +71,7 @@ __device__ __forceinline__ void write_encoding(uint32_t region, int row, int hal
   for (int ch = 0; ch < 8; ++ch) {
     if (ch * 8 < pad && (ch & 1) == half) {
       if (ch * 8 + 8 == pad) pe[ch * 8 + 7] = 1.0f;
-      store8(region, row, ch, pe + ch * 8);
+      store8(region, row, ch, pe + ch * 8, img_row);
     }
   }
 }
@@ -115,10 +79,11 @@ __device__ __forceinline__ void write_encoding(uint32_t region, int row, int hal
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
+template <bool kStore>
 __global__ void __launch_bounds__(kThreads, 1)
 field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const float* __restrict__ x_skel,
                 const float* __restrict__ hann_w, int ignore_non_rigid, float* __restrict__ raw,
-                float* __restrict__ xyz_out, float* __restrict__ off_out) {
+                float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
   const uint8_t* image = packed + hdr->image_off;
@@ -253,14 +218,17 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
     const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t sample = (pair * kTiles + tile) * kTileM + row;
+      const int64_t tile_idx = pair * kTiles + tile;
+      const int64_t sample = tile_idx * kTileM + row;
       const bool valid = sample < n_samples;
+      const bool store = kStore && tile_idx < bufs.n_tiles;      // the training images hold ceil(P/128) tiles
       float x[3] = {0.f, 0.f, 0.f};
       if (valid) { x[0] = x_skel[sample * 3 + 0]; x[1] = x_skel[sample * 3 + 1]; x[2] = x_skel[sample * 3 + 2]; }
       float q[3] = {x[0], x[1], x[2]};            // position fed to the canonical encoding
 
       if (!ignore_non_rigid) {
-        write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad);
+        write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad,
+                              store ? bufs.pe[0] + image_row_offset(tile_idx, row, nr_pad) : nullptr);
         fence_proxy_async();
         mbar_arrive(bar_ready);
       }
@@ -269,7 +237,8 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
         const bool is_nr = layer < nr_layers;
         const bool is_out = (layer == nr_layers - 1) || (layer == n_layers - 1);
         if (layer == nr_layers) {
-          write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad);
+          write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad,
+                               store ? bufs.pe[1] + image_row_offset(tile_idx, row, cn_pad) : nullptr);
           fence_proxy_async();
           mbar_arrive(bar_ready);
         }
@@ -277,8 +246,12 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
         acc_phase ^= 1;
         tc_fence_after();
         if (!is_out) {
-          const int n_half = (int)hdr->layer_n[layer] >> 1;        // columns owned by this thread
+          const int n_full = (int)hdr->layer_n[layer];
+          const int n_half = n_full >> 1;                          // columns owned by this thread
           const int c_begin = half * n_half;
+          uint8_t* h_img = nullptr;
+          if (store)
+            h_img = (is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers]) + image_row_offset(tile_idx, row, n_full);
           uint32_t v[2][32];
           tmem_ld32(t_acc + (uint32_t)c_begin, v[0]);
 #pragma unroll 1
@@ -289,11 +262,13 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
               const uint32_t* u = v[0] + g8 * 8;
-              const uint32_t addr = a_h + (uint32_t)(((c_begin + c0) >> 3) + g8) * kLboA + (uint32_t)row * 16u;
-              st_shared_v4(addr, pack_relu_bf16(__uint_as_float(u[0]), __uint_as_float(u[1])),
-                           pack_relu_bf16(__uint_as_float(u[2]), __uint_as_float(u[3])),
-                           pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
-                           pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
+              const int chunk = ((c_begin + c0) >> 3) + g8;
+              const uint4 pk = make_uint4(pack_relu_bf16(__uint_as_float(u[0]), __uint_as_float(u[1])),
+                                          pack_relu_bf16(__uint_as_float(u[2]), __uint_as_float(u[3])),
+                                          pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
+                                          pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
+              st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
+              if (store) *reinterpret_cast<uint4*>(h_img + (size_t)chunk * 256) = pk;
             }
             if (c0 + 32 < n_half) {
               tmem_ld_wait();
@@ -301,11 +276,13 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8) {
                 const uint32_t* u = v[1] + g8 * 8;
-                const uint32_t addr = a_h + (uint32_t)(((c_begin + c0 + 32) >> 3) + g8) * kLboA + (uint32_t)row * 16u;
-                st_shared_v4(addr, pack_relu_bf16(__uint_as_float(u[0]), __uint_as_float(u[1])),
-                             pack_relu_bf16(__uint_as_float(u[2]), __uint_as_float(u[3])),
-                             pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
-                             pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
+                const int chunk = ((c_begin + c0 + 32) >> 3) + g8;
+                const uint4 pk = make_uint4(pack_relu_bf16(__uint_as_float(u[0]), __uint_as_float(u[1])),
+                                            pack_relu_bf16(__uint_as_float(u[2]), __uint_as_float(u[3])),
+                                            pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
+                                            pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
+                st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
+                if (store) *reinterpret_cast<uint4*>(h_img + (size_t)chunk * 256) = pk;
               }
             }
           }
@@ -350,21 +327,6 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
 // ------------------------------------------------------------------------------------------
 // Weight packing
 // ------------------------------------------------------------------------------------------
-struct PackJob {            // one per chunk, consumed by pack_weights_kernel
-  const float* src;         // weight matrix (rows = out features), nullptr = all zero
-  const float* bias;        // bias vector placed in K row `bias_row` (nullptr / -1: none)
-  const float* fold_w;      // + fold_w[n, 0:fold_k] . cond added to the bias (condition-code fold)
-  int32_t src_ld;
-  int32_t src_col0;         // source column of the chunk's k = 0
-  int32_t valid_k;          // source columns available from src_col0 (rest is zero padding)
-  int32_t valid_n;          // rows of the weight matrix (rest is zero padding)
-  int32_t n;                // chunk N
-  int32_t kc;               // chunk K
-  int32_t bias_row;
-  int32_t fold_ld, fold_k;
-  uint32_t w_off;           // destination byte offset inside the image
-};
-
 // one thread per 16-byte core-matrix row: image[(k/8) * (N*16) + n*16 .. +16] = W[n][k0+k .. +8]
 __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs, const float* __restrict__ cond,
                                     uint8_t* __restrict__ image) {
@@ -380,7 +342,9 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
       const int k = kg * 8 + i;
       float v = 0.0f;
       if (n < job.valid_n) {
-        if (job.src && k < job.valid_k) v = job.src[(int64_t)n * job.src_ld + job.src_col0 + k];
+        if (job.src && k < job.valid_k)
+          v = job.transpose ? job.src[(int64_t)(job.src_row0 + k) * job.src_ld + job.src_col0 + n]
+                            : job.src[(int64_t)n * job.src_ld + job.src_col0 + k];
         if (k == job.bias_row) {
           v = job.bias ? job.bias[n] : 0.0f;
           if (job.fold_w && cond)
@@ -395,105 +359,10 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
   }
 }
 
-static inline int round16(int v) { return (v + 15) & ~15; }
-
-struct TcPlan {
-  TcHeader hdr;
-  std::vector<TcChunk> chunks;
-  std::vector<PackJob> jobs;
-  uint32_t jobs_off = 0;   // scratch table placed after the image
-};
-
-static int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
-  if (!p) return fail_arg("hn_field(bf16): null params");
-  if (p->nr_layers < 2 || p->nr_layers > HN_MAX_LAYERS || p->cn_layers < 2 || p->cn_layers > HN_MAX_LAYERS)
-    return fail_arg("hn_field(bf16): layer counts outside [2,%d]", HN_MAX_LAYERS);
-  if (p->nr_width % 64 || p->cn_width % 64 || p->nr_width < 64 || p->cn_width < 64 || p->nr_width > 256 ||
-      p->cn_width > 256)
-    return fail_arg("hn_field(bf16): widths must be multiples of 64 in [64,256]");
-  const int nr_pe = 6 * p->nr_freqs, cn_pe = 3 + 6 * p->cn_freqs;
-  // one spare column of the encoding block carries the constant 1 that multiplies the bias row
-  const int nr_pad = round16(nr_pe + 1), cn_pad = round16(cn_pe + 1);
-  if (p->nr_freqs < 1 || p->cn_freqs < 1 || p->nr_freqs > 10 || p->cn_freqs > 10 || nr_pad > 64 || cn_pad > 64)
-    return fail_arg("hn_field(bf16): encodings wider than 63 columns are not supported");
-  if (p->nr_skip == 0 || p->nr_skip >= p->nr_layers - 1 || p->cn_skip == 0 || p->cn_skip >= p->cn_layers - 1)
-    return fail_arg("hn_field(bf16): skip layer must be a hidden layer (or -1)");
-  TcHeader& h = plan.hdr;
-  memset(&h, 0, sizeof(h));
-  h.magic = kMagic;
-  h.nr_layers = p->nr_layers; h.cn_layers = p->cn_layers; h.nr_width = p->nr_width; h.cn_width = p->cn_width;
-  h.nr_freqs = p->nr_freqs; h.cn_freqs = p->cn_freqs; h.nr_pe_pad = nr_pad; h.cn_pe_pad = cn_pad;
-  uint32_t w_off = 0;
-  // One segment = a run of K columns of one A block.  `bias_col` (>= 0) is the column of the segment
-  // that multiplies the constant-1 column of the encoding block.
-  auto add_segment = [&](const float* W, int ldw, int col0, int valid_k, int k_pad, int valid_n, int n, bool in_pe,
-                         int a_col0, bool first, bool last, int bias_col, const float* bias, const float* fold_w,
-                         int fold_ld, int fold_k) {
-    int kc_max = (int)(kStageBytes / (uint32_t)(n * 2)) / 16 * 16;
-    if (kc_max > 240) kc_max = 240;                       // ksteps is a uint8
-    for (int k0 = 0; k0 < k_pad; k0 += kc_max) {
-      const int kc = std::min(kc_max, k_pad - k0);
-      TcChunk c;
-      c.w_off = w_off;
-      c.bytes = (uint32_t)(n * kc * 2);
-      c.a_off = (uint32_t)((a_col0 + k0) / 8) * kLboA;
-      c.n = (uint16_t)n;
-      c.ksteps = (uint8_t)(kc / 16);
-      c.flags = (uint8_t)(((first && k0 == 0) ? 1 : 0) | ((last && k0 + kc >= k_pad) ? 2 : 0) | (in_pe ? 4 : 0));
-      plan.chunks.push_back(c);
-      PackJob j;
-      memset(&j, 0, sizeof(j));
-      j.src = W; j.src_ld = ldw; j.src_col0 = col0 + k0; j.valid_k = std::max(0, valid_k - k0);
-      j.valid_n = valid_n; j.n = n; j.kc = kc; j.w_off = w_off;
-      j.bias_row = -1;
-      if (bias_col >= k0 && bias_col < k0 + kc) {
-        j.bias_row = bias_col - k0; j.bias = bias; j.fold_w = fold_w; j.fold_ld = fold_ld; j.fold_k = fold_k;
-      }
-      plan.jobs.push_back(j);
-      w_off += c.bytes;
-    }
-  };
-  int layer_idx = 0;
-  auto add_mlp = [&](int layers, int width, int skip, int pe, int pe_pad, int lead, bool pe_first,
-                     const float* const* W, const float* const* B, int out_dim) {
-    const int ones_col = pe_pad - 1;
-    for (int l = 0; l < layers; ++l) {
-      const bool out = l == layers - 1;
-      const int n = out ? 16 : width;
-      const int valid_n = out ? out_dim : width;
-      const int in_dim = (l == 0) ? lead + pe : (l == skip ? width + pe : width);
-      const float* fold = (l == 0 && lead > 0) ? W[l] : nullptr;
-      if (l == 0) {
-        add_segment(W[l], in_dim, lead, pe, pe_pad, valid_n, n, true, 0, true, true, ones_col, B[l], fold, in_dim, lead);
-      } else if (l == skip) {
-        if (pe_first) {
-          add_segment(W[l], in_dim, 0, pe, pe_pad, valid_n, n, true, 0, true, false, ones_col, B[l], nullptr, 0, 0);
-          add_segment(W[l], in_dim, pe, width, width, valid_n, n, false, 0, false, true, -1, nullptr, nullptr, 0, 0);
-        } else {
-          add_segment(W[l], in_dim, 0, width, width, valid_n, n, false, 0, true, false, -1, nullptr, nullptr, 0, 0);
-          add_segment(W[l], in_dim, width, pe, pe_pad, valid_n, n, true, 0, false, true, ones_col, B[l], nullptr, 0, 0);
-        }
-      } else {
-        add_segment(W[l], in_dim, 0, width, width, valid_n, n, false, 0, true, false, -1, nullptr, nullptr, 0, 0);
-        // bias step: the last 16 columns of the encoding block against an all-zero weight slab whose
-        // last K row is the bias
-        add_segment(nullptr, 0, 0, 0, 16, valid_n, n, true, pe_pad - 16, false, true, 15, B[l], nullptr, 0, 0);
-      }
-      h.layer_n[layer_idx++] = (uint32_t)n;
-    }
-  };
-  add_mlp(p->nr_layers, p->nr_width, p->nr_skip, nr_pe, nr_pad, p->cond_dim, false, p->nr_w, p->nr_b, 3);
-  add_mlp(p->cn_layers, p->cn_width, p->cn_skip, cn_pe, cn_pad, 0, true, p->cn_w, p->cn_b, 4);
-  if ((int)plan.chunks.size() > kMaxChunks) return fail_arg("hn_field(bf16): too many weight chunks");
-  for (const TcChunk& c : plan.chunks)
-    if (c.bytes > kStageBytes || c.bytes % 16 || c.ksteps == 0) return fail_arg("hn_field(bf16): internal chunk size error");
-  h.n_chunks = (uint32_t)plan.chunks.size();
-  auto align = [](uint32_t v, uint32_t a) { return (v + a - 1) / a * a; };
-  h.table_off = align((uint32_t)sizeof(TcHeader), 16);
-  h.image_off = align(h.table_off + h.n_chunks * (uint32_t)sizeof(TcChunk), 128);
-  plan.jobs_off = align(h.image_off + w_off, 128);
-  h.total_bytes = align(plan.jobs_off + (uint32_t)(plan.jobs.size() * sizeof(PackJob)), 128);
-  return 0;
+int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples) {
+  TcPlan plan;
+  if (make_tc_plan(p, plan) != 0) return -1;
+  return carve_train_bufs(plan, n_samples, nullptr, nullptr) + 256;
 }
 
 }  // namespace hn
@@ -526,6 +395,8 @@ int hn_field_pack_bf16(const hn_field_params* p, const float* cond, void* packed
   HN_TRY(check_cuda(cudaMemcpyAsync(dst, &plan.hdr, sizeof(TcHeader), cudaMemcpyHostToDevice, st), "pack/header"));
   HN_TRY(check_cuda(cudaMemcpyAsync(dst + plan.hdr.table_off, plan.chunks.data(),
                                     plan.chunks.size() * sizeof(TcChunk), cudaMemcpyHostToDevice, st), "pack/table"));
+  HN_TRY(check_cuda(cudaMemcpyAsync(dst + plan.hdr.bwd_table_off, plan.bwd_chunks.data(),
+                                    plan.bwd_chunks.size() * sizeof(TcChunk), cudaMemcpyHostToDevice, st), "pack/bwd table"));
   HN_TRY(check_cuda(cudaMemcpyAsync(dst + plan.jobs_off, plan.jobs.data(), plan.jobs.size() * sizeof(PackJob),
                                     cudaMemcpyHostToDevice, st), "pack/jobs"));
   dim3 grid(8, (unsigned)plan.jobs.size());
@@ -546,8 +417,6 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     return hn_field_fwd_fp32(p, n_samples, x_skel, cond, hann_w, ignore_non_rigid, raw, xyz, offsets, workspace,
                              workspace_bytes, save_for_backward, stream);
   if (precision != HN_PRECISION_BF16) return fail_arg("hn_field_fwd: unknown precision %d", precision);
-  if (save_for_backward)
-    return fail_arg("hn_field_fwd: the bf16 tensor-core path is forward-only; train with HN_PRECISION_FP32");
   if (!packed) return fail_arg("hn_field_fwd: bf16 path needs the image from hn_field_pack_bf16");
   if (n_samples == 0) return 0;
   if (n_samples < 0 || !x_skel || !raw || !xyz || !offsets) return fail_arg("hn_field_fwd: null pointer");
@@ -557,12 +426,25 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
   int dev = 0, sms = 0;
   HN_TRY(check_cuda(cudaGetDevice(&dev), "hn_field_fwd/device"));
   HN_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "hn_field_fwd/attr"));
-  HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemTotal), "hn_field_fwd/smem attr"));
   const int64_t n_pairs = ceil_div<int64_t>(n_samples, kTiles * kTileM);
   const unsigned grid = (unsigned)std::min<int64_t>(n_pairs, (int64_t)sms);
-  field_tc_kernel<<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
-      static_cast<const uint8_t*>(packed), n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  if (save_for_backward) {
+    TrainBufs bufs;
+    const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
+    if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kSmemTotal), "hn_field_fwd/smem attr"));
+    field_tc_kernel<true><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
+        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs);
+  } else {
+    TrainBufs bufs;
+    memset(&bufs, 0, sizeof(bufs));
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kSmemTotal), "hn_field_fwd/smem attr"));
+    field_tc_kernel<false><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
+        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs);
+  }
   return launched("hn_field_fwd/tcgen05");
 }
 

@@ -1,0 +1,282 @@
+// Host-side plan of the tcgen05 canonical-field kernels: shared-memory geometry, the packed weight
+// image (forward chunks W, backward-data chunks W^T), the round table of the backward chain and the
+// layout of the training buffers (T16 tile images).  Shared by mlp_tc.cu and mlp_tc_bwd.cu.
+#pragma once
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "tc_common.cuh"
+#include "tiles.cuh"
+
+namespace hn {
+
+constexpr int kTileM = 128;
+constexpr int kTiles = 2;                               // tiles per CTA pass
+constexpr int kStages = 4;
+constexpr uint32_t kStageBytes = 16384;
+constexpr uint32_t kActHTile = kTileM * 256 * 2;        // 64 KB per tile: hidden activations, <= 256 wide
+constexpr uint32_t kActPeTile = kTileM * 64 * 2;        // 16 KB per tile: positional encoding, <= 64 wide
+constexpr uint32_t kActHBytes = kTiles * kActHTile;
+constexpr uint32_t kActPeBytes = kTiles * kActPeTile;
+constexpr uint32_t kLboA = kTileM * 16;                 // bytes between K-adjacent core matrices of A
+constexpr uint32_t kRingOff = kActHBytes + kActPeBytes;
+constexpr uint32_t kBarOff = kRingOff + kStages * kStageBytes;
+constexpr int kMaxChunks = 128;
+constexpr uint32_t kTableOff = kBarOff + 128;
+constexpr uint32_t kSmemTotal = kTableOff + kMaxChunks * 16;
+constexpr int kTmemCols = 512;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (3 + kEpiWarps) * 32;          // producer, 2 MMA issuers (one per tile), epilogue
+constexpr int kMmaWarp0 = 1, kMmaWarp1 = 2 + kEpiWarps;
+constexpr uint32_t kMagic = 0x484e5433u;                // "HNT3"
+constexpr int kMaxTcLayers = 2 * HN_MAX_LAYERS;
+constexpr int kMaxRounds = 2 * HN_MAX_LAYERS + 4;
+static_assert(kSmemTotal <= 232448, "shared memory budget");
+
+struct TcChunk {
+  uint32_t w_off;     // byte offset of the chunk inside the weight image
+  uint32_t bytes;     // multiple of 16, <= kStageBytes
+  uint32_t a_off;     // byte offset of the chunk's first A core matrix inside tile 0's region
+  uint16_t n;         // MMA N
+  uint8_t ksteps;     // K / 16
+  uint8_t flags;      // bit0 first chunk of its layer / round, bit1 last chunk, bit2 A operand in the PE block
+};
+static_assert(sizeof(TcChunk) == 16, "TcChunk must be 16 bytes");
+
+// One accumulator round of the backward-data chain: MMAs of chunks [chunk0, chunk1) then an epilogue.
+struct BwdRound {
+  uint16_t chunk0, chunk1;
+  uint16_t n;          // accumulator columns
+  uint8_t epi;         // 0: dZ_prev = acc * [H_prev > 0] -> A block + dZ image;  1: acc -> d_pe (fp32)
+  uint8_t layer;       // epi 0: hidden layer whose activation masks / whose dZ is produced; epi 1: d_pe slot
+};
+static_assert(sizeof(BwdRound) == 8, "BwdRound must be 8 bytes");
+
+struct TcHeader {
+  uint32_t magic, n_chunks, table_off, image_off, total_bytes, reserved;
+  uint32_t nr_layers, cn_layers, nr_width, cn_width;
+  uint32_t nr_freqs, cn_freqs, nr_pe_pad, cn_pe_pad;
+  uint32_t layer_n[kMaxTcLayers];          // MMA N per layer (non-rigid layers first)
+  // backward-data chain (per MLP: 0 = non-rigid, 1 = canonical)
+  uint32_t bwd_table_off, bwd_n_chunks;    // chunk table of W^T chunks (w_off relative to image_off)
+  uint32_t bwd_chunk0[2], bwd_chunk1[2];
+  uint32_t bwd_round0[2], bwd_round1[2];
+  BwdRound rounds[kMaxRounds];
+};
+
+// Training buffers: T16 tile images of the encoding blocks, hidden activations and pre-activation
+// gradients, plus fp32 row-major gradients of the encoding blocks.  Passed to the kernels by value.
+struct TrainBufs {
+  uint8_t* pe[2];                    // [mlp]            F = pe_pad
+  uint8_t* h[2][HN_MAX_LAYERS];      // [mlp][layer]     F = width      (hidden layers)
+  uint8_t* dz[2][HN_MAX_LAYERS];     // [mlp][layer]     F = width, 16 for the output layer
+  float* d_pe[2][2];                 // [mlp][slot]      (P, pe_pad) fp32; slot 0 = skip layer, 1 = layer 0
+  int64_t n_tiles;                   // tiles that exist in the images
+};
+
+struct PackJob {            // one per chunk, consumed by pack_weights_kernel
+  const float* src;         // weight matrix (rows = out features), nullptr = all zero
+  const float* bias;        // bias vector placed in K row `bias_row` (nullptr / -1: none)
+  const float* fold_w;      // + fold_w[n, 0:fold_k] . cond added to the bias (condition-code fold)
+  int32_t src_ld;
+  int32_t src_col0;         // source column of the chunk's k = 0 (n = 0 when transposed)
+  int32_t valid_k;          // valid K extent from src_col0 (rest is zero padding)
+  int32_t valid_n;          // valid N extent (rest is zero padding)
+  int32_t n;                // chunk N
+  int32_t kc;               // chunk K
+  int32_t bias_row;
+  int32_t fold_ld, fold_k;
+  int32_t transpose;        // 0: B[n][k] = src[n][col0 + k];  1: B[n][k] = src[row0 + k][col0 + n]
+  int32_t src_row0;
+  uint32_t w_off;           // destination byte offset inside the image
+};
+
+static inline int round16(int v) { return (v + 15) & ~15; }
+
+struct TcPlan {
+  TcHeader hdr;
+  std::vector<TcChunk> chunks, bwd_chunks;
+  std::vector<PackJob> jobs;
+  uint32_t jobs_off = 0;   // scratch table placed after the image
+  int pe_dim[2], pe_pad[2], width[2], layers[2], skip[2], lead[2], out_dim[2];
+};
+
+inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
+  if (!p) return fail_arg("hn_field(bf16): null params");
+  if (p->nr_layers < 2 || p->nr_layers > HN_MAX_LAYERS || p->cn_layers < 2 || p->cn_layers > HN_MAX_LAYERS)
+    return fail_arg("hn_field(bf16): layer counts outside [2,%d]", HN_MAX_LAYERS);
+  if (p->nr_width % 64 || p->cn_width % 64 || p->nr_width < 64 || p->cn_width < 64 || p->nr_width > 256 ||
+      p->cn_width > 256)
+    return fail_arg("hn_field(bf16): widths must be multiples of 64 in [64,256]");
+  const int nr_pe = 6 * p->nr_freqs, cn_pe = 3 + 6 * p->cn_freqs;
+  // one spare column of the encoding block carries the constant 1 that multiplies the bias row
+  const int nr_pad = round16(nr_pe + 1), cn_pad = round16(cn_pe + 1);
+  if (p->nr_freqs < 1 || p->cn_freqs < 1 || p->nr_freqs > 10 || p->cn_freqs > 10 || nr_pad > 64 || cn_pad > 64)
+    return fail_arg("hn_field(bf16): encodings wider than 63 columns are not supported");
+  if (p->nr_skip == 0 || p->nr_skip >= p->nr_layers - 1 || p->cn_skip == 0 || p->cn_skip >= p->cn_layers - 1)
+    return fail_arg("hn_field(bf16): skip layer must be a hidden layer (or -1)");
+  TcHeader& h = plan.hdr;
+  memset(&h, 0, sizeof(h));
+  h.magic = kMagic;
+  h.nr_layers = p->nr_layers; h.cn_layers = p->cn_layers; h.nr_width = p->nr_width; h.cn_width = p->cn_width;
+  h.nr_freqs = p->nr_freqs; h.cn_freqs = p->cn_freqs; h.nr_pe_pad = nr_pad; h.cn_pe_pad = cn_pad;
+  plan.pe_dim[0] = nr_pe; plan.pe_dim[1] = cn_pe; plan.pe_pad[0] = nr_pad; plan.pe_pad[1] = cn_pad;
+  plan.width[0] = p->nr_width; plan.width[1] = p->cn_width; plan.layers[0] = p->nr_layers; plan.layers[1] = p->cn_layers;
+  plan.skip[0] = p->nr_skip; plan.skip[1] = p->cn_skip; plan.lead[0] = p->cond_dim; plan.lead[1] = 0;
+  plan.out_dim[0] = 3; plan.out_dim[1] = 4;
+  uint32_t w_off = 0;
+
+  // ---- forward: one segment = a run of K columns of one A block against W[:, cols] ----------------
+  auto add_segment = [&](std::vector<TcChunk>& table, const float* W, int ldw, int col0, int valid_k, int k_pad,
+                         int valid_n, int n, bool in_pe, int a_col0, bool first, bool last, int bias_col,
+                         const float* bias, const float* fold_w, int fold_ld, int fold_k, bool transpose, int row0) {
+    int kc_max = (int)(kStageBytes / (uint32_t)(n * 2)) / 16 * 16;
+    if (kc_max > 240) kc_max = 240;                       // ksteps is a uint8
+    for (int k0 = 0; k0 < k_pad; k0 += kc_max) {
+      const int kc = std::min(kc_max, k_pad - k0);
+      TcChunk c;
+      c.w_off = w_off;
+      c.bytes = (uint32_t)(n * kc * 2);
+      c.a_off = (uint32_t)((a_col0 + k0) / 8) * kLboA;
+      c.n = (uint16_t)n;
+      c.ksteps = (uint8_t)(kc / 16);
+      c.flags = (uint8_t)(((first && k0 == 0) ? 1 : 0) | ((last && k0 + kc >= k_pad) ? 2 : 0) | (in_pe ? 4 : 0));
+      table.push_back(c);
+      PackJob j;
+      memset(&j, 0, sizeof(j));
+      j.src = W; j.src_ld = ldw; j.valid_n = valid_n; j.n = n; j.kc = kc; j.w_off = w_off;
+      j.valid_k = std::max(0, valid_k - k0);
+      j.transpose = transpose ? 1 : 0;
+      if (transpose) { j.src_col0 = col0; j.src_row0 = row0 + k0; }
+      else { j.src_col0 = col0 + k0; j.src_row0 = 0; }
+      j.bias_row = -1;
+      if (bias_col >= k0 && bias_col < k0 + kc) {
+        j.bias_row = bias_col - k0; j.bias = bias; j.fold_w = fold_w; j.fold_ld = fold_ld; j.fold_k = fold_k;
+      }
+      plan.jobs.push_back(j);
+      w_off += c.bytes;
+    }
+  };
+  int layer_idx = 0;
+  auto add_mlp = [&](int m, const float* const* W, const float* const* B) {
+    const int layers = plan.layers[m], width = plan.width[m], skip = plan.skip[m], pe = plan.pe_dim[m];
+    const int pe_pad = plan.pe_pad[m], lead = plan.lead[m];
+    const bool pe_first = m == 1;
+    const int ones_col = pe_pad - 1;
+    for (int l = 0; l < layers; ++l) {
+      const bool out = l == layers - 1;
+      const int n = out ? 16 : width;
+      const int valid_n = out ? plan.out_dim[m] : width;
+      const int in_dim = (l == 0) ? lead + pe : (l == skip ? width + pe : width);
+      const float* fold = (l == 0 && lead > 0) ? W[l] : nullptr;
+      auto& T = plan.chunks;
+      if (l == 0) {
+        add_segment(T, W[l], in_dim, lead, pe, pe_pad, valid_n, n, true, 0, true, true, ones_col, B[l], fold, in_dim, lead, false, 0);
+      } else if (l == skip) {
+        if (pe_first) {
+          add_segment(T, W[l], in_dim, 0, pe, pe_pad, valid_n, n, true, 0, true, false, ones_col, B[l], nullptr, 0, 0, false, 0);
+          add_segment(T, W[l], in_dim, pe, width, width, valid_n, n, false, 0, false, true, -1, nullptr, nullptr, 0, 0, false, 0);
+        } else {
+          add_segment(T, W[l], in_dim, 0, width, width, valid_n, n, false, 0, true, false, -1, nullptr, nullptr, 0, 0, false, 0);
+          add_segment(T, W[l], in_dim, width, pe, pe_pad, valid_n, n, true, 0, false, true, ones_col, B[l], nullptr, 0, 0, false, 0);
+        }
+      } else {
+        add_segment(T, W[l], in_dim, 0, width, width, valid_n, n, false, 0, true, false, -1, nullptr, nullptr, 0, 0, false, 0);
+        // bias step: the last 16 columns of the encoding block against an all-zero weight slab whose
+        // last K row is the bias
+        add_segment(T, nullptr, 0, 0, 0, 16, valid_n, n, true, pe_pad - 16, false, true, 15, B[l], nullptr, 0, 0, false, 0);
+      }
+      h.layer_n[layer_idx++] = (uint32_t)n;
+    }
+  };
+  add_mlp(0, p->nr_w, p->nr_b);
+  add_mlp(1, p->cn_w, p->cn_b);
+
+  // ---- backward data: for layer l (last to first) dX = dZ_l W_l restricted to a column window.
+  //      A = dZ_l (K = out features of layer l, in the hidden A block), B = (W_l window)^T -----------
+  int n_rounds = 0;
+  auto add_round = [&](int chunk0, int n, int epi, int layer) {
+    BwdRound r;
+    r.chunk0 = (uint16_t)chunk0; r.chunk1 = (uint16_t)plan.bwd_chunks.size(); r.n = (uint16_t)n;
+    r.epi = (uint8_t)epi; r.layer = (uint8_t)layer;
+    h.rounds[n_rounds++] = r;
+  };
+  auto add_mlp_bwd = [&](int m, const float* const* W) {
+    const int layers = plan.layers[m], width = plan.width[m], skip = plan.skip[m], pe = plan.pe_dim[m];
+    const int pe_pad = plan.pe_pad[m], lead = plan.lead[m];
+    const bool pe_first = m == 1;
+    h.bwd_chunk0[m] = (uint32_t)plan.bwd_chunks.size();
+    h.bwd_round0[m] = (uint32_t)n_rounds;
+    for (int l = layers - 1; l >= 0; --l) {
+      const bool out = l == layers - 1;
+      const int k_pad = out ? 16 : width;                        // K = out features of layer l
+      const int valid_k = out ? plan.out_dim[m] : width;
+      const int in_dim = (l == 0) ? lead + pe : (l == skip ? width + pe : width);
+      const int pe_col = (l == 0) ? lead : (pe_first ? 0 : width);
+      const int h_col = (l == skip && pe_first) ? pe : 0;
+      if (l == 0 || l == skip) {
+        // gradient of the encoding columns -> fp32 buffer (slot 0: skip layer, slot 1: layer 0)
+        const int c0 = (int)plan.bwd_chunks.size();
+        add_segment(plan.bwd_chunks, W[l], in_dim, pe_col, valid_k, k_pad, pe, pe_pad, false, 0, true, true, -1, nullptr,
+                    nullptr, 0, 0, true, 0);
+        add_round(c0, pe_pad, 1, l == 0 ? 1 : 0);
+      }
+      if (l > 0) {
+        // gradient of the previous hidden layer -> masked by its activation -> dZ_{l-1}
+        const int c0 = (int)plan.bwd_chunks.size();
+        add_segment(plan.bwd_chunks, W[l], in_dim, h_col, valid_k, k_pad, width, width, false, 0, true, true, -1, nullptr,
+                    nullptr, 0, 0, true, 0);
+        add_round(c0, width, 0, l - 1);
+      }
+    }
+    h.bwd_chunk1[m] = (uint32_t)plan.bwd_chunks.size();
+    h.bwd_round1[m] = (uint32_t)n_rounds;
+  };
+  add_mlp_bwd(0, p->nr_w);
+  add_mlp_bwd(1, p->cn_w);
+  if (n_rounds > kMaxRounds) return fail_arg("hn_field(bf16): too many backward rounds");
+
+  if ((int)plan.chunks.size() > kMaxChunks || (int)plan.bwd_chunks.size() > kMaxChunks)
+    return fail_arg("hn_field(bf16): too many weight chunks");
+  for (const auto* tab : {&plan.chunks, &plan.bwd_chunks})
+    for (const TcChunk& c : *tab)
+      if (c.bytes > kStageBytes || c.bytes % 16 || c.ksteps == 0) return fail_arg("hn_field(bf16): internal chunk size error");
+  h.n_chunks = (uint32_t)plan.chunks.size();
+  h.bwd_n_chunks = (uint32_t)plan.bwd_chunks.size();
+  auto align = [](uint32_t v, uint32_t a) { return (v + a - 1) / a * a; };
+  h.table_off = align((uint32_t)sizeof(TcHeader), 16);
+  h.bwd_table_off = align(h.table_off + h.n_chunks * (uint32_t)sizeof(TcChunk), 16);
+  h.image_off = align(h.bwd_table_off + h.bwd_n_chunks * (uint32_t)sizeof(TcChunk), 128);
+  plan.jobs_off = align(h.image_off + w_off, 128);
+  h.total_bytes = align(plan.jobs_off + (uint32_t)(plan.jobs.size() * sizeof(PackJob)), 128);
+  return 0;
+}
+
+// Carves the training buffers out of `base` (may be null to only measure). Returns the bytes used.
+inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* base, TrainBufs* out) {
+  const int64_t n_tiles = ceil_div<int64_t>(std::max<int64_t>(n_samples, 1), 128);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += (bytes + 255) / 256 * 256;
+    return p;
+  };
+  TrainBufs b;
+  memset(&b, 0, sizeof(b));
+  b.n_tiles = n_tiles;
+  for (int m = 0; m < 2; ++m) {
+    b.pe[m] = take(n_tiles * 128 * plan.pe_pad[m] * 2);
+    for (int l = 0; l < plan.layers[m]; ++l) {
+      const bool outl = l == plan.layers[m] - 1;
+      if (!outl) b.h[m][l] = take(n_tiles * 128 * plan.width[m] * 2);
+      b.dz[m][l] = take(n_tiles * 128 * (outl ? 16 : plan.width[m]) * 2);
+    }
+    for (int s = 0; s < 2; ++s) b.d_pe[m][s] = reinterpret_cast<float*>(take(n_tiles * 128 * plan.pe_pad[m] * 4));
+  }
+  if (out) *out = b;
+  return off;
+}
+
+}  // namespace hn

@@ -229,9 +229,6 @@ class Network(nn.Module):
         nr_w, nr_b, cn_w, cn_b = self._field_weights()
         packed = None
         if precision == _lib.PRECISION_BF16:
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                raise RuntimeError('humannerf_b200: cfg.b200.mlp_precision="bf16" is a forward-only render path in '
-                                   'this build; wrap the call in torch.no_grad() or train with "fp32"')
             packed = ops.pack_field_bf16(self._spec, nr_w, nr_b, cn_w, cn_b, cond)
 
         outs = []

@@ -266,9 +266,6 @@ class _CanonicalField(torch.autograd.Function):
         x_skel = _f32c(x_skel)
         P = x_skel.shape[0]
         dev = x_skel.device
-        if need_grad and precision != _lib.PRECISION_FP32:
-            raise RuntimeError('humannerf_b200: the bf16 tensor-core field is forward-only in this build; '
-                               'set cfg.b200.mlp_precision = "fp32" for training')
         raw = torch.empty(P, 4, dtype=torch.float32, device=dev)
         xyz = torch.empty(P, 3, dtype=torch.float32, device=dev)
         off = torch.empty(P, 3, dtype=torch.float32, device=dev)
@@ -281,9 +278,9 @@ class _CanonicalField(torch.autograd.Function):
                                    ptr(raw), ptr(xyz), ptr(off), ptr(ws), wbytes, 1 if need_grad else 0, precision,
                                    ptr(packed), stream_ptr()), 'field_fwd')
         if need_grad:
-            ctx.spec, ctx.ignore = spec, ignore_non_rigid
-            ctx.ws = ws
-            ctx.save_for_backward(x_skel, cond, hann_w, *flat)
+            ctx.spec, ctx.ignore, ctx.precision = spec, ignore_non_rigid, precision
+            ctx.ws, ctx.packed = ws, packed
+            ctx.save_for_backward(x_skel, cond, hann_w, xyz, *flat)
         return raw, xyz, off
 
     @staticmethod
@@ -291,7 +288,7 @@ class _CanonicalField(torch.autograd.Function):
         lib = _lib.load()
         spec = ctx.spec
         nl, cl = spec.nr_layers, spec.cn_layers
-        x_skel, cond, hann_w, *flat = ctx.saved_tensors
+        x_skel, cond, hann_w, xyz, *flat = ctx.saved_tensors
         nr_w, nr_b, cn_w, cn_b = flat[:nl], flat[nl:2 * nl], flat[2 * nl:2 * nl + cl], flat[2 * nl + cl:]
         fp = spec.params(nr_w, nr_b, cn_w, cn_b)
         P = x_skel.shape[0]
@@ -308,13 +305,22 @@ class _CanonicalField(torch.autograd.Function):
         g_xyz = _f32c(g_xyz) if g_xyz is not None else None
         g_off = _f32c(g_off) if g_off is not None else None
         d_x = torch.empty(P, 3, dtype=torch.float32, device=dev)
-        sbytes = int(lib.hn_field_bwd_scratch_bytes(C.byref(fp), P))
-        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev), _timed('field_bwd_fp32'):
-            check(lib.hn_field_bwd(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(cond), ptr(hann_w),
-                                   1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
-                                   ptr(ctx.ws), ctx.ws.numel(), ptr(scratch), sbytes, stream_ptr()), 'field_bwd')
-        ctx.ws = None
+        if ctx.precision == _lib.PRECISION_BF16:
+            sbytes = int(lib.hn_field_bwd_bf16_scratch_bytes(C.byref(fp), P))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev), _timed('field_bwd_bf16'):
+                check(lib.hn_field_bwd_bf16(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(xyz), ptr(cond), ptr(hann_w),
+                                            1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
+                                            ptr(ctx.ws), ctx.ws.numel(), ptr(ctx.packed), ptr(scratch), sbytes,
+                                            stream_ptr()), 'field_bwd_bf16')
+        else:
+            sbytes = int(lib.hn_field_bwd_scratch_bytes(C.byref(fp), P))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev), _timed('field_bwd_fp32'):
+                check(lib.hn_field_bwd(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(cond), ptr(hann_w),
+                                       1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
+                                       ptr(ctx.ws), ctx.ws.numel(), ptr(scratch), sbytes, stream_ptr()), 'field_bwd')
+        ctx.ws = ctx.packed = None
         return (None, None, None, None, None, d_x, None, None, *grads)
 
 

@@ -134,7 +134,7 @@ typedef struct hn_field_grads {
 } hn_field_grads;
 
 #define HN_PRECISION_FP32 0   /* SIMT fp32 kernels, 1e-4 parity path                       */
-#define HN_PRECISION_BF16 1   /* tcgen05 / TMEM fused kernel, bf16 operands, fp32 accumulate */
+#define HN_PRECISION_BF16 1   /* tcgen05 / TMEM fused kernels, bf16 operands, fp32 accumulate */
 
 /* Bytes of workspace hn_field_fwd needs for n_samples.  save_for_backward != 0 keeps every
  * activation hn_field_bwd needs (the same workspace must then be passed to it untouched). */
@@ -160,6 +160,17 @@ int hn_field_bwd(const hn_field_params* p, const hn_field_grads* g, int64_t n_sa
                  const float* d_raw, const float* d_xyz, const float* d_offsets,
                  float* d_x_skel, const void* workspace, int64_t workspace_bytes,
                  void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Backward on the tensor cores (HN_PRECISION_BF16).  `workspace` is the one hn_field_fwd filled with
+ * save_for_backward != 0 and precision BF16 (T16 images of every activation), `packed` the image the
+ * forward used, `xyz` the forward's xyz output.  Runs the fused backward-data chains (tcgen05), the
+ * encoding backward, and hn_tile_wgrad jobs for every weight / bias; accumulates into `g`. */
+int64_t hn_field_bwd_bf16_scratch_bytes(const hn_field_params* p, int64_t n_samples);
+int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t n_samples,
+                      const float* x_skel, const float* xyz, const float* cond, const float* hann_w,
+                      int ignore_non_rigid, const float* d_raw, const float* d_xyz, const float* d_offsets,
+                      float* d_x_skel, void* workspace, int64_t workspace_bytes, const void* packed,
+                      void* scratch, int64_t scratch_bytes, void* stream);
 
 /* bf16 weight image for the tcgen05 kernel: weights re-tiled into the UMMA shared-memory
  * core-matrix layout, in consumption order, with the condition code folded into the first

@@ -80,3 +80,119 @@ def test_tile_wgrad_against_matmul(ops):
     # accumulation: running the same jobs again doubles the result
     ops.tile_wgrad(jobs[:1], P)
     check('accumulate', dw_full[:, 63:], 2 * (dzb.t() @ xb))
+
+
+# --------------------------------------------------------------------------------------
+# bf16 tensor-core training path: forward with stored activations + backward chains + wgrad
+# --------------------------------------------------------------------------------------
+def _weights(sd, dev, requires_grad=False):
+    nr = [sd[f'non_rigid_mlp.module.block_mlps.{i}.weight'] for i in range(0, 13, 2)]
+    nrb = [sd[f'non_rigid_mlp.module.block_mlps.{i}.bias'] for i in range(0, 13, 2)]
+    cn = [sd[f'cnl_mlp.module.pts_linears.{i}.weight'] for i in range(0, 15, 2)] + [sd['cnl_mlp.module.output_linear.0.weight']]
+    cnb = [sd[f'cnl_mlp.module.pts_linears.{i}.bias'] for i in range(0, 15, 2)] + [sd['cnl_mlp.module.output_linear.0.bias']]
+    mk = lambda ts: [t.clone().to(dev).requires_grad_(requires_grad) for t in ts]
+    return mk(nr), mk(nrb), mk(cn), mk(cnb)
+
+
+NAMES = ([f'non_rigid_mlp.module.block_mlps.{i}.weight' for i in range(0, 13, 2)]
+         + [f'non_rigid_mlp.module.block_mlps.{i}.bias' for i in range(0, 13, 2)]
+         + [f'cnl_mlp.module.pts_linears.{i}.weight' for i in range(0, 15, 2)] + ['cnl_mlp.module.output_linear.0.weight']
+         + [f'cnl_mlp.module.pts_linears.{i}.bias' for i in range(0, 15, 2)] + ['cnl_mlp.module.output_linear.0.bias'])
+
+
+@pytest.mark.parametrize('P,ignore', [(700, False), (128 * 7 + 5, True), (4099, False)])
+def test_field_bf16_backward(ops, P, ignore):
+    """Gradients of the bf16 path against fp32 autograd through the oracle.  bf16 operands (8 mantissa
+    bits) in every GEMM of the forward and backward chains bound the agreement: stated tolerance 5e-2
+    relative L2 per tensor (measured values are printed)."""
+    from humannerf_b200 import _lib, synthetic as syn
+    from oracle import humannerf_oracle as orc
+    sd = syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True)
+    frame = syn.make_frame(0)
+    gen = torch.Generator().manual_seed(P)
+    x0 = torch.rand(P, 3, generator=gen) * 1.6 - 0.8
+    cond = torch.from_numpy(frame['dst_posevec'])
+    hann = orc.hann_weights(30000, 6, 10000, 50000)
+    g_raw, g_xyz, g_off = torch.randn(P, 4, generator=gen), torch.randn(P, 3, generator=gen), torch.randn(P, 3, generator=gen)
+    # oracle
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k in NAMES}
+    x = x0.clone().requires_grad_()
+    if ignore:
+        xyz_o, off_o = x, torch.zeros_like(x)
+    else:
+        xyz_o, off_o = orc.non_rigid_mlp(sdo, orc.fourier_pe(x, 6, hann, False), x, cond[None])
+    raw_o = orc.canonical_mlp(sdo, orc.fourier_pe(xyz_o, 10))
+    ((raw_o * g_raw).sum() + (xyz_o * g_xyz).sum() + (off_o * g_off).sum()).backward()
+    # CUDA bf16
+    spec = ops.FieldSpec()
+    w = _weights(sd, DEV, requires_grad=True)
+    packed = ops.pack_field_bf16(spec, *w, cond.to(DEV))
+    xc = x0.to(DEV).requires_grad_()
+    raw, xyz, off = ops.canonical_field(spec, xc, cond.to(DEV), hann.to(DEV), *w, ignore_non_rigid=ignore,
+                                        precision=_lib.PRECISION_BF16, packed=packed)
+    ((raw * g_raw.to(DEV)).sum() + (xyz * g_xyz.to(DEV)).sum() + (off * g_off.to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+
+    def rel_l2(a, b):
+        return float((a.double().cpu() - b.double()).norm() / (b.double().norm() + 1e-20))
+    bad = []
+    e = rel_l2(xc.grad, x.grad)
+    print(f'[parity] field16.d_x[P={P},ignore={ignore}]: rel L2 {e:.3e}')
+    if not e < 8e-2:
+        bad.append(('d_x', e))
+    for n, p in zip(NAMES, w[0] + w[1] + w[2] + w[3]):
+        if ignore and n.startswith('non_rigid'):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        e = rel_l2(p.grad, sdo[n].grad)
+        print(f'[parity] field16.grad {n}[P={P},ignore={ignore}]: rel L2 {e:.3e}  |ref| {float(sdo[n].grad.norm()):.3e}')
+        if not e < 5e-2:
+            bad.append((n, e))
+    assert not bad, bad
+
+
+def test_network_train_bf16(ops):
+    """End to end: Network in train mode on the bf16 path vs the reference's golden gradients."""
+    import os
+    from humannerf_b200 import synthetic as syn
+    from humannerf_b200.config import make_cfg
+    from humannerf_b200.network import Network
+    GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    g = np.load(os.path.join(GOLD, 'network_e2e.npz'))
+    st = np.load(os.path.join(GOLD, 'stages.npz'))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    cfg = make_cfg()
+    cfg.b200.mlp_precision = 'bf16'
+    cfg.perturb = 1.0
+    net = Network()
+    net.load_state_dict(syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True))
+    net = net.to(DEV).train()
+    fr = {k: T(v) for k, v in syn.make_frame(0).items()}
+    data = dict(rays=T(st['rays']), near=T(st['near']), far=T(st['far']), dst_Rs=fr['dst_Rs'], dst_Ts=fr['dst_Ts'],
+                cnl_gtfms=fr['cnl_gtfms'], motion_weights_priors=fr['motion_weights_priors'], dst_posevec=fr['dst_posevec'],
+                cnl_bbox_min_xyz=fr['cnl_bbox_min_xyz'], cnl_bbox_max_xyz=fr['cnl_bbox_max_xyz'],
+                cnl_bbox_scale_xyz=fr['cnl_bbox_scale_xyz'], bgcolor=T(g['bgcolor']))
+    out = net(**data, iter_val=torch.full((1,), 30000, device=DEV), t_rand=T(st['t_rand']))
+    for k in ('rgb', 'alpha'):
+        err = float((out[k].detach().cpu() - torch.from_numpy(g['train_' + k])).abs().max())
+        print(f'[parity] bf16 train_{k}: max abs err {err:.3e}')
+        assert err < 2e-2
+    loss = (out['rgb'] * T(g['train_loss_w'])).sum() + 0.3 * out['alpha'].sum() + 0.1 * out['depth'].sum()
+    net.zero_grad()
+    loss.backward()
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    bad = []
+    for n, ref_l2 in zip([str(x) for x in g['grad_names']], g['grad_l2']):
+        ours = float(grads[n].double().norm())
+        err = abs(ours - ref_l2) / max(ref_l2, 1e-12)
+        print(f'[parity] bf16 grad L2 {n}: ours {ours:.5g} ref {ref_l2:.5g} rel {err:.2e}')
+        if err > 1e-1:
+            bad.append((n, err))
+    for key in g.files:
+        if key.startswith('grad/'):
+            ref = torch.from_numpy(g[key]).double()
+            e = float((grads[key[5:]].double().cpu() - ref).norm() / ref.norm())
+            print(f'[parity] bf16 {key}: rel L2 err {e:.3e}')
+            if e > 1e-1:
+                bad.append((key, e))
+    assert not bad, bad
