@@ -165,7 +165,8 @@ def main():
     ap.add_argument('--warmup-ref', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true')
-    ap.add_argument('--precision', default='fp32', choices=['fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help='MLP arithmetic of the train step: bf16 tcgen05 kernels (default) or the fp32 SIMT parity path')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.steps > 6:
@@ -222,7 +223,7 @@ def main():
         with torch.no_grad():
             rays = torch.stack([o_c, d_c, d_c], 0)
             out = net(rays=rays, near=near_c, far=far_c, iter_val=cfg.eval_iter, **frame_kw)
-        cfg.b200.mlp_precision, cfg.perturb = 'fp32', 1.0
+        cfg.b200.mlp_precision, cfg.perturb = args.precision, 1.0
         net.train()
         return out
 
@@ -329,9 +330,12 @@ def main():
 
     # =========================== rooflines from the per-op CUDA-event times ========================
     samples_local = rays_local * N_SAMPLES
-    fld_ms = op_ms.get('field_fwd_fp32', (0, 0))[0] + op_ms.get('field_bwd_fp32', (0, 0))[0]
+    sfx = '_' + args.precision
+    fld_ms = op_ms.get('field_fwd' + sfx, (0, 0))[0] + op_ms.get('field_bwd' + sfx, (0, 0))[0]
     achieved_tf = FLOPS_FWD_BWD * samples_local / (fld_ms * 1e-3) / 1e12 if fld_ms > 0 else 0.0
-    roofline = {'kernel': 'canonical field fwd+bwd (fp32 SIMT sgemm_kernel chain; the bf16 tcgen05 kernel is forward-only in round 1)',
+    kname = ('canonical field fwd+bwd: field_tc_kernel<store> + field_tc_bwd_kernel x2 + tile_wgrad_kernel (tcgen05, bf16)'
+             if args.precision == 'bf16' else 'canonical field fwd+bwd (fp32 SIMT sgemm_kernel chain)')
+    roofline = {'kernel': kname,
                 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peaks['tf_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ' (sustained bf16)',
                 'share_of_step': fld_ms / max(ev0.elapsed_time(ev1), 1e-9)}
@@ -340,7 +344,8 @@ def main():
     result = {
         'metric': 'train_step_rays_per_sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world),
+        'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': workload_config(world),
         'samples_per_sec': value * N_SAMPLES,
         'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},

@@ -61,7 +61,10 @@ def test_field_plan_sizes():
     # bf16 image (hidden layers carry one extra 16-row K step for the folded bias):
     nr = 48 * 128 + 3 * (128 + 16) * 128 + (128 + 48) * 128 + (128 + 16) * 128 + (128 + 16) * 16
     cn = 64 * 256 + 4 * (256 + 16) * 256 + (64 + 256) * 256 + 2 * (256 + 16) * 256 + (256 + 16) * 16
-    elems = nr + cn
+    # backward-data image: W^T windows, K = out features (16 for the output layers), N = width / pe_pad
+    nr_bwd = 16 * 128 + 5 * 128 * 128 + 2 * 128 * 48
+    cn_bwd = 16 * 256 + 7 * 256 * 256 + 2 * 256 * 64
+    elems = nr + cn + nr_bwd + cn_bwd
     assert 2 * elems < packed < 2 * elems + 64 * 1024
 
 
