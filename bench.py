@@ -165,6 +165,7 @@ def main():
     ap.add_argument('--warmup-ref', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='run the train step eagerly instead of as one CUDA graph')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='MLP arithmetic of the train step: bf16 tcgen05 kernels (default) or the fp32 SIMT parity path')
     args = ap.parse_args()
@@ -181,7 +182,7 @@ def main():
     from humannerf_b200.data import make_train_batch
     from humannerf_b200.network import Network
     from humannerf_b200.parallel import CutBReducer, allreduce_bucket
-    from humannerf_b200.training import PerceptualLoss, RenderLoss, make_optimizer, patch_scatter_index
+    from humannerf_b200.training import GraphedTrainStep, PerceptualLoss, RenderLoss, make_optimizer
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -247,19 +248,21 @@ def main():
     rng = np.random.RandomState(1000 + rank)
     host_batches = []
     for _ in range(total_steps):
-        b = make_train_batch(o_np, d_np, near_np, far_np, mask_np, subject, image_np, H, W, N_PATCHES, PATCH, rng)
-        hb = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items() if k != 'patch_div_indices'}
-        hb['n_rays'] = int(b['near'].shape[0])
+        b = make_train_batch(o_np, d_np, near_np, far_np, mask_np, subject, image_np, H, W, N_PATCHES, PATCH, rng,
+                             pad_rays=True)
+        hb = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items()
+              if k not in ('patch_div_indices', 'n_rays', 'patch_masks')}
+        hb['n_rays'] = int(b['n_rays'])
         host_batches.append(hb)
     h2d_bytes = int(np.mean([sum(v.numel() * v.element_size() for k, v in hb.items() if torch.is_tensor(v))
                              for hb in host_batches]))
     bg01 = fr['bgcolor'] / 255.0
     reducer = CutBReducer(net)
 
-    def train_step(batch, it):
+    def eager_step(batch, it):
         opt.zero_grad(set_to_none=True)
         out = net(rays=batch['rays'], near=batch['near'], far=batch['far'], iter_val=it, **frame_kw)
-        losses = crit(out['rgb'], batch['patch_masks'], bg01, batch['target_patches'])
+        losses = crit(out['rgb'], None, bg01, batch['target_patches'], index=batch['scatter_index'])
         loss = losses['total'] / world
         if world > 1:
             reducer.set_boundary(**net.boundary_tensors)
@@ -268,6 +271,17 @@ def main():
             loss.backward()
         opt.step()
         return losses['total']
+
+    graphed = None
+    if not args.eager:
+        graphed = GraphedTrainStep(net, crit, opt, frame_kw, bg01, N_PATCHES, PATCH, reducer=reducer, world=world)
+
+    def train_step(batch, it):
+        # batch: pinned host tensors (e2e leg) or device tensors (`value` leg); the graphed step copies
+        # them into its static input buffers, the eager step consumes device tensors directly
+        if graphed is not None:
+            return graphed(batch, it)
+        return eager_step(batch, it)
 
     def to_device(hb):
         return {k: v.to(dev, non_blocking=True) for k, v in hb.items() if torch.is_tensor(v)}
@@ -287,15 +301,16 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = _lib.launch_count()
-    ops.timing_start()
+    if graphed is None:
+        ops.timing_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.warmup, total_steps):
         train_step(dev_batches[i], it_val)
     ev1.record()
     barrier()
-    op_ms = ops.timing_stop()
-    launches = _lib.launch_count() - launches0
+    op_ms = ops.timing_stop() if graphed is None else {}
+    launches = (_lib.launch_count() - launches0) if graphed is None else graphed.launches_per_step * args.steps
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
     rays_local = sum(hb['n_rays'] for hb in host_batches[args.warmup:])
@@ -311,13 +326,14 @@ def main():
     value = rays_total / (ms / 1e3)
 
     # =========================== leg 2: end to end through the public API (`e2e`) =================
+    feed = (lambda hb: hb) if graphed is not None else to_device      # graphed: H2D straight into the static buffers
     for i in range(3):
-        train_step(to_device(host_batches[i]), it_val)
+        train_step(feed(host_batches[i]), it_val)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, total_steps):
-        loss_val = train_step(to_device(host_batches[i]), it_val)
+        loss_val = train_step(feed(host_batches[i]), it_val)
         _ = float(loss_val.item())                                     # device -> host read of the step's result
     e1.record()
     barrier()
@@ -329,6 +345,19 @@ def main():
     e2e = rays_total / (ms_e2e / 1e3)
 
     # =========================== rooflines from the per-op CUDA-event times ========================
+    # Kernels inside a replayed graph cannot be bracketed by events; the same steps are therefore run once
+    # more EAGERLY (same kernels, same inputs, per-op CUDA events on the launching stream).
+    roof_steps = args.steps
+    if graphed is not None:
+        roof_steps = min(args.steps, 5)
+        for i in range(2):
+            eager_step(dev_batches[i], it_val)
+        barrier()
+        ops.timing_start()
+        for i in range(args.warmup, args.warmup + roof_steps):
+            eager_step(dev_batches[i], it_val)
+        op_ms = ops.timing_stop()
+        rays_local = sum(hb['n_rays'] for hb in host_batches[args.warmup:args.warmup + roof_steps])
     samples_local = rays_local * N_SAMPLES
     sfx = '_' + args.precision
     fld_ms = op_ms.get('field_fwd' + sfx, (0, 0))[0] + op_ms.get('field_bwd' + sfx, (0, 0))[0]
@@ -338,7 +367,9 @@ def main():
     roofline = {'kernel': kname,
                 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peaks['tf_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ' (sustained bf16)',
-                'share_of_step': fld_ms / max(ev0.elapsed_time(ev1), 1e-9)}
+                'share_of_step': (fld_ms / roof_steps) / max(ms / args.steps, 1e-9),
+                'timed': 'per-op CUDA events' + (' in an eager re-run of the same steps (the timed region replays a CUDA graph)'
+                                                 if graphed is not None else ' inside the timed region')}
     op_table = {k: {'ms_total': round(v[0], 3), 'calls': v[1]} for k, v in sorted(op_ms.items())}
 
     result = {
@@ -349,6 +380,7 @@ def main():
         'samples_per_sec': value * N_SAMPLES,
         'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
+        'step_mode': 'eager' if graphed is None else 'cuda_graph (training.GraphedTrainStep)',
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'ops_ms': op_table,
         'valid_rays_in_frame': int(n_valid),
     }

@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-HN_ABI_VERSION = 1
+HN_ABI_VERSION = 2
 HN_MAX_LAYERS = 16
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
@@ -38,6 +38,10 @@ class WgradJob(C.Structure):
     _fields_ = [('dz', _p), ('x', _p), ('dw', _p), ('db', _p), ('f_dz', C.c_int32), ('f_x', C.c_int32),
                 ('m', C.c_int32), ('x_f0', C.c_int32), ('n', C.c_int32), ('n_valid', C.c_int32),
                 ('dw_ld', C.c_int32), ('dw_col0', C.c_int32), ('bias_col', C.c_int32), ('reserved', C.c_int32)]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [('param', _p), ('grad', _p), ('exp_avg', _p), ('exp_avg_sq', _p), ('numel', C.c_int64)]
 
 
 class FieldGrads(C.Structure):
@@ -68,6 +72,11 @@ SIGNATURES = {
                                  _p, _p, _i64, _p, _p, _i64, _p]),
     'hn_field_packed_bytes': (_i64, [C.POINTER(FieldParams)]),
     'hn_field_pack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
+    'hn_field_repack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
+    'hn_adam_plan_bytes': (_i64, [C.POINTER(AdamTensor), _int]),
+    'hn_adam_n_chunks': (_i64, [C.POINTER(AdamTensor), _int]),
+    'hn_adam_plan': (_int, [C.POINTER(AdamTensor), _int, _p, _i64]),
+    'hn_adam_step': (_int, [_p, _i64, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, _p]),
     'hn_composite_fwd': (_int, [_i64, _int] + [_p] * 15),
     'hn_composite_bwd': (_int, [_i64, _int] + [_p] * 12),
     'hn_tile_image_bytes': (_i64, [_i64, _int]),

@@ -161,6 +161,8 @@ _DEFAULTS: Dict[str, Any] = {
         # stratified-jitter noise: 'reference' = CPU default generator like network.py:468
         # (same random stream as the reference), 'device' = torch.rand on the GPU
         'jitter_rng': 'reference',
+        # one-launch multi-tensor Adam (csrc/adam.cu) instead of torch.optim.Adam's per-group kernels
+        'fused_adam': True,
     },
 }
 

@@ -405,6 +405,18 @@ int hn_field_pack_bf16(const hn_field_params* p, const float* cond, void* packed
   return launched("hn_field_pack_bf16");
 }
 
+int hn_field_repack_bf16(const hn_field_params* p, const float* cond, void* packed, void* stream) {
+  TcPlan plan;
+  HN_TRY(make_tc_plan(p, plan));
+  if (!packed) return fail_arg("hn_field_repack_bf16: null image");
+  if (p->cond_dim > 0 && !cond) return fail_arg("hn_field_repack_bf16: cond missing");
+  uint8_t* dst = static_cast<uint8_t*>(packed);
+  dim3 grid(8, (unsigned)plan.jobs.size());
+  pack_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const PackJob*>(dst + plan.jobs_off),
+                                                           (int)plan.jobs.size(), cond, dst + plan.hdr.image_off);
+  return launched("hn_field_repack_bf16");
+}
+
 int hn_field_fwd_fp32(const hn_field_params* p, int64_t n_samples, const float* x_skel, const float* cond,
                       const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
                       void* workspace, int64_t workspace_bytes, int save_for_backward, void* stream);

@@ -253,11 +253,9 @@ __global__ void outer_add_kernel(float* __restrict__ dw, int ld, int rows, int c
   dw[(int64_t)r * ld + c] += a[r] * b[c];
 }
 
-constexpr int kMaxWgradJobs = 4 * HN_MAX_LAYERS;
-
 static int64_t bwd_scratch_bytes(int64_t n) {
   const int64_t rows = ceil_div<int64_t>(std::max<int64_t>(n, 1), 128) * 128;
-  return 2 * rows * 4 * (int64_t)sizeof(float) + kMaxWgradJobs * (int64_t)sizeof(WgradJob) + 1024;
+  return 2 * rows * 4 * (int64_t)sizeof(float) + 1024;
 }
 
 }  // namespace hn
@@ -292,7 +290,6 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   const int64_t rows = ceil_div<int64_t>(n, 128) * 128;
   float* d_xyz_tot = static_cast<float*>(scratch);             // (n, 4)
   float* dz_nr = d_xyz_tot + rows * 4;                         // (n, 4)
-  WgradJob* jobs_dev = reinterpret_cast<WgradJob*>(dz_nr + rows * 4);
   float* dummy = d_xyz_tot;                                    // never written (n_valid = 0 jobs)
 
   int dev = 0, sms = 0;
@@ -358,11 +355,7 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
     }
   }
   if ((int)jobs.size() > kMaxWgradJobs) return fail_arg("hn_field_bwd_bf16: too many weight-gradient jobs");
-  if (!jobs.empty()) {
-    HN_TRY(check_cuda(cudaMemcpyAsync(jobs_dev, jobs.data(), jobs.size() * sizeof(WgradJob), cudaMemcpyHostToDevice, st),
-                      "hn_field_bwd_bf16/jobs"));
-    HN_TRY(launch_tile_wgrad(jobs_dev, (int)jobs.size(), n, st));
-  }
+  if (!jobs.empty()) HN_TRY(launch_tile_wgrad(jobs.data(), (int)jobs.size(), n, st));
   // 5. condition-code columns of the first non-rigid layer: the input is the same vector for every sample
   if (!ignore_non_rigid && p->cond_dim > 0 && g->nr_w[0] && g->nr_b[0]) {
     const int rows_w = p->nr_width, cols = p->cond_dim;

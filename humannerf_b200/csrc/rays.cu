@@ -234,7 +234,7 @@ __global__ void scatter_rows_kernel(int64_t n_rows, int C, const float* __restri
   if (i >= n_rows * C) return;
   int64_t r = i / C;
   int c = (int)(i - r * C);
-  out[idx[r] * C + c] = src[i];
+  if (idx[r] >= 0) out[idx[r] * C + c] = src[i];       // negative index = padding row, skipped
 }
 
 __global__ void gather_rows_kernel(int64_t n_rows, int C, const float* __restrict__ src,
@@ -243,7 +243,7 @@ __global__ void gather_rows_kernel(int64_t n_rows, int C, const float* __restric
   if (i >= n_rows * C) return;
   int64_t r = i / C;
   int c = (int)(i - r * C);
-  out[i] = src[idx[r] * C + c];
+  out[i] = idx[r] >= 0 ? src[idx[r] * C + c] : 0.0f;   // negative index = padding row
 }
 
 }  // namespace hn

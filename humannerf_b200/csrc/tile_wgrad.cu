@@ -14,6 +14,7 @@
 // Replaces the autograd of nn.Linear in reference non_rigid_motion_mlps/mlp_offset.py:74-84 and
 // canonical_mlps/mlp_rgb_sigma.py:163-166,198 on the bf16 path.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "tc_common.cuh"
@@ -32,8 +33,15 @@ constexpr int kWgThreads = 6 * 32;                                    // produce
 // MN-major for both operands: bits 15 / 16 of the instruction descriptor
 __device__ __forceinline__ uint32_t make_idesc_mn(uint32_t n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
 
+// The job list travels as a kernel parameter (constant bank): no host->device copy, so a launch can be
+// captured in a CUDA graph.
+struct WgradJobTable {
+  WgradJob jobs[kMaxWgradJobs];
+};
+
 __global__ void __launch_bounds__(kWgThreads, 1)
-tile_wgrad_kernel(const WgradJob* __restrict__ jobs, int n_jobs, int n_tiles, int tiles_per_slab) {
+tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles, int tiles_per_slab) {
+  const WgradJob* jobs = tab.jobs;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_full = s_base + kWgBarOff;
@@ -212,8 +220,12 @@ __global__ void tile_unpack_kernel(int64_t n_samples, int n_feat, int f_pad, con
   }
 }
 
-int launch_tile_wgrad(const WgradJob* jobs_dev, int n_jobs, int64_t n_samples, cudaStream_t st) {
+int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, cudaStream_t st) {
   if (n_jobs <= 0 || n_samples <= 0) return 0;
+  if (n_jobs > kMaxWgradJobs) return fail_arg("tile_wgrad: at most %d jobs per launch", kMaxWgradJobs);
+  WgradJobTable tab;
+  memset(&tab, 0, sizeof(tab));
+  memcpy(tab.jobs, jobs_host, (size_t)n_jobs * sizeof(WgradJob));
   int dev = 0, sms = 0;
   HN_TRY(check_cuda(cudaGetDevice(&dev), "tile_wgrad/device"));
   HN_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "tile_wgrad/attr"));
@@ -225,7 +237,7 @@ int launch_tile_wgrad(const WgradJob* jobs_dev, int n_jobs, int64_t n_samples, c
   const int tiles_per_slab = (n_tiles + n_slabs - 1) / n_slabs;
   n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
   const int grid = std::min(n_jobs * n_slabs, sms);
-  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(jobs_dev, n_jobs, n_tiles, tiles_per_slab);
+  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, tiles_per_slab);
   return launched("tile_wgrad");
 }
 
@@ -273,13 +285,13 @@ int hn_tile_unpack(int64_t n_samples, int n_features, int n_features_padded, con
 int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, void* jobs_scratch_dev,
                   void* stream) {
   if (n_jobs == 0 || n_samples == 0) return 0;
-  if (n_jobs < 0 || n_samples < 0 || !jobs_host || !jobs_scratch_dev) return fail_arg("hn_tile_wgrad: bad argument");
-  static_assert(sizeof(hn_wgrad_job) == sizeof(WgradJob), "job layouts must agree");
+  (void)jobs_scratch_dev;
+  if (n_jobs < 0 || n_samples < 0 || !jobs_host) return fail_arg("hn_tile_wgrad: bad argument");
   for (int i = 0; i < n_jobs; ++i) HN_TRY(check_job(jobs_host[i]));
   cudaStream_t st = as_stream(stream);
-  HN_TRY(check_cuda(cudaMemcpyAsync(jobs_scratch_dev, jobs_host, (size_t)n_jobs * sizeof(hn_wgrad_job),
-                                    cudaMemcpyHostToDevice, st), "hn_tile_wgrad/jobs"));
-  return launch_tile_wgrad(static_cast<const WgradJob*>(jobs_scratch_dev), n_jobs, n_samples, st);
+  for (int i = 0; i < n_jobs; i += kMaxWgradJobs)
+    HN_TRY(launch_tile_wgrad(jobs_host + i, std::min(kMaxWgradJobs, n_jobs - i), n_samples, st));
+  return 0;
 }
 
 }  // extern "C"

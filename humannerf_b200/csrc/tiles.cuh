@@ -16,6 +16,9 @@ __host__ __device__ __forceinline__ size_t tile_offset(int64_t s, int f, int f_p
          (size_t)(r & 15) * 16 + (size_t)(f & 7) * 2;
 }
 
-int launch_tile_wgrad(const WgradJob* jobs_dev, int n_jobs, int64_t n_samples, cudaStream_t st);
+constexpr int kMaxWgradJobs = 48;   // per launch: the table is a kernel parameter (48 x 72 B < 4 KB)
+
+// jobs_host: HOST array of n_jobs <= kMaxWgradJobs jobs
+int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, cudaStream_t st);
 
 }  // namespace hn

@@ -38,15 +38,35 @@ def sample_patches(ray_mask: np.ndarray, subject_mask: np.ndarray, H: int, W: in
 
 def make_train_batch(rays_o: np.ndarray, rays_d: np.ndarray, near: np.ndarray, far: np.ndarray,
                      ray_mask: np.ndarray, subject_mask: np.ndarray, image: np.ndarray, H: int, W: int,
-                     n_patches: int, patch_size: int, rng: np.random.RandomState) -> Dict[str, np.ndarray]:
-    """rays_o / rays_d / near / far are the COMPACTED per-ray arrays (ray_mask order)."""
+                     n_patches: int, patch_size: int, rng: np.random.RandomState,
+                     pad_rays: bool = False) -> Dict[str, np.ndarray]:
+    """rays_o / rays_d / near / far are the COMPACTED per-ray arrays (ray_mask order).
+
+    `scatter_index[r]` is the flat pixel (patch, y, x) ray r lands on (what `patch_imgs[i, patch_masks[i]] =
+    rgbs[div[i]:div[i+1]]` does in trainer.py:35), computed here on the host so the step needs no
+    device-side `nonzero`.  With `pad_rays` every per-ray array is padded to n_patches * patch_size**2
+    rows (zero rays, near = far = 0, scatter_index = -1: the scatter skips them, so they get no
+    gradient) - fixed shapes for the CUDA-graph train step; `n_rays` is the number of real rays."""
     sel, masks, div, xy = sample_patches(ray_mask, subject_mask, H, W, n_patches, patch_size, rng)
     targets = np.stack([image[y:y + patch_size, x:x + patch_size] for x, y in xy], axis=0)
+    rays = np.stack([rays_o[sel], rays_d[sel], rays_d[sel]], axis=0)
+    near_s = near[sel].reshape(-1, 1).astype(np.float32)
+    far_s = far[sel].reshape(-1, 1).astype(np.float32)
+    index = np.nonzero(masks.reshape(-1))[0].astype(np.int64)
+    n = int(sel.shape[0])
+    if pad_rays:
+        cap = n_patches * patch_size * patch_size
+        rays = np.concatenate([rays, np.zeros((3, cap - n, 3), rays.dtype)], axis=1)
+        near_s = np.concatenate([near_s, np.zeros((cap - n, 1), np.float32)], axis=0)
+        far_s = np.concatenate([far_s, np.zeros((cap - n, 1), np.float32)], axis=0)
+        index = np.concatenate([index, np.full(cap - n, -1, np.int64)])
     return {
-        'rays': np.stack([rays_o[sel], rays_d[sel], rays_d[sel]], axis=0),
-        'near': near[sel].reshape(-1, 1).astype(np.float32),
-        'far': far[sel].reshape(-1, 1).astype(np.float32),
+        'rays': rays,
+        'near': near_s,
+        'far': far_s,
         'patch_masks': masks,
         'patch_div_indices': div,
         'target_patches': targets.astype(np.float32),
+        'scatter_index': index,
+        'n_rays': np.asarray(n, dtype=np.int64),
     }

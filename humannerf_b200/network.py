@@ -140,6 +140,7 @@ class Network(nn.Module):
             nr_freqs=nr_cfg.multires, cond_dim=nr_cfg.condition_code_size,
             cn_layers=len(cn.linear_layers()), cn_width=cn_cfg.mlp_width, cn_skip=cn.skip_layer_index(),
             cn_freqs=cn_cfg.multires)
+        self._packed_field = ops.PackedField(self._spec)
         self._vol_cache = None
         self.motion_weights_vol = None
         self.boundary_tensors = {}
@@ -195,9 +196,15 @@ class Network(nn.Module):
         # 2. condition code and hann window (network.py:697-738)
         nr_cfg = cfg.non_rigid_motion_mlp
         cond = dst_posevec[0]
-        if it < nr_cfg.kick_in_iter:
-            cond = torch.zeros_like(cond)
-        hann = hann_window_weights(it, nr_cfg.multires, nr_cfg.kick_in_iter, nr_cfg.full_band_iter).to(dev)
+        if kwargs.get('b200_hann_w') is not None:
+            # schedule values supplied as DEVICE tensors (training.GraphedTrainStep): the hann window (6,)
+            # and the 0/1 factor that zeroes the condition code before kick-in - no host->device copy
+            hann = kwargs['b200_hann_w']
+            cond = cond * kwargs['b200_cond_gate']
+        else:
+            if it < nr_cfg.kick_in_iter:
+                cond = torch.zeros_like(cond)
+            hann = hann_window_weights(it, nr_cfg.multires, nr_cfg.kick_in_iter, nr_cfg.full_band_iter).to(dev)
 
         # 3. motion bases and blend-weight volume (network.py:757-763)
         scale_Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts, cnl_gtfms)
@@ -229,7 +236,7 @@ class Network(nn.Module):
         nr_w, nr_b, cn_w, cn_b = self._field_weights()
         packed = None
         if precision == _lib.PRECISION_BF16:
-            packed = ops.pack_field_bf16(self._spec, nr_w, nr_b, cn_w, cn_b, cond)
+            packed = self._packed_field.refresh(nr_w, nr_b, cn_w, cn_b, cond)
 
         outs = []
         R = rays_o.shape[0]

@@ -112,5 +112,14 @@ class MotionBasisComputer(nn.Module):
         for i in range(1, J):
             glob.append(torch.matmul(glob[SMPL_PARENT[i]], local[:, i]))
         glob = torch.stack(glob, dim=1).view(-1, 4, 4)
-        f = torch.matmul(cnl_gtfms.reshape(-1, 4, 4), torch.inverse(glob)).view(B, J, 4, 4)
+        # The reference calls torch.inverse (LU, network_util.py:148), which synchronises with the host
+        # to check for singular matrices.  Every global transform is rigid (a product of [R t; 0 1] with
+        # R a rotation), so the inverse is [R^T  -R^T t; 0 1] exactly; the two agree to fp32 rounding
+        # and this form has no host synchronisation (CUDA-graph capturable).
+        Rt = glob[:, :3, :3].transpose(1, 2)
+        inv = torch.zeros_like(glob)
+        inv[:, :3, :3] = Rt
+        inv[:, :3, 3] = -torch.matmul(Rt, glob[:, :3, 3:4])[..., 0]
+        inv[:, 3, 3] = 1.0
+        f = torch.matmul(cnl_gtfms.reshape(-1, 4, 4), inv).view(B, J, 4, 4)
         return f[:, :, :3, :3], f[:, :, :3, 3]

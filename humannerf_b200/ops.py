@@ -251,6 +251,30 @@ def pack_field_bf16(spec: FieldSpec, nr_w, nr_b, cn_w, cn_b, cond: torch.Tensor)
     return packed
 
 
+class PackedField:
+    """Persistent bf16 weight image.  The first `refresh` (and any later one after a parameter moved)
+    builds the image with its tables; every other `refresh` only re-runs the conversion kernel on the
+    same buffer (`hn_field_repack_bf16`: no allocation, no host->device copy, CUDA-graph capturable)."""
+
+    def __init__(self, spec: FieldSpec):
+        self.spec, self.image, self._key = spec, None, None
+
+    def refresh(self, nr_w, nr_b, cn_w, cn_b, cond: torch.Tensor) -> torch.Tensor:
+        ws = [_f32c(t.detach()) for t in list(nr_w) + list(nr_b) + list(cn_w) + list(cn_b)]
+        key = tuple(t.data_ptr() for t in ws)
+        if self.image is None or key != self._key:
+            self.image = pack_field_bf16(self.spec, nr_w, nr_b, cn_w, cn_b, cond)
+            self._key = key
+            return self.image
+        lib = _lib.load()
+        nl, cl = self.spec.nr_layers, self.spec.cn_layers
+        fp = self.spec.params(ws[:nl], ws[nl:2 * nl], ws[2 * nl:2 * nl + cl], ws[2 * nl + cl:])
+        cond = _f32c(cond.detach()).reshape(-1)
+        with torch.cuda.device(cond.device):
+            check(lib.hn_field_repack_bf16(C.byref(fp), ptr(cond), ptr(self.image), stream_ptr()), 'field_repack_bf16')
+        return self.image
+
+
 class _CanonicalField(torch.autograd.Function):
     """inputs: x_skel (P,3), cond (cond_dim), hann_w (nr_freqs), then the flat parameter list
     [nr_w..., nr_b..., cn_w..., cn_b...]."""

@@ -122,7 +122,10 @@ class CutBReducer:
         allreduce_bucket(grads, group=group)
         n_mlp = len(self.mlp_params)
         for p, g in zip(self.mlp_params, grads[:n_mlp]):
-            p.grad = g if p.grad is None else p.grad + g
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)          # in place: keeps the flat-buffer views of training.FusedAdam
         b_tensors = list(self.boundary.values())
         b_grads = grads[n_mlp:]
         live = [(t, g) for t, g in zip(b_tensors, b_grads) if t.requires_grad]

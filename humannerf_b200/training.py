@@ -72,6 +72,8 @@ class RenderLoss(nn.Module):
         self.perceptual = perceptual
 
     def forward(self, rgb, patch_masks, bgcolor01, targets, index=None) -> Dict[str, torch.Tensor]:
+        """`index` (R,) = flat destination pixel of every ray (-1: padding ray); when given, `patch_masks`
+        is not needed (and no device-side nonzero / host sync happens)."""
         w = get_cfg().train.lossweights
         imgs = unpack_imgs(rgb, patch_masks, bgcolor01, targets, index=index)
         losses = {}
@@ -86,9 +88,106 @@ class RenderLoss(nn.Module):
         return losses
 
 
-def make_optimizer(network: nn.Module) -> torch.optim.Optimizer:
-    """Adam with one group per tensor and per-name learning rates (optimizer.py:12-43): a parameter
-    whose name contains `mweight_vol_decoder` / `pose_decoder` / `non_rigid_mlp` uses cfg.train.lr_<name>."""
+class FusedAdam(torch.optim.Optimizer):
+    """Adam over all parameter tensors in ONE kernel launch (`hn_adam_step`, csrc/adam.cu).
+
+    Same constructor groups and update rule as the `torch.optim.Adam` the reference builds
+    (optimizer.py:12-43: one group per tensor, per-name learning rates); `param_groups[i]['lr']` stays
+    the knob `update_lr` turns.  Differences in mechanism, not arithmetic:
+
+    * gradients, first and second moments live in three flat fp32 buffers owned by the optimizer;
+      `p.grad` and `state[p]['exp_avg' / 'exp_avg_sq']` are views into them, so `zero_grad()` is one
+      memset (it never sets `.grad` to None) and the kernel's pointer table is built once;
+    * step counts, learning rates, an optional global `lr_scale` and the per-tensor `active` mask are
+      read from device memory, so a step captured in a CUDA graph follows the schedule on replay;
+    * a tensor whose `active` entry is 0 is skipped like a parameter whose `.grad` is None.
+    """
+
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        import ctypes as C
+        from humannerf_b200 import _lib
+        self._lib = _lib
+        ps = [p for g in self.param_groups for p in g['params']]
+        if not ps or any(not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() for p in ps):
+            raise RuntimeError('FusedAdam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)')
+        if len({(g['betas'], g['eps']) for g in self.param_groups}) != 1:
+            raise RuntimeError('FusedAdam: betas / eps must be the same for every group')
+        dev = ps[0].device
+        self._ps = ps
+        offs, total = [], 0
+        for p in ps:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4                # keep every view 16-byte aligned
+        self.flat_grad = torch.zeros(total, device=dev)
+        self._flat_m = torch.zeros(total, device=dev)
+        self._flat_v = torch.zeros(total, device=dev)
+        self.step_dev = torch.zeros(len(ps), device=dev)         # per-tensor step counts (floats)
+        self.active = torch.ones(len(ps), device=dev)            # 0 = skip this tensor
+        self.lr_scale: Optional[torch.Tensor] = None             # optional (1,) device factor on every lr
+        self._grad_views = []
+        table = (_lib.AdamTensor * len(ps))()
+        for i, (p, o) in enumerate(zip(ps, offs)):
+            n = p.numel()
+            gv = self.flat_grad[o:o + n].view_as(p)
+            p.grad = gv
+            self._grad_views.append(gv)
+            self.state[p] = {'step': self.step_dev[i:i + 1], 'exp_avg': self._flat_m[o:o + n].view_as(p),
+                             'exp_avg_sq': self._flat_v[o:o + n].view_as(p)}
+            table[i].param, table[i].grad = p.data_ptr(), gv.data_ptr()
+            table[i].exp_avg, table[i].exp_avg_sq = self._flat_m[o:o + n].data_ptr(), self._flat_v[o:o + n].data_ptr()
+            table[i].numel = n
+        lib = _lib.load()
+        nbytes = int(lib.hn_adam_plan_bytes(table, len(ps)))
+        self._n_chunks = int(lib.hn_adam_n_chunks(table, len(ps)))
+        host = torch.empty(nbytes, dtype=torch.uint8)
+        _lib.check(lib.hn_adam_plan(table, len(ps), host.data_ptr(), nbytes), 'adam_plan')
+        self._plan = host.to(dev)
+        self._lr_cache = None
+        self._lr_dev = torch.zeros(len(ps), device=dev)
+        self._sync_lr()
+
+    def _lrs(self):
+        return [float(g['lr']) for g in self.param_groups for _ in g['params']]
+
+    def _sync_lr(self):
+        lrs = self._lrs()
+        if lrs != self._lr_cache:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('FusedAdam: param_groups lr changed during CUDA graph capture; use lr_scale')
+            self._lr_dev.copy_(torch.tensor(lrs, dtype=torch.float32))
+            self._lr_cache = lrs
+
+    def zero_grad(self, set_to_none: bool = True):
+        """One memset; `.grad` stays a view of the flat buffer (set_to_none is ignored on purpose)."""
+        self.flat_grad.zero_()
+        for p, gv in zip(self._ps, self._grad_views):
+            if p.grad is not gv:
+                p.grad = gv
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for p, gv in zip(self._ps, self._grad_views):
+            if p.grad is None:
+                gv.zero_()
+                p.grad = gv
+            elif p.grad is not gv and p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)             # someone replaced .grad: fold it back into the flat buffer
+                p.grad = gv
+        self._sync_lr()
+        self.step_dev.add_(self.active)
+        g0 = self.param_groups[0]
+        lib, ptr = self._lib.load(), self._lib.ptr
+        with torch.cuda.device(self._plan.device):
+            self._lib.check(lib.hn_adam_step(ptr(self._plan), self._n_chunks, ptr(self._lr_dev), ptr(self.lr_scale),
+                                             ptr(self.step_dev), ptr(self.active), float(g0['betas'][0]),
+                                             float(g0['betas'][1]), float(g0['eps']), self._lib.stream_ptr()),
+                            'adam_step')
+        return loss
+
+
+def _param_groups(network: nn.Module):
     cfg = get_cfg()
     custom = [k[3:] for k in cfg.train.keys() if k.startswith('lr_')]
     groups = []
@@ -100,6 +199,20 @@ def make_optimizer(network: nn.Module) -> torch.optim.Optimizer:
             groups.append({'params': [p], 'lr': cfg.train[f'lr_{lr_name}'], 'name': lr_name})
         else:
             groups.append({'params': [p], 'name': name})
+    return groups
+
+
+def make_optimizer(network: nn.Module, fused: Optional[bool] = None) -> torch.optim.Optimizer:
+    """Adam with one group per tensor and per-name learning rates (optimizer.py:12-43): a parameter
+    whose name contains `mweight_vol_decoder` / `pose_decoder` / `non_rigid_mlp` uses cfg.train.lr_<name>.
+    On a CUDA network this is the single-launch `FusedAdam` (cfg.b200.fused_adam, default on)."""
+    cfg = get_cfg()
+    groups = _param_groups(network)
+    on_cuda = all(p.is_cuda for g in groups for p in g['params'])
+    if fused is None:
+        fused = bool(cfg.get('b200', {}).get('fused_adam', True))
+    if fused and on_cuda:
+        return FusedAdam(groups, lr=cfg.train.lr, betas=(0.9, 0.999))
     return torch.optim.Adam(groups, lr=cfg.train.lr, betas=(0.9, 0.999))
 
 
@@ -110,3 +223,138 @@ def update_lr(optimizer: torch.optim.Optimizer, iter_step: int) -> None:
     for g in optimizer.param_groups:
         base = cfg.train[f"lr_{g['name']}"] if f"lr_{g['name']}" in cfg.train else cfg.train.lr
         g['lr'] = base * decay
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole train step as one CUDA graph
+# ---------------------------------------------------------------------------------------------
+class GraphedTrainStep:
+    """forward + loss + backward (+ gradient all-reduce) + Adam of `trainer.py:194-220` captured once in
+    a CUDA graph and replayed per step: an eager step is ~1350 kernel launches and is bound by the
+    host's launch rate (19 ms of host time for ~11 ms of GPU work); a replay is one launch.
+
+    What makes the step capturable:
+    * fixed shapes - batches come padded to `n_patches * patch_size**2` rays (data.make_train_batch
+      `pad_rays=True`): padding rays have near = far = 0 and scatter_index = -1, render something that
+      is never looked at and receive exactly zero gradient;
+    * no host<->device traffic inside - the step-dependent scalars (hann window of the non-rigid
+      encoding, condition-code gate, learning-rate decay) live in one small device tensor that
+      `__call__` refreshes from pinned host memory before the replay; the bf16 weight image is
+      re-packed by a kernel (ops.PackedField); Adam is the one-launch FusedAdam with device-side step
+      counts; the rigid inverse of the motion bases is analytic (no LU `info` check);
+    * inputs are copied into static device buffers before the replay (`load`).
+
+    The loss returned by `__call__` is a static device scalar (valid until the next call).
+    """
+
+    def __init__(self, net: nn.Module, crit: nn.Module, opt: 'FusedAdam', frame_kw: Dict[str, torch.Tensor],
+                 bgcolor01: torch.Tensor, n_patches: int, patch_size: int, reducer=None, world: int = 1,
+                 rays_dtype: torch.dtype = torch.float64):
+        if not isinstance(opt, FusedAdam):
+            raise RuntimeError('GraphedTrainStep needs the FusedAdam optimizer (device-side schedule)')
+        cfg = get_cfg()
+        if cfg.perturb > 0 and str(cfg.get('b200', {}).get('jitter_rng', 'reference')) != 'device':
+            raise RuntimeError("GraphedTrainStep: set cfg.b200.jitter_rng = 'device' (the reference draws the "
+                               "stratified jitter on the CPU generator, which cannot be captured in a CUDA graph)")
+        self.net, self.crit, self.opt, self.frame_kw, self.bg01 = net, crit, opt, frame_kw, bgcolor01
+        self.reducer, self.world = reducer, world
+        dev = bgcolor01.device
+        self.cap = n_patches * patch_size * patch_size
+        self.rays = torch.zeros(3, self.cap, 3, dtype=rays_dtype, device=dev)
+        self.near = torch.zeros(self.cap, 1, device=dev)
+        self.far = torch.zeros(self.cap, 1, device=dev)
+        self.index = torch.full((self.cap,), -1, dtype=torch.int64, device=dev)
+        self.targets = torch.zeros(n_patches, patch_size, patch_size, 3, device=dev)
+        nf = int(cfg.non_rigid_motion_mlp.multires)
+        self._nf = nf
+        self.sched = torch.zeros(nf + 2, device=dev)                  # [hann (nf) | cond gate | lr scale]
+        self._sched_host = torch.zeros(nf + 2).pin_memory()
+        opt.lr_scale = self.sched[nf + 1:nf + 2]
+        self._base_lrs = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss: Optional[torch.Tensor] = None
+        self.launches_per_step = 0
+        self._iter_cfg = None
+
+    # -- per-step host work ---------------------------------------------------------------
+    def _set_schedule(self, iter_step: int) -> None:
+        from humannerf_b200.embedders.hannw_fourier import hann_window_weights
+        cfg = get_cfg()
+        nr = cfg.non_rigid_motion_mlp
+        h = self._sched_host
+        h[:self._nf] = hann_window_weights(iter_step, self._nf, nr.kick_in_iter, nr.full_band_iter)
+        h[self._nf] = 0.0 if iter_step < nr.kick_in_iter else 1.0
+        h[self._nf + 1] = 0.1 ** (iter_step / (cfg.train.lrate_decay * 1000))      # exp_decay.py:7-16
+        self.sched.copy_(h, non_blocking=True)
+        pose_on = (not cfg.pose_decoder_off) and iter_step >= cfg.pose_decoder.get('kick_in_iter', 0)
+        if self._iter_cfg is None:
+            self._iter_cfg = pose_on
+        elif self._iter_cfg != pose_on:
+            self.graph = None                   # the pose decoder switched on: the captured graph is stale
+            self._iter_cfg = pose_on
+
+    def load(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Copy a padded batch (host pinned or device tensors) into the static input buffers."""
+        if batch['near'].shape[0] != self.cap:
+            raise RuntimeError(f'GraphedTrainStep: batch has {batch["near"].shape[0]} rays, expected the padded '
+                               f'{self.cap} (data.make_train_batch(pad_rays=True))')
+        self.rays.copy_(batch['rays'], non_blocking=True)
+        self.near.copy_(batch['near'], non_blocking=True)
+        self.far.copy_(batch['far'], non_blocking=True)
+        self.index.copy_(batch['scatter_index'], non_blocking=True)
+        self.targets.copy_(batch['target_patches'], non_blocking=True)
+
+    # -- the step -----------------------------------------------------------------------
+    def _body(self, iter_step: int) -> torch.Tensor:
+        self.opt.zero_grad()
+        out = self.net(rays=self.rays, near=self.near, far=self.far, iter_val=iter_step,
+                       b200_hann_w=self.sched[:self._nf], b200_cond_gate=self.sched[self._nf:self._nf + 1],
+                       **self.frame_kw)
+        losses = self.crit(out['rgb'], None, self.bg01, self.targets, index=self.index)
+        loss = losses['total'] / self.world
+        if self.world > 1 and self.reducer is not None:
+            self.reducer.set_boundary(**self.net.boundary_tensors)
+            self.reducer.exchange_and_finish(loss)
+        else:
+            loss.backward()
+        self.opt.step()
+        return losses['total'].detach()
+
+    def _capture(self, iter_step: int) -> None:
+        from humannerf_b200 import _lib
+        # learning rates: the graph multiplies the BASE rates by the device-side decay factor
+        cfg = get_cfg()
+        for g in self.opt.param_groups:
+            g['lr'] = cfg.train[f"lr_{g['name']}"] if f"lr_{g['name']}" in cfg.train else cfg.train.lr
+        # the warm-up iterations below are real optimizer steps on the loaded batch; undo them afterwards
+        # so that capture has no side effect on the training state
+        snap_p = [p.detach().clone() for p in self.opt._ps]
+        snap = (self.opt._flat_m.clone(), self.opt._flat_v.clone(), self.opt.step_dev.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._body(iter_step)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self.loss = self._body(iter_step)
+        self.launches_per_step = _lib.launch_count() - n0
+        with torch.no_grad():
+            for p, q in zip(self.opt._ps, snap_p):
+                p.copy_(q)
+            self.opt._flat_m.copy_(snap[0])
+            self.opt._flat_v.copy_(snap[1])
+            self.opt.step_dev.copy_(snap[2])
+        self.graph = graph
+
+    def __call__(self, batch: Optional[Dict[str, torch.Tensor]], iter_step: int) -> torch.Tensor:
+        self._set_schedule(int(iter_step))
+        if batch is not None:
+            self.load(batch)
+        if self.graph is None:
+            self._capture(int(iter_step))
+        self.graph.replay()
+        return self.loss

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 1
+#define HN_ABI_VERSION 2
 #define HN_MAX_LAYERS 16
 
 /* ABI version of the loaded library (compare with HN_ABI_VERSION). */
@@ -177,6 +177,10 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
  * non-rigid bias (W0[:, :cond_dim] . cond + b0 is constant per frame, mlp_offset.py:75-77). */
 int64_t hn_field_packed_bytes(const hn_field_params* p);
 int hn_field_pack_bf16(const hn_field_params* p, const float* cond, void* packed, void* stream);
+/* Refresh the image after the weights / cond changed IN PLACE (same pointers as the hn_field_pack_bf16
+ * call that initialised `packed`): one conversion kernel, no host->device copies, so it can be captured
+ * in a CUDA graph (a training step re-packs the weights the optimizer just updated). */
+int hn_field_repack_bf16(const hn_field_params* p, const float* cond, void* packed, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a15  core/nets/human_nerf/network.py:355-388  _raw2outputs
@@ -200,6 +204,7 @@ int hn_composite_bwd(int64_t n_rays, int n_samples, const float* raw, const floa
  * a16  core/train/trainers/human_nerf/trainer.py:28-37 _unpack_imgs and run.py:49-65
  * Scatter per-ray values (R,C) into a dense image / patch stack pre-filled with `fill` (C floats,
  * device): out[dst_index[r]*C + c] = src[r*C + c].  And the matching gather for the backward.
+ * A negative index marks a padding row: the scatter skips it, the gather returns 0 for it.
  */
 int hn_scatter_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* dst_index,
                     float* out, void* stream);
@@ -240,9 +245,37 @@ int hn_tile_pack(int64_t n_samples, int n_features, int n_features_padded, const
                  void* image, void* stream);
 int hn_tile_unpack(int64_t n_samples, int n_features, int n_features_padded, const void* image, float* dst,
                    int64_t ld, void* stream);
-/* jobs_host: host array; jobs_scratch_dev: device scratch of n_jobs * sizeof(hn_wgrad_job) bytes. */
+/* jobs_host: host array (travels to the kernel as a launch parameter, at most 48 jobs per launch;
+ * longer lists are split).  jobs_scratch_dev is unused since ABI 2 and may be NULL. */
 int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, void* jobs_scratch_dev,
                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a17  core/train/optimizers/human_nerf/optimizer.py:12-43 (Adam, one group per tensor) and
+ *      core/train/lr_updaters/exp_decay.py:7-16 (per-step learning-rate decay)
+ * Fused multi-tensor Adam: one launch for all tensors.  hn_adam_plan writes a plan (tensor table +
+ * chunk table) into HOST memory; the caller copies it to the device once.  The step reads, from DEVICE
+ * memory, lr_dev[n_tensors] (per-tensor learning rates), lr_scale_dev (nullable global factor),
+ * step_dev[n_tensors] (1-based step count of each tensor, as floats) and active_dev[n_tensors]
+ * (nullable; 0 = leave the tensor and its moments untouched, like torch skipping a parameter whose
+ * .grad is None), so a captured launch follows the schedule.
+ * Update rule = torch.optim.Adam(amsgrad=False, weight_decay=0).
+ */
+typedef struct hn_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} hn_adam_tensor;
+
+int64_t hn_adam_plan_bytes(const hn_adam_tensor* tensors_host, int n_tensors);
+int hn_adam_plan(const hn_adam_tensor* tensors_host, int n_tensors, void* plan_host, int64_t plan_bytes);
+/* n_chunks = (plan_bytes - chunk table offset) / 8 is returned by hn_adam_n_chunks. */
+int64_t hn_adam_n_chunks(const hn_adam_tensor* tensors_host, int n_tensors);
+int hn_adam_step(const void* plan_dev, int64_t n_chunks, const float* lr_dev, const float* lr_scale_dev,
+                 const float* step_dev, const float* active_dev, float beta1, float beta2, float eps,
+                 void* stream);
 
 #ifdef __cplusplus
 }
