@@ -438,9 +438,19 @@ def main():
                                   'sample': f'oracle fwd + MSE-style loss + bwd on the first {R} rays x {N_SAMPLES} samples of one step '
                                             f'(no LPIPS/Adam), best of 2 after 1 warm-up'}
     if rank == 0:
-        print(json.dumps(result))
+        print(json.dumps(result), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down in a fixed order: the captured graph holds NCCL kernels, and destroying the process
+        # group while it is alive hung a 2-GPU run at exit.  Drop the graph, drain the device, meet at a
+        # barrier, then leave without running the communicator destructors (the result is already out).
+        if graphed is not None:
+            graphed.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
