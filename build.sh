@@ -7,6 +7,8 @@ OUT=humannerf_b200/lib
 mkdir -p "$OUT" build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v"
+# HN_TC_PROFILE=1 ./build.sh compiles the per-role cycle counters into the tcgen05 forward kernel (measurement builds only)
+if [ "${HN_TC_PROFILE:-0}" = "1" ]; then FLAGS="$FLAGS -DHN_TC_PROFILE"; fi
 objs=()
 pids=()
 for f in api rays motion_field composite field_fp32 mlp_tc mlp_tc_bwd tile_wgrad adam; do

@@ -55,13 +55,14 @@ SIGNATURES = {
     'hn_last_error': (C.c_char_p, []),
     'hn_launch_count': (_i64, []),
     'hn_has_tcgen05': (_int, []),
+    'hn_debug_tc_prof': (_int, [_p]),
     'hn_gen_rays': (_int, [_int, _int, _p, _p, _p, _p, _p]),
     'hn_rays_bbox': (_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     'hn_compact_rays_workspace_bytes': (_i64, [_i64]),
     'hn_compact_rays': (_int, [_i64] + [_p] * 13),
     'hn_sample_z': (_int, [_i64, _int, _p, _p, _p, _p, _p, _p]),
     'hn_motion_field_fwd': (_int, [_i64, _int, _int, _int] + [_p] * 13),
-    'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 16),
+    'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 18),
     'hn_field_workspace_bytes': (_i64, [C.POINTER(FieldParams), _i64, _int, _int]),
     'hn_field_fwd': (_int, [C.POINTER(FieldParams), _i64, _p, _p, _p, _int, _p, _p, _p, _p, _i64, _int, _int, _p, _p]),
     'hn_field_bwd_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),

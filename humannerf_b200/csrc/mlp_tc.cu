@@ -22,6 +22,8 @@
 //
 // Reference semantics: embedders/hannw_fourier.py:38-49, embedders/fourier.py:9-38,
 // non_rigid_motion_mlps/mlp_offset.py:74-114, canonical_mlps/mlp_rgb_sigma.py:132-206.
+#include <cstdlib>
+
 #include "mlp_tc_plan.cuh"
 
 namespace hn {
@@ -77,13 +79,34 @@ __device__ __forceinline__ void write_encoding(uint32_t region, int row, int hal
 }
 
 // ------------------------------------------------------------------------------------------
+// Cycle accounting of block 0 (measurement aid, active only with HN_TC_ABLATE & 8):
+//  [0..3]  producer: total, wait-empty
+//  [4..9]  issuer tile 0: total, wait a_ready, wait full, issue ; [10..15] issuer tile 1
+//  [16..21] epilogue thread (tile 0, quarter 0, half 0, lane 0): total, wait acc, encoding, hidden, out
+// ------------------------------------------------------------------------------------------
+// Compiled in only with -DHN_TC_PROFILE (HN_TC_PROFILE=1 ./build.sh): the counters cost registers.
+__device__ unsigned long long g_tc_prof[32];
+#ifdef HN_TC_PROFILE
+// counters accumulate in registers (pacc[4] per role) and are flushed once when the role finishes
+#define HN_PROF_T(var) const long long var = prof ? clock64() : 0
+#define HN_PROF_ADD(slot, t0) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - (t0)); } while (0)
+#define HN_PROF_FLUSH(base) do { if (prof) { for (int _i = 0; _i < 4; ++_i) g_tc_prof[(base) + _i] += pacc[_i]; } } while (0)
+#define HN_PROF_DECL unsigned long long pacc[4] = {0, 0, 0, 0}
+#else
+#define HN_PROF_T(var) do { } while (0)
+#define HN_PROF_ADD(slot, t0) do { } while (0)
+#define HN_PROF_FLUSH(base) do { } while (0)
+#define HN_PROF_DECL do { } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
 template <bool kStore>
 __global__ void __launch_bounds__(kThreads, 1)
 field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const float* __restrict__ x_skel,
                 const float* __restrict__ hann_w, int ignore_non_rigid, float* __restrict__ raw,
-                float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs) {
+                float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs, int ablate) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
   const uint8_t* image = packed + hdr->image_off;
@@ -101,6 +124,9 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
   const TcChunk* table = reinterpret_cast<const TcChunk*>(smem + kTableOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef HN_TC_PROFILE
+  const bool prof = (ablate & 8) && blockIdx.x == 0;
+#endif
   const int64_t n_pairs = (n_samples + kTiles * kTileM - 1) / (kTiles * kTileM);
   const int nr_layers = (int)hdr->nr_layers;
   const int n_layers = nr_layers + (int)hdr->cn_layers;
@@ -147,15 +173,21 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      HN_PROF_DECL;
+      HN_PROF_T(p_t0);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (uint32_t c = first_chunk; c < n_chunks; ++c) {
           const TcChunk ch = table[c];
+          HN_PROF_T(p_w);
           mbar_wait(s_empty + stage * 8, phase ^ 1, 1);
+          HN_PROF_ADD(1, p_w);
           mbar_expect_tx(s_full + stage * 8, ch.bytes);
           tma_bulk_g2s(s_ring + stage * kStageBytes, image + ch.w_off, ch.bytes, s_full + stage * 8);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      HN_PROF_ADD(0, p_t0);
+      HN_PROF_FLUSH(0);
     }
   } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
     // ===================== MMA issuers: warp 1 drives tile 0, warp 18 drives tile 1 =====================
@@ -167,17 +199,25 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_const = ((kLboA >> 4) << 16);
       uint32_t stage = 0, phase = 0, a_phase = 0;
+      const int pbase = 4 + 6 * (int)t;
+      HN_PROF_DECL;
+      HN_PROF_T(m_t0);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (uint32_t c = first_chunk; c < n_chunks; ++c) {
           const TcChunk ch = table[c];
           if (ch.flags & 1) {
             // the A operand of this layer is complete (and the previous accumulator drained)
+            HN_PROF_T(m_w);
             mbar_wait(bar_ready, a_phase, 2);
+            HN_PROF_ADD(1, m_w);
             a_phase ^= 1;
             tc_fence_after();
           }
+          HN_PROF_T(m_f);
           mbar_wait(s_full + stage * 8, phase, 3);
+          HN_PROF_ADD(2, m_f);
           tc_fence_after();
+          HN_PROF_T(m_i);
           const uint32_t idesc = make_idesc(ch.n);
           const bool in_pe = (ch.flags & 4) != 0;
           const uint32_t a_addr = (in_pe ? s_act_pe + t * kActPeTile : s_base + t * kActHTile) + ch.a_off;
@@ -195,9 +235,12 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
           }
           umma_commit(s_empty + stage * 8);            // ring slot is free once both issuers' MMAs retire
           if (ch.flags & 2) umma_commit(bar_acc);      // accumulator of the layer is complete
+          HN_PROF_ADD(3, m_i);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      HN_PROF_ADD(0, m_t0);
+      HN_PROF_FLUSH(pbase);
     }
   } else {
     // ===================== epilogue warps (2 .. 17) =====================
@@ -216,6 +259,16 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
     for (int k = 0; k < 10; ++k) hw[k] = (k < (int)hdr->nr_freqs && hann_w) ? __ldg(hann_w + k) : 0.0f;
     const int nr_freqs = (int)hdr->nr_freqs, cn_freqs = (int)hdr->cn_freqs;
     const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
+#ifdef HN_TC_PROFILE
+    const bool eprof = prof && warp == 4 && lane == 0;      // warp 4: tile 0, quarter 0, half 0
+#define HN_EPROF_T(var) const long long var = eprof ? clock64() : 0
+#define HN_EPROF_ADD(slot, t0) do { if (eprof) pacc[(slot) - 16] += (unsigned long long)(clock64() - (t0)); } while (0)
+    unsigned long long pacc[4] = {0, 0, 0, 0};
+#else
+#define HN_EPROF_T(var) do { } while (0)
+#define HN_EPROF_ADD(slot, t0) do { } while (0)
+#endif
+    HN_EPROF_T(e_t0);
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile_idx = pair * kTiles + tile;
@@ -227,25 +280,37 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
       float q[3] = {x[0], x[1], x[2]};            // position fed to the canonical encoding
 
       if (!ignore_non_rigid) {
+        HN_EPROF_T(e_pe);
         write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad,
                               store ? bufs.pe[0] + image_row_offset(tile_idx, row, nr_pad) : nullptr);
         fence_proxy_async();
         mbar_arrive(bar_ready);
+        HN_EPROF_ADD(18, e_pe);
       }
 
       for (int layer = first_layer; layer < n_layers; ++layer) {
         const bool is_nr = layer < nr_layers;
         const bool is_out = (layer == nr_layers - 1) || (layer == n_layers - 1);
         if (layer == nr_layers) {
+          HN_EPROF_T(e_pe);
           write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad,
                                store ? bufs.pe[1] + image_row_offset(tile_idx, row, cn_pad) : nullptr);
           fence_proxy_async();
           mbar_arrive(bar_ready);
+          HN_EPROF_ADD(18, e_pe);
         }
+        HN_EPROF_T(e_w);
         mbar_wait(bar_acc, acc_phase, 4);
+        HN_EPROF_ADD(17, e_w);
         acc_phase ^= 1;
         tc_fence_after();
-        if (!is_out) {
+        HN_EPROF_T(e_h);
+        if (!is_out && (ablate & 1)) {
+          // measurement aid (HN_TC_ABLATE=1): barrier handshake only, accumulator never read
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(bar_ready);
+        } else if (!is_out) {
           const int n_full = (int)hdr->layer_n[layer];
           const int n_half = n_full >> 1;                          // columns owned by this thread
           const int c_begin = half * n_half;
@@ -289,6 +354,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(bar_ready);
+          HN_EPROF_ADD(19, e_h);
         } else {
           uint32_t v[16];
           tmem_ld16(t_acc, v);
@@ -314,6 +380,10 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
         }
       }
     }
+    HN_EPROF_ADD(16, e_t0);
+#ifdef HN_TC_PROFILE
+    if (eprof) { for (int i = 0; i < 4; ++i) g_tc_prof[16 + i] += pacc[i]; }
+#endif
   }
 
   tc_fence_before();
@@ -372,6 +442,14 @@ using namespace hn;
 extern "C" {
 
 int hn_has_tcgen05(void) { return 1; }
+
+/* measurement aid: copies (and clears) the 32 cycle counters of block 0 (HN_TC_ABLATE & 8) */
+int hn_debug_tc_prof(unsigned long long* out_host) {
+  if (!out_host) return fail_arg("hn_debug_tc_prof: null");
+  HN_TRY(check_cuda(cudaMemcpyFromSymbol(out_host, g_tc_prof, sizeof(unsigned long long) * 32), "hn_debug_tc_prof/read"));
+  unsigned long long zero[32] = {0};
+  return check_cuda(cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)), "hn_debug_tc_prof/clear");
+}
 
 int64_t hn_field_packed_bytes(const hn_field_params* p) {
   TcPlan plan;
@@ -441,6 +519,10 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
   const int64_t n_pairs = ceil_div<int64_t>(n_samples, kTiles * kTileM);
   const unsigned grid = (unsigned)std::min<int64_t>(n_pairs, (int64_t)sms);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  // measurement aid, never set in production: HN_TC_ABLATE=1 skips the hidden-layer epilogue work
+  // (results are garbage) to expose how much of the kernel time the epilogue accounts for
+  const char* abl = getenv("HN_TC_ABLATE");
+  const int ablate = abl ? atoi(abl) : 0;
   if (save_for_backward) {
     TrainBufs bufs;
     const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
@@ -448,14 +530,14 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemTotal), "hn_field_fwd/smem attr"));
     field_tc_kernel<true><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
-        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs);
+        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs, ablate);
   } else {
     TrainBufs bufs;
     memset(&bufs, 0, sizeof(bufs));
     HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemTotal), "hn_field_fwd/smem attr"));
     field_tc_kernel<false><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
-        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs);
+        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs, ablate);
   }
   return launched("hn_field_fwd/tcgen05");
 }

@@ -5,11 +5,12 @@
 //      UMMA K-major core-matrix layout), W^T chunks stream through the TMA ring, the accumulator
 //      dH = dZ W lands in TMEM, and the epilogue masks it with the stored activation of the previous
 //      layer (T16 image written by the forward kernel) to get dZ of that layer - written in place as
-//      the next A operand AND to a T16 image in HBM for the weight-gradient kernel.  Gradients of the
-//      positional-encoding columns leave the chain as fp32 (P, pe_pad) buffers.
-//   2. the existing fp32 pe_bwd kernels turn those into d_xyz / d_x_skel,
-//   3. hn_tile_wgrad jobs produce every dW and db from the dZ / activation images,
-//   4. the condition-code columns of the first non-rigid layer get dW0[:, :69] += db0 (x) cond.
+//      the next A operand AND to a T16 image in HBM for the weight-gradient kernel.  The gradient of
+//      the positional-encoding columns is contracted with the encoding's derivative right in the
+//      epilogue (d_pos += PE'(pos) . d_pe, two threads per row, fp32 atomics), so the (P, pe_pad)
+//      encoding gradients never reach HBM,
+//   2. hn_tile_wgrad jobs produce every dW and db from the dZ / activation images,
+//   3. the condition-code columns of the first non-rigid layer get dW0[:, :69] += db0 (x) cond.
 //
 // Autograd of reference mlp_offset.py:74-114 and mlp_rgb_sigma.py:132-206 on the bf16 path.
 #include "mlp_tc_plan.cuh"
@@ -17,8 +18,6 @@
 namespace hn {
 
 // field_fp32.cu
-int pe_bwd(int64_t n, const float* x, int64_t ldx, int nf, const float* fw, bool incl, const float* d_out,
-           int64_t ldo, float* d_x, int64_t lddx, bool accumulate, cudaStream_t st);
 int add3(int64_t n, const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
          cudaStream_t st);
 int copy_cols(int64_t n, int n_cols, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
@@ -37,7 +36,8 @@ __device__ __forceinline__ uint32_t mask_pack(uint32_t h2, uint32_t a_lo, uint32
 
 __global__ void __launch_bounds__(kThreads, 1)
 field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, int mlp, const float* __restrict__ d_out,
-                    int ld_out, int n_out, const TrainBufs bufs) {
+                    int ld_out, int n_out, const TrainBufs bufs, const float* __restrict__ pos,
+                    const float* __restrict__ hann_w, float* __restrict__ d_pos, int ld_dpos) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
   const uint8_t* image = packed + hdr->image_off;
@@ -211,23 +211,49 @@ field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, int m
           fence_proxy_async();
           if (!last) mbar_arrive(bar_ready);
         } else {
-          // gradient of the encoding block -> fp32 (P, pe_pad)
+          // gradient of the encoding block, contracted with the encoding's derivative:
+          //   d_pos[a] += [raw x] g[a] + sum_k w_k 2^k (cos(2^k x_a) g_sin(k,a) - sin(2^k x_a) g_cos(k,a))
+          // (embedders/fourier.py:22-25 column order: per frequency sin(x,y,z) then cos(x,y,z)).
+          // The two threads of a row take alternate 16-column groups and add their partial sums atomically.
           mbar_wait(bar_acc, acc_phase, 4);
           acc_phase ^= 1;
           tc_fence_after();
           const int n_full = rd.n;
-          float* dst = bufs.d_pe[mlp][rd.layer] + sample * n_full;
-          // the two threads of a row take alternate 16-column groups
+          const int n_freqs = (int)(mlp == 0 ? hdr->nr_freqs : hdr->cn_freqs);
+          const int raw_cols = mlp == 0 ? 0 : 3;                  // the canonical encoding starts with x itself
+          const int pe_dim = raw_cols + 6 * n_freqs;
+          float px = 0.f, py = 0.f, pz = 0.f;
+          if (valid) { px = pos[sample * 3 + 0]; py = pos[sample * 3 + 1]; pz = pos[sample * 3 + 2]; }
+          float ax = 0.f, ay = 0.f, az = 0.f;
           for (int c0 = half * 16; c0 < n_full; c0 += 32) {
             uint32_t v[16];
             tmem_ld16(t_acc + (uint32_t)c0, v);
             tmem_ld_wait();
-            if (valid) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              if (c >= pe_dim) continue;                          // zero padding and the constant-1 column
+              const float g = __uint_as_float(v[j]);
+              if (c < raw_cols) {
+                if (c == 0) ax += g; else if (c == 1) ay += g; else az += g;
+                continue;
+              }
+              const int cc = c - raw_cols;
+              const int k = cc / 6, r = cc - 6 * k;
+              const int a = r >= 3 ? r - 3 : r;
+              const float freq = (float)(1 << k);
+              const float w = (hann_w ? __ldg(hann_w + k) : 1.0f) * freq;
+              const float xa = a == 0 ? px : (a == 1 ? py : pz);
+              float sn, cs;
+              __sincosf(xa * freq, &sn, &cs);
+              const float t = w * g * (r >= 3 ? -sn : cs);
+              if (a == 0) ax += t; else if (a == 1) ay += t; else az += t;
             }
+          }
+          if (valid) {
+            atomicAdd(d_pos + sample * ld_dpos + 0, ax);
+            atomicAdd(d_pos + sample * ld_dpos + 1, ay);
+            atomicAdd(d_pos + sample * ld_dpos + 2, az);
           }
           tc_fence_before();
           if (!last) mbar_arrive(bar_ready);
@@ -301,27 +327,20 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   const unsigned grid = (unsigned)std::min<int64_t>(n_pairs, (int64_t)sms);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
 
-  // 1. canonical MLP: d_raw -> dZ images + d(encoding)
-  field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, 1, d_raw, 4, 4, bufs);
-  HN_TRY(launched("hn_field_bwd_bf16/canonical chain"));
-  // 2. d_xyz = upstream + PE'(xyz) . d(encoding)   (two slots: skip layer, layer 0)
+  // 1. canonical MLP: d_raw -> dZ images; d_xyz_tot = upstream d_xyz + PE'(xyz) . d(encoding), accumulated
+  //    by the chain's epilogue (both encoding reads: skip layer and layer 0)
   if (d_xyz) HN_TRY(copy_cols(n, 3, d_xyz, 3, d_xyz_tot, 4, st));
-  HN_TRY(pe_bwd(n, xyz, 3, p->cn_freqs, nullptr, true, bufs.d_pe[1][1], plan.pe_pad[1], d_xyz_tot, 4, d_xyz != nullptr, st));
-  if (p->cn_skip > 0)
-    HN_TRY(pe_bwd(n, xyz, 3, p->cn_freqs, nullptr, true, bufs.d_pe[1][0], plan.pe_pad[1], d_xyz_tot, 4, true, st));
-  // 3. non-rigid MLP
+  else HN_TRY(check_cuda(cudaMemsetAsync(d_xyz_tot, 0, (size_t)rows * 4 * sizeof(float), st), "hn_field_bwd_bf16/memset"));
+  field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4);
+  HN_TRY(launched("hn_field_bwd_bf16/canonical chain"));
+  // 2. non-rigid MLP: its output gradient is d_xyz_tot + d_offsets; d_x_skel = d_xyz_tot + PE'(x_skel) . d(encoding)
+  HN_TRY(copy_cols(n, 3, d_xyz_tot, 4, d_x_skel, 3, st));
   if (!ignore_non_rigid) {
     HN_TRY(add3(n, d_xyz_tot, 4, d_offsets, 3, dz_nr, 4, st));
-    field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, 0, dz_nr, 4, 3, bufs);
+    field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3);
     HN_TRY(launched("hn_field_bwd_bf16/non-rigid chain"));
-    HN_TRY(copy_cols(n, 3, d_xyz_tot, 4, d_x_skel, 3, st));
-    HN_TRY(pe_bwd(n, x_skel, 3, p->nr_freqs, hann_w, false, bufs.d_pe[0][1], plan.pe_pad[0], d_x_skel, 3, true, st));
-    if (p->nr_skip > 0)
-      HN_TRY(pe_bwd(n, x_skel, 3, p->nr_freqs, hann_w, false, bufs.d_pe[0][0], plan.pe_pad[0], d_x_skel, 3, true, st));
-  } else {
-    HN_TRY(copy_cols(n, 3, d_xyz_tot, 4, d_x_skel, 3, st));
   }
-  // 4. weight / bias gradients from the images
+  // 3. weight / bias gradients from the images
   std::vector<WgradJob> jobs;
   auto add_job = [&](const uint8_t* dz, int f_dz, int m, const uint8_t* x, int f_x, int x_f0, int nn, int n_valid,
                      float* dw, int dw_ld, int dw_col0, int bias_col, float* db) {
@@ -356,7 +375,7 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   }
   if ((int)jobs.size() > kMaxWgradJobs) return fail_arg("hn_field_bwd_bf16: too many weight-gradient jobs");
   if (!jobs.empty()) HN_TRY(launch_tile_wgrad(jobs.data(), (int)jobs.size(), n, st));
-  // 5. condition-code columns of the first non-rigid layer: the input is the same vector for every sample
+  // 4. condition-code columns of the first non-rigid layer: the input is the same vector for every sample
   if (!ignore_non_rigid && p->cond_dim > 0 && g->nr_w[0] && g->nr_b[0]) {
     const int rows_w = p->nr_width, cols = p->cond_dim;
     outer_add_kernel<<<ceil_div(rows_w * cols, 256), 256, 0, st>>>(g->nr_w[0], p->cond_dim + plan.pe_dim[0], rows_w, cols,

@@ -67,12 +67,11 @@ struct TcHeader {
 };
 
 // Training buffers: T16 tile images of the encoding blocks, hidden activations and pre-activation
-// gradients, plus fp32 row-major gradients of the encoding blocks.  Passed to the kernels by value.
+// gradients.  Passed to the kernels by value.
 struct TrainBufs {
   uint8_t* pe[2];                    // [mlp]            F = pe_pad
   uint8_t* h[2][HN_MAX_LAYERS];      // [mlp][layer]     F = width      (hidden layers)
   uint8_t* dz[2][HN_MAX_LAYERS];     // [mlp][layer]     F = width, 16 for the output layer
-  float* d_pe[2][2];                 // [mlp][slot]      (P, pe_pad) fp32; slot 0 = skip layer, 1 = layer 0
   int64_t n_tiles;                   // tiles that exist in the images
 };
 
@@ -273,7 +272,6 @@ inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* 
       if (!outl) b.h[m][l] = take(n_tiles * 128 * plan.width[m] * 2);
       b.dz[m][l] = take(n_tiles * 128 * (outl ? 16 : plan.width[m]) * 2);
     }
-    for (int s = 0; s < 2; ++s) b.d_pe[m][s] = reinterpret_cast<float*>(take(n_tiles * 128 * plan.pe_pad[m] * 4));
   }
   if (out) *out = b;
   return off;

@@ -137,7 +137,8 @@ motion_field_bwd_kernel(int64_t n_pts, int S, int J, int V, const float* __restr
                         const float* __restrict__ Ts, const float* __restrict__ vol,
                         const float* __restrict__ bbox_min, const float* __restrict__ bbox_scale,
                         const float* __restrict__ d_x_skel, const float* __restrict__ d_mask,
-                        const float* __restrict__ d_weights, float* __restrict__ d_vol,
+                        const float* __restrict__ d_weights, const float* __restrict__ x_skel_fwd,
+                        const float* __restrict__ mask_fwd, float* __restrict__ d_vol,
                         float* __restrict__ d_Rs, float* __restrict__ d_Ts) {
   __shared__ float s_R[kMaxJoints * 9];
   __shared__ float s_T[kMaxJoints * 3];
@@ -160,9 +161,14 @@ motion_field_bwd_kernel(int64_t n_pts, int S, int J, int V, const float* __restr
     if (d_mask) gm = d_mask[i];
   }
   const int64_t vstride = (int64_t)V * V * V;
-  // pass 1: W and N
+  // pass 1: W and N - skipped when the caller hands back the forward outputs (x = N / max(W, 1e-4), W)
   float nx = 0.f, ny = 0.f, nz = 0.f, wsum = 0.f;
-  if (live) {
+  const bool have_fwd = x_skel_fwd != nullptr && mask_fwd != nullptr;
+  if (live && have_fwd) {
+    wsum = mask_fwd[i];
+    const float c = fmaxf(wsum, 1e-4f);
+    nx = x_skel_fwd[i * 3 + 0] * c; ny = x_skel_fwd[i * 3 + 1] * c; nz = x_skel_fwd[i * 3 + 2] * c;
+  } else if (live) {
     for (int j = 0; j < J; ++j) {
       const float* R = s_R + j * 9;
       float px = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + s_T[j * 3 + 0];
@@ -233,14 +239,36 @@ motion_field_bwd_kernel(int64_t n_pts, int S, int J, int V, const float* __restr
         }
       }
     }
-    // warp-reduce the 12 transform gradients, one shared-memory atomic per warp
+    // warp-reduce the 12 transform gradients with 18 shuffles instead of 60: two transposing steps
+    // (lanes trade half of their values, so the value count halves as the lane groups merge), then a
+    // plain butterfly over the last 3 values; lanes 0, 8, 16, 24 end up with 3 totals each
     if (__any_sync(0xffffffffu, contributes)) {
       float v[12] = {dp[0] * p[0], dp[0] * p[1], dp[0] * p[2], dp[1] * p[0], dp[1] * p[1], dp[1] * p[2],
                      dp[2] * p[0], dp[2] * p[1], dp[2] * p[2], dp[0], dp[1], dp[2]};
+      const bool up = (lane & 16) != 0;
+      float a[6];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        float r = warp_sum(v[k]);
-        if (lane == 0) atomicAdd(&s_acc[j * 12 + k], r);
+      for (int k = 0; k < 6; ++k) {
+        const float recv = __shfl_xor_sync(0xffffffffu, up ? v[k] : v[k + 6], 16);
+        a[k] = (up ? v[k + 6] : v[k]) + recv;
+      }
+      const bool up2 = (lane & 8) != 0;
+      float b[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float recv = __shfl_xor_sync(0xffffffffu, up2 ? a[k] : a[k + 3], 8);
+        b[k] = (up2 ? a[k + 3] : a[k]) + recv;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        b[k] += __shfl_xor_sync(0xffffffffu, b[k], 4);
+        b[k] += __shfl_xor_sync(0xffffffffu, b[k], 2);
+        b[k] += __shfl_xor_sync(0xffffffffu, b[k], 1);
+      }
+      if ((lane & 7) == 0) {
+        const int base = j * 12 + (up ? 6 : 0) + (up2 ? 3 : 0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(&s_acc[base + k], b[k]);
       }
     }
   }
@@ -299,7 +327,8 @@ int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
                         const float* rays_o, const float* rays_d, const float* z, const float* Rs,
                         const float* Ts, const float* vol, const float* bbox_min,
                         const float* bbox_scale, const float* d_x_skel, const float* d_mask,
-                        const float* d_weights, float* d_vol, float* d_Rs, float* d_Ts, void* stream) {
+                        const float* d_weights, const float* x_skel_fwd, const float* mask_fwd,
+                        float* d_vol, float* d_Rs, float* d_Ts, void* stream) {
   HN_TRY(check_common("hn_motion_field_bwd", n_rays, n_samples, n_joints, vol_size, pts, rays_o, rays_d, z,
                       Rs, Ts, vol, bbox_min, bbox_scale));
   if (!d_vol || !d_Rs || !d_Ts) return fail_arg("hn_motion_field_bwd: null gradient output");
@@ -308,7 +337,7 @@ int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
   unsigned grid = (unsigned)ceil_div<int64_t>(n, 256);
   motion_field_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       n, n_samples, n_joints, vol_size, pts, rays_o, rays_d, z, Rs, Ts, vol, bbox_min, bbox_scale, d_x_skel,
-      d_mask, d_weights, d_vol, d_Rs, d_Ts);
+      d_mask, d_weights, x_skel_fwd, mask_fwd, d_vol, d_Rs, d_Ts);
   return launched("hn_motion_field_bwd");
 }
 

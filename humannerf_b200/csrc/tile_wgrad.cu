@@ -14,6 +14,7 @@
 // Replaces the autograd of nn.Linear in reference non_rigid_motion_mlps/mlp_offset.py:74-84 and
 // canonical_mlps/mlp_rgb_sigma.py:163-166,198 on the bf16 path.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,7 +41,7 @@ struct WgradJobTable {
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles, int tiles_per_slab) {
+tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles, int tiles_per_slab, int slab_major) {
   const WgradJob* jobs = tab.jobs;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -77,8 +78,12 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const WgradJob job = jobs[item / n_slabs];
-        const int t0 = (item % n_slabs) * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        // slab-major order: CTAs that run at the same time work on the SAME slab of samples for
+        // neighbouring jobs, so a dZ image that two jobs of a layer read (weights + bias column)
+        // comes from HBM once and from L2 the second time
+        const int ji = slab_major ? item % n_jobs : item / n_slabs, si = slab_major ? item / n_jobs : item % n_slabs;
+        const WgradJob job = jobs[ji];
+        const int t0 = si * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
         const uint32_t a_blk = (uint32_t)job.f_dz * 32u;       // bytes per 16-sample block of the dZ image
         const uint32_t x_blk = (uint32_t)job.f_x * 32u;
         const uint32_t b_blk = (uint32_t)job.n * 32u;          // bytes of the X window per 16-sample block
@@ -110,8 +115,9 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
       const uint32_t lo_const = ((128u >> 4) << 16);          // LBO = 128 B (next 8 samples)
       bool first_item = true;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const WgradJob job = jobs[item / n_slabs];
-        const int t0 = (item % n_slabs) * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        const int ji = slab_major ? item % n_jobs : item / n_slabs, si = slab_major ? item / n_jobs : item % n_slabs;
+        const WgradJob job = jobs[ji];
+        const int t0 = si * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
         const int m_tiles = (job.m + 127) / 128;
         const uint32_t idesc = make_idesc_mn((uint32_t)job.n);
         const uint32_t a_blk = (uint32_t)job.f_dz * 32u, b_blk = (uint32_t)job.n * 32u;
@@ -151,7 +157,7 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
     const int row = quarter * 32 + lane;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const WgradJob job = jobs[item / n_slabs];
+      const WgradJob job = jobs[slab_major ? item % n_jobs : item / n_slabs];
       const int m_tiles = (job.m + 127) / 128;
       mbar_wait(s_acc, acc_phase, 4);
       acc_phase ^= 1;
@@ -237,7 +243,8 @@ int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, 
   const int tiles_per_slab = (n_tiles + n_slabs - 1) / n_slabs;
   n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
   const int grid = std::min(n_jobs * n_slabs, sms);
-  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, tiles_per_slab);
+  const char* ord = getenv("HN_WGRAD_SLAB_MAJOR");       // measurement aid (A/B of the item order)
+  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, tiles_per_slab, ord ? atoi(ord) : 0);
   return launched("tile_wgrad");
 }
 

@@ -168,7 +168,7 @@ class _MotionField(torch.autograd.Function):
             check(lib.hn_motion_field_fwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
                                           ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(x_skel),
                                           ptr(mask), ptr(weights), stream_ptr()), 'motion_field_fwd')
-        ctx.save_for_backward(rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale)
+        ctx.save_for_backward(rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale, x_skel, mask)
         ctx.dims = (n_rays, S, J, V)
         if weights is None:
             weights = torch.empty(0, device=dev)
@@ -178,7 +178,7 @@ class _MotionField(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_x, g_m, g_w):
         lib = _lib.load()
-        rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale = ctx.saved_tensors
+        rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale, x_skel, mask = ctx.saved_tensors
         n_rays, S, J, V = ctx.dims
         dev = Rs.device
         g_x = _f32c(g_x) if g_x is not None else None
@@ -190,7 +190,8 @@ class _MotionField(torch.autograd.Function):
         with torch.cuda.device(dev), _timed('motion_field_bwd'):
             check(lib.hn_motion_field_bwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
                                           ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(g_x), ptr(g_m),
-                                          ptr(g_w), ptr(d_vol), ptr(d_Rs), ptr(d_Ts), stream_ptr()),
+                                          ptr(g_w), ptr(x_skel), ptr(mask), ptr(d_vol), ptr(d_Rs), ptr(d_Ts),
+                                          stream_ptr()),
                   'motion_field_bwd')
         return None, None, None, None, d_Rs, d_Ts, d_vol, None, None, None
 

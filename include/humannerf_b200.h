@@ -37,6 +37,9 @@ const char* hn_last_error(void);
 int64_t hn_launch_count(void);
 /* 1 if the tcgen05/TMEM fused-MLP kernel was compiled in (sm_100a build). */
 int hn_has_tcgen05(void);
+/* Measurement aid: with the environment variable HN_TC_ABLATE & 8 set, block 0 of the tcgen05 forward
+ * kernel accumulates cycle counters per role; this copies the 32 counters to the host and clears them. */
+int hn_debug_tc_prof(unsigned long long* out_host);
 
 /* ------------------------------------------------------------------------------------------
  * a1  core/utils/camera_util.py:132-159  get_rays_from_KRT
@@ -87,13 +90,16 @@ int hn_motion_field_fwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
                         float* x_skel, float* mask, float* weights, void* stream);
 
 /* Backward of the above.  d_x_skel (P,3), d_mask (P), d_weights (P,J) are nullable upstream
- * gradients.  Accumulates (+=) into d_vol (J,V,V,V), d_Rs (J,3,3), d_Ts (J,3): caller zeroes.
+ * gradients.  x_skel_fwd (P,3) and mask_fwd (P) are the forward's outputs (both nullable together):
+ * when given, the kernel skips re-evaluating the 24 lookups that only rebuild them.
+ * Accumulates (+=) into d_vol (J,V,V,V), d_Rs (J,3,3), d_Ts (J,3): caller zeroes.
  */
 int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_size,
                         const float* pts, const float* rays_o, const float* rays_d, const float* z,
                         const float* Rs, const float* Ts, const float* vol,
                         const float* bbox_min, const float* bbox_scale,
                         const float* d_x_skel, const float* d_mask, const float* d_weights,
+                        const float* x_skel_fwd, const float* mask_fwd,
                         float* d_vol, float* d_Rs, float* d_Ts, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,0 +1,43 @@
+"""Times the forward render legs (CUDA events) for a given number of rays; prints per-op ms."""
+import argparse, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from humannerf_b200 import ops, synthetic as syn
+from humannerf_b200.config import make_cfg
+from humannerf_b200.network import Network
+ap = argparse.ArgumentParser(); ap.add_argument('--rays', type=int, default=232224); ap.add_argument('--reps', type=int, default=5)
+args = ap.parse_args()
+dev = 'cuda:0'
+cfg = make_cfg(); cfg.b200.heavy_outputs = False; cfg.b200.mlp_precision = 'bf16'; cfg.perturb = 0.0
+net = Network(); net.load_state_dict(syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True)); net = net.to(dev).eval()
+frame = syn.make_frame(0)
+fr = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in frame.items()}
+K, E = syn.look_at_camera(512, 512, 1250.0)
+o64, d64 = ops.gen_rays(512, 512, K, E, dev)
+near, far, mask = ops.rays_bbox(np.stack([frame['dst_bbox_min_xyz'], frame['dst_bbox_max_xyz']]), o64, d64)
+o, d, nr, fr_, _ = ops.compact_rays(mask, o64, d64, near, far)
+R = min(args.rays, o.shape[0])
+kw = {k: fr[k] for k in ('dst_Rs', 'dst_Ts', 'cnl_gtfms', 'motion_weights_priors', 'dst_posevec', 'cnl_bbox_min_xyz', 'cnl_bbox_max_xyz', 'cnl_bbox_scale_xyz', 'bgcolor')}
+rays = torch.stack([o[:R], d[:R], d[:R]], 0)
+with torch.no_grad():
+    for _ in range(2):
+        net(rays=rays, near=nr[:R], far=fr_[:R], iter_val=cfg.eval_iter, **kw)
+    torch.cuda.synchronize()
+    ops.timing_start()
+    for _ in range(args.reps):
+        net(rays=rays, near=nr[:R], far=fr_[:R], iter_val=cfg.eval_iter, **kw)
+    t = ops.timing_stop()
+P = R * 128
+print({k: round(v[0] / args.reps, 3) for k, v in t.items()}, 'TFLOP/s', round(1184768.0 * P / (t['field_fwd_bf16'][0] / args.reps * 1e-3) / 1e12, 1))
+
+if int(os.environ.get('HN_TC_ABLATE', '0')) & 8:
+    import ctypes
+    from humannerf_b200 import _lib
+    buf = (ctypes.c_ulonglong * 32)()
+    _lib.check(_lib.load().hn_debug_tc_prof(buf), 'prof')
+    v = [int(x) for x in buf]
+    names = {0: 'producer total', 1: 'producer wait-empty', 4: 'issuer0 total', 5: 'issuer0 wait a_ready', 6: 'issuer0 wait full',
+             7: 'issuer0 issue', 10: 'issuer1 total', 11: 'issuer1 wait a_ready', 12: 'issuer1 wait full', 13: 'issuer1 issue',
+             16: 'epi total', 17: 'epi wait acc', 18: 'epi encoding', 19: 'epi hidden work'}
+    for k, n in names.items():
+        print(f'  {n:24s} {v[k] / 1e6:10.2f} Mcyc')
