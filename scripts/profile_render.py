@@ -1,5 +1,5 @@
 """Short command for ncu: renders `--rays` rays x 128 samples on the bf16 tcgen05 path (and,
-with --train, one fp32 train-style forward/backward) so a capture replays few, representative launches."""
+with --train, one train-style forward / backward / Adam step) so a capture replays few, representative launches."""
 import argparse
 import os
 import sys
@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--rays', type=int, default=32768)
 ap.add_argument('--train', action='store_true')
 ap.add_argument('--reps', type=int, default=2)
+ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'], help='MLP arithmetic of the --train pass')
 args = ap.parse_args()
 dev = 'cuda:0'
 cfg = make_cfg()
@@ -24,6 +25,8 @@ cfg.b200.jitter_rng = 'device'
 net = Network()
 net.load_state_dict(syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True))
 net = net.to(dev)
+from humannerf_b200.training import make_optimizer      # noqa: E402
+opt = make_optimizer(net) if args.train else None        # FusedAdam: one adam_kernel launch per step
 frame = syn.make_frame(0)
 fr = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in frame.items()}
 K, E = syn.look_at_camera(512, 512, 1250.0)
@@ -36,11 +39,12 @@ kw = {k: fr[k] for k in ('dst_Rs', 'dst_Ts', 'cnl_gtfms', 'motion_weights_priors
 rays = torch.stack([o[:R], d[:R], d[:R]], 0)
 for _ in range(args.reps):
     if args.train:
-        cfg.b200.mlp_precision, cfg.perturb = 'fp32', 1.0
+        cfg.b200.mlp_precision, cfg.perturb = args.precision, 1.0
         net.train()
+        opt.zero_grad()
         out = net(rays=rays, near=nr[:R], far=fr_[:R], iter_val=60000, **kw)
-        net.zero_grad()
         (out['rgb'] ** 2).mean().backward()
+        opt.step()
     else:
         cfg.b200.mlp_precision, cfg.perturb = 'bf16', 0.0
         net.eval()
