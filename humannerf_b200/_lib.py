@@ -77,7 +77,7 @@ SIGNATURES = {
     'hn_adam_plan_bytes': (_i64, [C.POINTER(AdamTensor), _int]),
     'hn_adam_n_chunks': (_i64, [C.POINTER(AdamTensor), _int]),
     'hn_adam_plan': (_int, [C.POINTER(AdamTensor), _int, _p, _i64]),
-    'hn_adam_step': (_int, [_p, _i64, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, _p]),
+    'hn_adam_step': (_int, [_p, _i64, _p, _p, _p, _p, _p, C.c_float, C.c_float, C.c_float, _p]),
     'hn_composite_fwd': (_int, [_i64, _int] + [_p] * 15),
     'hn_composite_bwd': (_int, [_i64, _int] + [_p] * 12),
     'hn_tile_image_bytes': (_i64, [_i64, _int]),

@@ -31,7 +31,8 @@ struct AdamHeader {
 };
 
 __global__ void __launch_bounds__(kAdamThreads)
-adam_kernel(const uint8_t* __restrict__ plan, const float* __restrict__ lr, const float* __restrict__ lr_scale,
+adam_kernel(const uint8_t* __restrict__ plan, const float* const* __restrict__ grad_ptrs,
+            const float* __restrict__ lr, const float* __restrict__ lr_scale,
             const float* __restrict__ step, const float* __restrict__ active, float beta1, float beta2, float eps) {
   const AdamHeader* hdr = reinterpret_cast<const AdamHeader*>(plan);
   const hn_adam_tensor* tensors = reinterpret_cast<const hn_adam_tensor*>(plan + hdr->tensors_off);
@@ -42,7 +43,8 @@ adam_kernel(const uint8_t* __restrict__ plan, const float* __restrict__ lr, cons
   for (int64_t c = blockIdx.x; c < hdr->n_chunks; c += gridDim.x) {
     const int2 ch = chunks[c];
     if (active && active[ch.x] == 0.0f) continue;
-    const hn_adam_tensor t = tensors[ch.x];
+    hn_adam_tensor t = tensors[ch.x];
+    if (grad_ptrs) t.grad = grad_ptrs[ch.x];          // this step's gradient buffers (autograd re-allocates them)
     // bias corrections in double, like the host arithmetic of torch.optim.Adam (one thread per chunk;
     // the chunk loop and the `continue` above are block-uniform)
     __syncthreads();
@@ -120,7 +122,7 @@ int hn_adam_plan(const hn_adam_tensor* tensors_host, int n_tensors, void* plan_h
   if (need < 0 || !plan_host || plan_bytes < need) return fail_arg("hn_adam_plan: bad argument or buffer too small");
   for (int i = 0; i < n_tensors; ++i) {
     const hn_adam_tensor& t = tensors_host[i];
-    if (t.numel > 0 && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq))
+    if (t.numel > 0 && (!t.param || !t.exp_avg || !t.exp_avg_sq))
       return fail_arg("hn_adam_plan: null pointer in tensor %d", i);
     if (ceil_div<int64_t>(t.numel, kAdamChunk) > 0x7fffffff) return fail_arg("hn_adam_plan: tensor %d too large", i);
   }
@@ -140,16 +142,17 @@ int hn_adam_plan(const hn_adam_tensor* tensors_host, int n_tensors, void* plan_h
   return 0;
 }
 
-int hn_adam_step(const void* plan_dev, int64_t n_chunks, const float* lr_dev, const float* lr_scale_dev,
-                 const float* step_dev, const float* active_dev, float beta1, float beta2, float eps,
-                 void* stream) {
+int hn_adam_step(const void* plan_dev, int64_t n_chunks, const void* grad_ptrs_dev, const float* lr_dev,
+                 const float* lr_scale_dev, const float* step_dev, const float* active_dev, float beta1,
+                 float beta2, float eps, void* stream) {
   if (n_chunks == 0) return 0;
   if (!plan_dev || n_chunks < 0 || !lr_dev || !step_dev) return fail_arg("hn_adam_step: null pointer");
   int dev = 0, sms = 0;
   HN_TRY(check_cuda(cudaGetDevice(&dev), "hn_adam_step/device"));
   HN_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "hn_adam_step/attr"));
   const unsigned grid = (unsigned)std::min<int64_t>(n_chunks, (int64_t)sms * 8);
-  adam_kernel<<<grid, kAdamThreads, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(plan_dev), lr_dev, lr_scale_dev,
+  adam_kernel<<<grid, kAdamThreads, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(plan_dev),
+                                                            static_cast<const float* const*>(grad_ptrs_dev), lr_dev, lr_scale_dev,
                                                             step_dev, active_dev, beta1, beta2, eps);
   return launched("hn_adam_step");
 }

@@ -207,6 +207,10 @@ class Network(nn.Module):
             hann = hann_window_weights(it, nr_cfg.multires, nr_cfg.kick_in_iter, nr_cfg.full_band_iter).to(dev)
 
         # 3. motion bases and blend-weight volume (network.py:757-763)
+        precision = _lib.PRECISION_BF16 if str(b200.get('mlp_precision', 'fp32')).lower() == 'bf16' \
+            else _lib.PRECISION_FP32
+        if hasattr(self.mweight_vol_decoder, 'allow_tf32'):
+            self.mweight_vol_decoder.allow_tf32 = precision == _lib.PRECISION_BF16
         scale_Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts, cnl_gtfms)
         vol = self._decode_volume(priors.float())[0]
         self.motion_weights_vol = vol
@@ -231,8 +235,6 @@ class Network(nn.Module):
         S = int(cfg.N_samples)
         heavy = bool(b200.get('heavy_outputs', True))
         ignore_nr = bool(cfg.ignore_non_rigid_motions)
-        precision = _lib.PRECISION_BF16 if str(b200.get('mlp_precision', 'fp32')).lower() == 'bf16' \
-            else _lib.PRECISION_FP32
         nr_w, nr_b, cn_w, cn_b = self._field_weights()
         packed = None
         if precision == _lib.PRECISION_BF16:

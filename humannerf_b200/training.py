@@ -95,17 +95,19 @@ class FusedAdam(torch.optim.Optimizer):
     (optimizer.py:12-43: one group per tensor, per-name learning rates); `param_groups[i]['lr']` stays
     the knob `update_lr` turns.  Differences in mechanism, not arithmetic:
 
-    * gradients, first and second moments live in three flat fp32 buffers owned by the optimizer;
-      `p.grad` and `state[p]['exp_avg' / 'exp_avg_sq']` are views into them, so `zero_grad()` is one
-      memset (it never sets `.grad` to None) and the kernel's pointer table is built once;
+    * first and second moments live in two flat fp32 buffers (`state[p]['exp_avg' / 'exp_avg_sq']` are
+      views), the kernel's tensor table is built once;
+    * gradients are taken where autograd left them: each step uploads the 55 `.grad` pointers (one
+      440-byte copy from pinned memory) - `zero_grad()` just drops the old tensors, so there is no
+      zero-fill and no `grad += new` pass over 64 M elements;
     * step counts, learning rates, an optional global `lr_scale` and the per-tensor `active` mask are
       read from device memory, so a step captured in a CUDA graph follows the schedule on replay;
-    * a tensor whose `active` entry is 0 is skipped like a parameter whose `.grad` is None.
+    * a tensor whose `.grad` is None or whose `active` entry is 0 is skipped, like torch skips a
+      parameter without gradient.
     """
 
     def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
-        import ctypes as C
         from humannerf_b200 import _lib
         self._lib = _lib
         ps = [p for g in self.param_groups for p in g['params']]
@@ -115,36 +117,38 @@ class FusedAdam(torch.optim.Optimizer):
             raise RuntimeError('FusedAdam: betas / eps must be the same for every group')
         dev = ps[0].device
         self._ps = ps
+        n_t = len(ps)
         offs, total = [], 0
         for p in ps:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4                # keep every view 16-byte aligned
-        self.flat_grad = torch.zeros(total, device=dev)
         self._flat_m = torch.zeros(total, device=dev)
         self._flat_v = torch.zeros(total, device=dev)
-        self.step_dev = torch.zeros(len(ps), device=dev)         # per-tensor step counts (floats)
-        self.active = torch.ones(len(ps), device=dev)            # 0 = skip this tensor
+        self.step_dev = torch.zeros(n_t, device=dev)             # per-tensor step counts (floats)
+        self.active = torch.ones(n_t, device=dev)                # user mask: 0 = skip this tensor
         self.lr_scale: Optional[torch.Tensor] = None             # optional (1,) device factor on every lr
-        self._grad_views = []
-        table = (_lib.AdamTensor * len(ps))()
+        table = (_lib.AdamTensor * n_t)()
         for i, (p, o) in enumerate(zip(ps, offs)):
             n = p.numel()
-            gv = self.flat_grad[o:o + n].view_as(p)
-            p.grad = gv
-            self._grad_views.append(gv)
             self.state[p] = {'step': self.step_dev[i:i + 1], 'exp_avg': self._flat_m[o:o + n].view_as(p),
                              'exp_avg_sq': self._flat_v[o:o + n].view_as(p)}
-            table[i].param, table[i].grad = p.data_ptr(), gv.data_ptr()
+            table[i].param, table[i].grad = p.data_ptr(), None
             table[i].exp_avg, table[i].exp_avg_sq = self._flat_m[o:o + n].data_ptr(), self._flat_v[o:o + n].data_ptr()
             table[i].numel = n
         lib = _lib.load()
-        nbytes = int(lib.hn_adam_plan_bytes(table, len(ps)))
-        self._n_chunks = int(lib.hn_adam_n_chunks(table, len(ps)))
+        nbytes = int(lib.hn_adam_plan_bytes(table, n_t))
+        self._n_chunks = int(lib.hn_adam_n_chunks(table, n_t))
         host = torch.empty(nbytes, dtype=torch.uint8)
-        _lib.check(lib.hn_adam_plan(table, len(ps), host.data_ptr(), nbytes), 'adam_plan')
+        _lib.check(lib.hn_adam_plan(table, n_t, host.data_ptr(), nbytes), 'adam_plan')
         self._plan = host.to(dev)
+        # per-step upload: [gradient pointers (int64) | has-gradient flags (float32 bit patterns in int64 slots)]
+        self._step_host = torch.zeros(2 * n_t, dtype=torch.int64).pin_memory()
+        self._step_dev = torch.zeros(2 * n_t, dtype=torch.int64, device=dev)
+        self._has_grad = self._step_dev[n_t:].view(torch.float32)[::2]      # low halves of the int64 slots
+        self._step_active = torch.ones(n_t, device=dev)
+        self._keep = []
         self._lr_cache = None
-        self._lr_dev = torch.zeros(len(ps), device=dev)
+        self._lr_dev = torch.zeros(n_t, device=dev)
         self._sync_lr()
 
     def _lrs(self):
@@ -158,32 +162,40 @@ class FusedAdam(torch.optim.Optimizer):
             self._lr_dev.copy_(torch.tensor(lrs, dtype=torch.float32))
             self._lr_cache = lrs
 
-    def zero_grad(self, set_to_none: bool = True):
-        """One memset; `.grad` stays a view of the flat buffer (set_to_none is ignored on purpose)."""
-        self.flat_grad.zero_()
-        for p, gv in zip(self._ps, self._grad_views):
-            if p.grad is not gv:
-                p.grad = gv
-
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
-        for p, gv in zip(self._ps, self._grad_views):
-            if p.grad is None:
-                gv.zero_()
-                p.grad = gv
-            elif p.grad is not gv and p.grad.data_ptr() != gv.data_ptr():
-                gv.copy_(p.grad)             # someone replaced .grad: fold it back into the flat buffer
-                p.grad = gv
+        n_t = len(self._ps)
+        # Captured in a graph, the copy below becomes a memcpy node that re-reads the pinned buffer on every
+        # replay (it is not touched again after capture).  Eagerly, a pageable staging tensor is used: that
+        # copy has consumed its source when it returns, so the next step may overwrite nothing in flight.
+        capturing = torch.cuda.is_current_stream_capturing()
+        host = self._step_host if capturing else torch.zeros(2 * n_t, dtype=torch.int64)
+        flags = host[n_t:].view(torch.float32)
+        keep = []
+        for i, p in enumerate(self._ps):
+            g = p.grad
+            if g is None:
+                host[i] = 0
+                flags[2 * i] = 0.0
+                continue
+            if g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+                g = g.to(torch.float32).contiguous().view_as(p)
+            keep.append(g)
+            host[i] = g.data_ptr()
+            flags[2 * i] = 1.0
+        self._keep = keep                              # the kernel reads these buffers asynchronously
+        self._step_dev.copy_(host, non_blocking=capturing)
+        torch.mul(self.active, self._has_grad, out=self._step_active)
         self._sync_lr()
-        self.step_dev.add_(self.active)
+        self.step_dev.add_(self._step_active)
         g0 = self.param_groups[0]
         lib, ptr = self._lib.load(), self._lib.ptr
         with torch.cuda.device(self._plan.device):
-            self._lib.check(lib.hn_adam_step(ptr(self._plan), self._n_chunks, ptr(self._lr_dev), ptr(self.lr_scale),
-                                             ptr(self.step_dev), ptr(self.active), float(g0['betas'][0]),
-                                             float(g0['betas'][1]), float(g0['eps']), self._lib.stream_ptr()),
-                            'adam_step')
+            self._lib.check(lib.hn_adam_step(ptr(self._plan), self._n_chunks, ptr(self._step_dev), ptr(self._lr_dev),
+                                             ptr(self.lr_scale), ptr(self.step_dev), ptr(self._step_active),
+                                             float(g0['betas'][0]), float(g0['betas'][1]), float(g0['eps']),
+                                             self._lib.stream_ptr()), 'adam_step')
         return loss
 
 
@@ -306,7 +318,7 @@ class GraphedTrainStep:
 
     # -- the step -----------------------------------------------------------------------
     def _body(self, iter_step: int) -> torch.Tensor:
-        self.opt.zero_grad()
+        self.opt.zero_grad(set_to_none=True)
         out = self.net(rays=self.rays, near=self.near, far=self.far, iter_val=iter_step,
                        b200_hann_w=self.sched[:self._nf], b200_cond_gate=self.sched[self._nf:self._nf + 1],
                        **self.frame_kw)

@@ -269,7 +269,7 @@ int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, 
  */
 typedef struct hn_adam_tensor {
   float* param;
-  const float* grad;
+  const float* grad;      /* may be NULL when hn_adam_step gets grad_ptrs_dev */
   float* exp_avg;
   float* exp_avg_sq;
   int64_t numel;
@@ -279,9 +279,12 @@ int64_t hn_adam_plan_bytes(const hn_adam_tensor* tensors_host, int n_tensors);
 int hn_adam_plan(const hn_adam_tensor* tensors_host, int n_tensors, void* plan_host, int64_t plan_bytes);
 /* n_chunks = (plan_bytes - chunk table offset) / 8 is returned by hn_adam_n_chunks. */
 int64_t hn_adam_n_chunks(const hn_adam_tensor* tensors_host, int n_tensors);
-int hn_adam_step(const void* plan_dev, int64_t n_chunks, const float* lr_dev, const float* lr_scale_dev,
-                 const float* step_dev, const float* active_dev, float beta1, float beta2, float eps,
-                 void* stream);
+/* grad_ptrs_dev (nullable): device array of n_tensors gradient pointers that overrides the plan's `grad`
+ * fields for this step - autograd allocates fresh gradient tensors every backward pass, and stealing them
+ * is cheaper than accumulating into persistent buffers (no zero-fill, no `grad += new` pass). */
+int hn_adam_step(const void* plan_dev, int64_t n_chunks, const void* grad_ptrs_dev, const float* lr_dev,
+                 const float* lr_scale_dev, const float* step_dev, const float* active_dev, float beta1,
+                 float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -266,14 +266,16 @@ def test_fused_adam_matches_torch_adam(ops):
         our.zero_grad()
         for p, q, gr in zip(ref_p, our_p, grads):
             p.grad = gr.clone()
-            q.grad.add_(gr)
+            q.grad = gr.clone()
         if step == 3:
             for opt in (ref, our):
                 for grp in opt.param_groups:
                     grp['lr'] *= 0.5
         if step == 4:                                  # tensor 1 gets no gradient this step
             ref_p[1].grad = None
-            our.active[1] = 0.0
+            our_p[1].grad = None                       # skipped like torch skips a parameter without .grad
+            ref_p[4].grad = None
+            our.active[4] = 0.0                        # ... or through the explicit mask
         ref.step()
         our.step()
     torch.cuda.synchronize()
