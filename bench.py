@@ -220,10 +220,14 @@ def main():
                                    'cnl_bbox_min_xyz', 'cnl_bbox_max_xyz', 'cnl_bbox_scale_xyz', 'bgcolor')}
 
     # ---- forward render of the whole frame on the bf16 tensor-core path -> target image + subject mask
-    def render_frame(sharded=False):
+    def render_frame(sharded=False, cull_eps=0.0, one_chunk=False):
         """sharded: this rank renders its contiguous block of the frame's rays and one all_gather of
         (rgb, alpha, depth) = 20 B / ray assembles the frame on every rank (render)."""
         cfg.b200.mlp_precision, cfg.perturb = 'bf16', 0.0
+        cfg.b200.cull_mask_eps = cull_eps
+        chunk0 = cfg.chunk
+        if one_chunk:
+            cfg.chunk = 1 << 30          # 180 GB of HBM: the whole frame's samples fit in one pass
         net.eval()
         a, b = shard_bounds(n_valid, rank, world) if (sharded and world > 1) else (0, n_valid)
         with torch.no_grad():
@@ -234,6 +238,7 @@ def main():
                 full = all_gather_rows(packed, n_valid)
                 out = {'rgb': full[:, :3], 'alpha': full[:, 3], 'depth': full[:, 4]}
         cfg.b200.mlp_precision, cfg.perturb = args.precision, 1.0
+        cfg.b200.cull_mask_eps, cfg.chunk = 0.0, chunk0
         net.train()
         return out
 
@@ -429,6 +434,30 @@ def main():
                                       'bound': 'hbm', 'achieved': mf_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                       'frac': mf_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source']},
         }
+
+        # opt-in empty-space skipping (cfg.b200.cull_mask_eps = 1e-7: outputs within 2.6e-5 of the dense
+        # render) with the frame in one chunk; reported next to the dense leg, never instead of it
+        dense_ref = render_frame(sharded=True)
+        for _ in range(2):
+            culled = render_frame(sharded=True, cull_eps=1e-7, one_chunk=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(reps):
+            culled = render_frame(sharded=True, cull_eps=1e-7, one_chunk=True)
+        c1.record()
+        barrier()
+        cms = c0.elapsed_time(c1) / reps
+        if world > 1:
+            t = torch.tensor([cms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cms = float(t[0])
+        result['render']['empty_space_skipping'] = {
+            'cull_mask_eps': 1e-7, 'ms_per_frame': cms, 'rays_per_sec': n_valid / (cms * 1e-3),
+            'samples_skipped_frac': float(net.last_cull_fraction),
+            'max_abs_rgb_diff_vs_dense': float((culled['rgb'] - dense_ref['rgb']).abs().max()),
+            'max_abs_alpha_diff_vs_dense': float((culled['alpha'] - dense_ref['alpha']).abs().max()),
+            'bound': 2 * N_SAMPLES * 1e-7}
 
     # =========================== CPU baseline (rank 0, N = 1 only) =================================
     if world == 1 and not args.no_cpu_baseline:

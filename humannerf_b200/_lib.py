@@ -61,8 +61,9 @@ SIGNATURES = {
     'hn_compact_rays_workspace_bytes': (_i64, [_i64]),
     'hn_compact_rays': (_int, [_i64] + [_p] * 13),
     'hn_sample_z': (_int, [_i64, _int, _p, _p, _p, _p, _p, _p]),
-    'hn_motion_field_fwd': (_int, [_i64, _int, _int, _int] + [_p] * 13),
-    'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 18),
+    'hn_motion_field_workspace_bytes': (_i64, [_int, _int]),
+    'hn_motion_field_fwd': (_int, [_i64, _int, _int, _int] + [_p] * 13 + [_i64, _p]),
+    'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 19),
     'hn_field_workspace_bytes': (_i64, [C.POINTER(FieldParams), _i64, _int, _int]),
     'hn_field_fwd': (_int, [C.POINTER(FieldParams), _i64, _p, _p, _p, _int, _p, _p, _p, _p, _i64, _int, _int, _p, _p]),
     'hn_field_bwd_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),

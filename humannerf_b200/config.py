@@ -161,6 +161,10 @@ _DEFAULTS: Dict[str, Any] = {
         # stratified-jitter noise: 'reference' = CPU default generator like network.py:468
         # (same random stream as the reference), 'device' = torch.rand on the GPU
         'jitter_rng': 'reference',
+        # empty-space skipping in no-grad rendering: samples whose foreground likelihood (sum of the 24
+        # blend weights) is below this value skip the MLPs (raw = 0).  0 = off (dense, the parity path);
+        # output error <= 2 * N_samples * eps
+        'cull_mask_eps': 0.0,
         # one-launch multi-tensor Adam (csrc/adam.cu) instead of torch.optim.Adam's per-group kernels
         'fused_adam': True,
     },

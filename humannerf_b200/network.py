@@ -142,6 +142,7 @@ class Network(nn.Module):
             cn_freqs=cn_cfg.multires)
         self._packed_field = ops.PackedField(self._spec)
         self._vol_cache = None
+        self.last_cull_fraction = 0.0
         self.motion_weights_vol = None
         self.boundary_tensors = {}
 
@@ -234,6 +235,7 @@ class Network(nn.Module):
 
         S = int(cfg.N_samples)
         heavy = bool(b200.get('heavy_outputs', True))
+        cull_eps = float(b200.get('cull_mask_eps', 0.0))
         ignore_nr = bool(cfg.ignore_non_rigid_motions)
         nr_w, nr_b, cn_w, cn_b = self._field_weights()
         packed = None
@@ -241,6 +243,7 @@ class Network(nn.Module):
             packed = self._packed_field.refresh(nr_w, nr_b, cn_w, cn_b, cond)
 
         outs = []
+        n_kept = 0
         R = rays_o.shape[0]
         chunk = int(cfg.chunk)
         for a in range(0, R, chunk):
@@ -257,10 +260,26 @@ class Network(nn.Module):
             z = ops.sample_z(near[a:b], far[a:b], S, t_rand)
             x_skel, mask, bw = ops.motion_field(scale_Rs[0], Ts[0], vol_j, bbox_min, bbox_scale,
                                                 rays_o=o_c, rays_d=d_c, z=z, want_weights=heavy)
-            raw, xyz, offs = ops.canonical_field(self._spec, x_skel.reshape(-1, 3), cond, hann, nr_w, nr_b,
+            n = b - a
+            xs_flat = x_skel.reshape(-1, 3)
+            keep_idx = None
+            if cull_eps > 0.0 and not torch.is_grad_enabled():
+                # empty-space skipping (opt-in): a sample's alpha is (1 - exp(-sigma delta)) *
+                # mask <= mask, so dropping the samples with mask < eps changes no compositing weight by
+                # more than eps and no output by more than 2 * S * eps.  They keep xyz = x_skel, offset = 0
+                # and raw = 0 (sigma = 0).  torch.nonzero synchronises with the host: render path only.
+                keep_idx = torch.nonzero(mask.reshape(-1) >= cull_eps)[:, 0]
+                n_kept += int(keep_idx.numel())
+                xs_in = ops.gather_rows(xs_flat, keep_idx)
+            else:
+                xs_in = xs_flat
+            raw, xyz, offs = ops.canonical_field(self._spec, xs_in, cond, hann, nr_w, nr_b,
                                                  cn_w, cn_b, ignore_non_rigid=ignore_nr, precision=precision,
                                                  packed=packed)
-            n = b - a
+            if keep_idx is not None:
+                raw = ops.scatter_rows(raw, keep_idx, torch.zeros(n * S, 4, device=dev))
+                xyz = ops.scatter_rows(xyz, keep_idx, xs_flat)
+                offs = ops.scatter_rows(offs, keep_idx, torch.zeros(n * S, 3, device=dev))
             xyz = xyz.view(n, S, 3)
             rgb, acc, depth, weights, cnl_xyz, cnl_rgb, w_max, rgbs = ops.composite(
                 raw.view(n, S, 4), mask, z, d_c, xyz, bgcolor, heavy=heavy)
@@ -273,6 +292,8 @@ class Network(nn.Module):
 
         if not outs:
             raise RuntimeError('humannerf_b200.Network.forward: no rays')
+        if cull_eps > 0.0 and not torch.is_grad_enabled():
+            self.last_cull_fraction = 1.0 - n_kept / float(R * S)
         all_ret = {k: (outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs], dim=0)) for k in outs[0]}
         for k in all_ret:
             all_ret[k] = all_ret[k].reshape(lead_shape + list(all_ret[k].shape[1:]))

@@ -164,10 +164,15 @@ class _MotionField(torch.autograd.Function):
         x_skel = torch.empty(n_rays, S, 3, dtype=torch.float32, device=dev)
         mask = torch.empty(n_rays, S, 1, dtype=torch.float32, device=dev)
         weights = torch.empty(n_rays, S, J, dtype=torch.float32, device=dev) if want_weights else None
+        # corner table (27.6 MB at J = 24, V = 32): built by the forward call, reused by the backward
+        tbytes = int(lib.hn_motion_field_workspace_bytes(J, V))
+        table = torch.empty(tbytes, dtype=torch.uint8, device=dev) if n_rays * S >= 4096 else None
         with torch.cuda.device(dev), _timed('motion_field_fwd'):
             check(lib.hn_motion_field_fwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
                                           ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(x_skel),
-                                          ptr(mask), ptr(weights), stream_ptr()), 'motion_field_fwd')
+                                          ptr(mask), ptr(weights), ptr(table), tbytes if table is not None else 0,
+                                          stream_ptr()), 'motion_field_fwd')
+        ctx.table = table
         ctx.save_for_backward(rays_o, rays_d, z, pts, Rs, Ts, vol, bbox_min, bbox_scale, x_skel, mask)
         ctx.dims = (n_rays, S, J, V)
         if weights is None:
@@ -191,7 +196,7 @@ class _MotionField(torch.autograd.Function):
             check(lib.hn_motion_field_bwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
                                           ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(g_x), ptr(g_m),
                                           ptr(g_w), ptr(x_skel), ptr(mask), ptr(d_vol), ptr(d_Rs), ptr(d_Ts),
-                                          stream_ptr()),
+                                          ptr(ctx.table), stream_ptr()),
                   'motion_field_bwd')
         return None, None, None, None, d_Rs, d_Ts, d_vol, None, None, None
 
@@ -437,6 +442,19 @@ class _ScatterRows(torch.autograd.Function):
         with torch.cuda.device(g.device):
             check(lib.hn_gather_rows(n, c, ptr(g.reshape(-1, c)), ptr(index), ptr(out), stream_ptr()), 'gather_rows')
         return out, None, None
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """out[r] = src[index[r]] for a (N, C) fp32 matrix (rows with a negative index come back as zeros).
+    Not differentiable (used by the no-grad empty-space skipping)."""
+    lib = _lib.load()
+    src = _f32c(src)
+    index = index.to(torch.int64).contiguous()
+    n, c = index.shape[0], src.shape[-1]
+    out = torch.empty(n, c, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.hn_gather_rows(n, c, ptr(src.reshape(-1, c)), ptr(index), ptr(out), stream_ptr()), 'gather_rows')
+    return out
 
 
 def scatter_rows(src: torch.Tensor, index: torch.Tensor, base: torch.Tensor) -> torch.Tensor:

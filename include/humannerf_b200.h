@@ -82,16 +82,23 @@ int hn_sample_z(int64_t n_rays, int n_samples, const float* near, const float* f
  * Rs (J,3,3), Ts (J,3): motion bases; vol (>=J, V, V, V) blend-weight volume indexed [z][y][x];
  * bbox_min, bbox_scale: 3 floats each (device).  Trilinear, align_corners=True, zero padding.
  * Outputs: x_skel (P,3), mask (P) = sum_j w_j, weights (P,J) nullable.  J <= 32.
+ * workspace (nullable, 16-byte aligned, hn_motion_field_workspace_bytes): when given, the call first
+ * builds the corner table (per joint and stencil cell the 8 corner values, zero outside the volume, in
+ * one 32-byte sector) and the lookups read it instead of the volume; the filled workspace can be handed
+ * to hn_motion_field_bwd as `table`.
  */
+int64_t hn_motion_field_workspace_bytes(int n_joints, int vol_size);
 int hn_motion_field_fwd(int64_t n_rays, int n_samples, int n_joints, int vol_size,
                         const float* pts, const float* rays_o, const float* rays_d, const float* z,
                         const float* Rs, const float* Ts, const float* vol,
                         const float* bbox_min, const float* bbox_scale,
-                        float* x_skel, float* mask, float* weights, void* stream);
+                        float* x_skel, float* mask, float* weights,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Backward of the above.  d_x_skel (P,3), d_mask (P), d_weights (P,J) are nullable upstream
  * gradients.  x_skel_fwd (P,3) and mask_fwd (P) are the forward's outputs (both nullable together):
  * when given, the kernel skips re-evaluating the 24 lookups that only rebuild them.
+ * table (nullable): the corner table a forward call left in its workspace (same vol).
  * Accumulates (+=) into d_vol (J,V,V,V), d_Rs (J,3,3), d_Ts (J,3): caller zeroes.
  */
 int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_size,
@@ -100,7 +107,7 @@ int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
                         const float* bbox_min, const float* bbox_scale,
                         const float* d_x_skel, const float* d_mask, const float* d_weights,
                         const float* x_skel_fwd, const float* mask_fwd,
-                        float* d_vol, float* d_Rs, float* d_Ts, void* stream);
+                        float* d_vol, float* d_Rs, float* d_Ts, const void* table, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a11-a14  embedders/{hannw_fourier,fourier}.py, non_rigid_motion_mlps/mlp_offset.py:74-114,

@@ -555,6 +555,39 @@ def test_network_eval_bf16(sd, frame):
         report('bf16.eval_' + k, out[k], g['eval_' + k], 2e-2 if k != 'depth' else 6e-2)
 
 
+@pytest.mark.parametrize('precision,eps', [('fp32', 1e-7), ('bf16', 1e-5)])
+def test_empty_space_skipping_bound(sd, frame, precision, eps):
+    """cfg.b200.cull_mask_eps (opt-in): samples whose foreground likelihood is below eps
+    skip the MLPs.  Stated bound: every per-ray output within 2 * N_samples * eps of the dense render -
+    2.6e-5 at eps = 1e-7, i.e. inside the 1e-4 parity bound against the reference's golden render."""
+    g = gold('network_e2e.npz')
+    net, cfg = _network(sd, mlp_precision=precision)
+    data, _ = _e2e_data(g, frame)
+    cfg.perturb = 0.
+    net.eval()
+    with torch.no_grad():
+        dense = net(**data, iter_val=cfg.eval_iter)
+        cfg.b200.cull_mask_eps = eps
+        try:
+            culled = net(**data, iter_val=cfg.eval_iter)
+        finally:
+            cfg.b200.cull_mask_eps = 0.0
+    frac = net.last_cull_fraction
+    print(f'[parity] culling eps={eps:g} ({precision}): {100 * frac:.1f} % of the samples skipped')
+    assert 0.0 < frac < 1.0
+    bound = 2 * cfg.N_samples * eps
+    for k in ('rgb', 'alpha'):
+        err = float((culled[k] - dense[k]).abs().max())
+        print(f'[parity] culled vs dense {k}: max abs {err:.3e} (bound {bound:.1e})')
+        assert err <= bound
+    if precision == 'fp32':
+        for k in ('rgb', 'alpha', 'depth'):
+            report('culled.eval_' + k, culled[k], g['eval_' + k], 1e-4, 1e-4)
+    # a culled sample keeps xyz = x_skel, offset = 0 and gets no compositing weight
+    w = culled['weights_on_rays']
+    assert float(w.min()) >= 0.0 and torch.isfinite(culled['xyz_on_rays']).all()
+
+
 def test_full_size_properties(ops, sd, frame):
     """BASELINE-size chunk (32768 rays x 128 samples) through the whole kernel chain; checked through
     size-independent properties instead of the (too slow) oracle."""
