@@ -429,6 +429,11 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
   }
 }
 
+// mlp_tc_cl.cu
+int launch_field_tcc(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const float* x_skel,
+                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                     const TrainBufs* bufs, int sms, cudaStream_t st);
+
 int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples) {
   TcPlan plan;
   if (make_tc_plan(p, plan) != 0) return -1;
@@ -523,6 +528,18 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
   // (results are garbage) to expose how much of the kernel time the epilogue accounts for
   const char* abl = getenv("HN_TC_ABLATE");
   const int ablate = abl ? atoi(abl) : 0;
+  // default: the tile-pair kernel below; HN_TC_KERNEL=cluster selects the experimental cluster kernel
+  // (mlp_tc_cl.cu: correct, but slower - its single tile per CTA exposes the ~2000-clk accumulator ->
+  // epilogue -> operand hand-over latency of every layer)
+  if (use_cluster_kernel() && sms >= 2) {
+    TrainBufs bufs;
+    if (save_for_backward) {
+      const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
+      if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
+    }
+    return launch_field_tcc(plan, pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets,
+                            save_for_backward ? &bufs : nullptr, sms, as_stream(stream));
+  }
   if (save_for_backward) {
     TrainBufs bufs;
     const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -94,6 +95,16 @@ struct PackJob {            // one per chunk, consumed by pack_weights_kernel
 
 static inline int round16(int v) { return (v + 15) & ~15; }
 
+// HN_TC_KERNEL=cluster selects the experimental cluster forward kernel (read once per process: the weight
+// image's chunk table depends on it)
+static inline bool use_cluster_kernel() {
+  static const bool v = [] {
+    const char* e = getenv("HN_TC_KERNEL");
+    return e != nullptr && e[0] == 'c';
+  }();
+  return v;
+}
+
 struct TcPlan {
   TcHeader hdr;
   std::vector<TcChunk> chunks, bwd_chunks;
@@ -133,6 +144,9 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
                          const float* bias, const float* fold_w, int fold_ld, int fold_k, bool transpose, int row0) {
     int kc_max = (int)(kStageBytes / (uint32_t)(n * 2)) / 16 * 16;
     if (kc_max > 240) kc_max = 240;                       // ksteps is a uint8
+    // for the experimental cluster kernel (HN_TC_KERNEL=cluster, mlp_tc_cl.cu) forward chunks never span
+    // more than one 32-column block of the A operand: it hands the operand over block by block
+    if (&table == &plan.chunks && kc_max > 32 && use_cluster_kernel()) kc_max = 32;
     for (int k0 = 0; k0 < k_pad; k0 += kc_max) {
       const int kc = std::min(kc_max, k_pad - k0);
       TcChunk c;

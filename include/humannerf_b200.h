@@ -40,6 +40,8 @@ int hn_has_tcgen05(void);
 /* Measurement aid: with the environment variable HN_TC_ABLATE & 8 set, block 0 of the tcgen05 forward
  * kernel accumulates cycle counters per role; this copies the 32 counters to the host and clears them. */
 int hn_debug_tc_prof(unsigned long long* out_host);
+/* same for the cluster kernel (16 counters) */
+int hn_debug_tcc_prof(unsigned long long* out_host);
 
 /* ------------------------------------------------------------------------------------------
  * a1  core/utils/camera_util.py:132-159  get_rays_from_KRT

@@ -52,5 +52,15 @@ if int(os.environ.get('HN_TC_ABLATE', '0')) & 8:
     names = {0: 'producer total', 1: 'producer wait-empty', 4: 'issuer0 total', 5: 'issuer0 wait a_ready', 6: 'issuer0 wait full',
              7: 'issuer0 issue', 10: 'issuer1 total', 11: 'issuer1 wait a_ready', 12: 'issuer1 wait full', 13: 'issuer1 issue',
              16: 'epi total', 17: 'epi wait acc', 18: 'epi encoding', 19: 'epi hidden work'}
-    for k, n in names.items():
-        print(f'  {n:24s} {v[k] / 1e6:10.2f} Mcyc')
+    if sum(v):
+        for k, n in names.items():
+            print(f'  {n:24s} {v[k] / 1e6:10.2f} Mcyc')
+    buf2 = (ctypes.c_ulonglong * 16)()
+    _lib.check(_lib.load().hn_debug_tcc_prof(buf2), 'prof')
+    v = [int(x) for x in buf2]
+    names = {0: 'producer total', 1: 'producer wait-empty', 4: 'issuer total', 5: 'issuer wait block/pe', 6: 'issuer wait full',
+             7: 'issuer issue', 8: 'epi total', 9: 'epi wait acc', 11: 'epi hidden blocks'}
+    if sum(v):
+        print(' cluster kernel:')
+        for k, n in names.items():
+            print(f'  {n:24s} {v[k] / 1e6:10.2f} Mcyc')

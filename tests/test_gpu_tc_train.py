@@ -371,3 +371,18 @@ def test_graphed_train_step_matches_eager(ops, precision):
         assert d <= 2e-3 and dm <= (2e-5 if precision == 'fp32' else 2e-4), (k, d, dm)
     print(f'[parity] graphed step ({precision}): worst mean parameter difference {worst_mean:.3e}')
     print(f'[parity] graphed step ({precision}): max parameter difference after 3 steps {worst:.3e}')
+
+
+def test_experimental_cluster_kernel_parity():
+    """The experimental cluster forward kernel (HN_TC_KERNEL=cluster, csrc/mlp_tc_cl.cu: TMA multicast of the
+    weight stream across a CTA pair, double-buffered TMEM accumulators, block-granular operand hand-over)
+    must pass the same forward parity and training tests as the default kernel.  The choice is read once
+    per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HN_TC_KERNEL='cluster')
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', '-k',
+                        'field_bf16_forward or network_eval_bf16 or field_bf16_backward',
+                        os.path.join(root, 'tests')], env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-1500:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
