@@ -225,6 +225,7 @@ def main():
         (rgb, alpha, depth) = 20 B / ray assembles the frame on every rank (render)."""
         cfg.b200.mlp_precision, cfg.perturb = 'bf16', 0.0
         cfg.b200.cull_mask_eps = cull_eps
+        cfg.b200.cache_eval_volume = True     # the decoded volume is pose independent: decoded once per weight version
         chunk0 = cfg.chunk
         if one_chunk:
             cfg.chunk = 1 << 30          # 180 GB of HBM: the whole frame's samples fit in one pass

@@ -168,11 +168,17 @@ class Network(nn.Module):
         cfg = get_cfg()
         cache_ok = (not self.training) and (not torch.is_grad_enabled()) and \
             bool(cfg.get('b200', {}).get('cache_eval_volume', False))
-        if cache_ok and self._vol_cache is not None and self._vol_cache[0] is priors:
+        # the decoded volume depends only on the decoder's parameters and the prior (deconv_vol_decoder.py:25-33),
+        # not on the pose: across eval frames it is the same tensor.  The cache key includes the parameters'
+        # in-place version counters, so an optimizer step in between invalidates it.
+        key = (priors.data_ptr(), priors._version, tuple(priors.shape),
+               tuple(p._version for p in self.mweight_vol_decoder.parameters()),
+               bool(getattr(self.mweight_vol_decoder, 'allow_tf32', False)))
+        if cache_ok and self._vol_cache is not None and self._vol_cache[0] == key:
             return self._vol_cache[1]
         vol = self.mweight_vol_decoder(motion_weights_priors=priors)
         if cache_ok:
-            self._vol_cache = (priors, vol)
+            self._vol_cache = (key, vol)
         return vol
 
     def forward(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec=None,
