@@ -202,9 +202,20 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const flo
       const int pbase = 4 + 6 * (int)t;
       HN_PROF_DECL;
       HN_PROF_T(m_t0);
+      // A dependent shared-memory round trip of this thread costs ~120 clk while MMAs are in flight
+      // (scripts/micro/umma_rate.cu): the NEXT chunk's table entry is fetched before this chunk's waits.
+      const uint32_t s_table = smem_u32(table);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        TcChunk ch_next = table[first_chunk];
         for (uint32_t c = first_chunk; c < n_chunks; ++c) {
-          const TcChunk ch = table[c];
+          const TcChunk ch = ch_next;
+          {
+            const uint32_t cn = c + 1 < n_chunks ? c + 1 : c;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(s_table + cn * 16u));
+            ch_next.w_off = w0; ch_next.bytes = w1; ch_next.a_off = w2;
+            ch_next.n = (uint16_t)(w3 & 0xFFFFu); ch_next.ksteps = (uint8_t)((w3 >> 16) & 0xFFu); ch_next.flags = (uint8_t)(w3 >> 24);
+          }
           if (ch.flags & 1) {
             // the A operand of this layer is complete (and the previous accumulator drained)
             HN_PROF_T(m_w);

@@ -107,9 +107,20 @@ field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, int m
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_const = ((kLboA >> 4) << 16);
       uint32_t stage = 0, phase = 0, a_phase = 0;
+      // the NEXT chunk's table entry is fetched before this chunk's waits (a dependent shared-memory round
+      // trip of the issuing thread costs ~120 clk while MMAs are in flight, scripts/micro/umma_rate.cu)
+      const uint32_t s_table = smem_u32(table);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        TcChunk ch_next = table[c_first];
         for (uint32_t c = c_first; c < c_last; ++c) {
-          const TcChunk ch = table[c];
+          const TcChunk ch = ch_next;
+          {
+            const uint32_t cn = c + 1 < c_last ? c + 1 : c;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(s_table + cn * 16u));
+            ch_next.w_off = w0; ch_next.bytes = w1; ch_next.a_off = w2;
+            ch_next.n = (uint16_t)(w3 & 0xFFFFu); ch_next.ksteps = (uint8_t)((w3 >> 16) & 0xFFu); ch_next.flags = (uint8_t)(w3 >> 24);
+          }
           if (ch.flags & 1) {
             mbar_wait(bar_ready, a_phase, 2);
             a_phase ^= 1;
