@@ -47,38 +47,67 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML from a background thread every
+    10 ms (pynvml), falling back to polling `nvidia-smi` when NVML is not importable."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self.stop_flag, self.thread, self.source = False, None, 'nvml'
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and all(t.strip().isdigit() for t in vis.split(',')) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv, self.source = None, 'nvidia-smi'
 
-    def _run(self):
+    def _run_nvml(self):
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.h))
+                self.reasons.update(n for n, bit in names.items() if mask & bit)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _run_smi(self):
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                if out.strip():
-                    self.rows.append([c.strip() for c in out.strip().split('\n')[0].split(',')])
+                r = [c.strip() for c in out.strip().split('\n')[0].split(',')] if out.strip() else []
+                if r and r[0].replace('.', '').isdigit():
+                    self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace('.', '').isdigit():
+                    self.max_mhz = max(self.max_mhz or 0.0, float(r[1]))
+                self.reasons.update(n for n, v in zip(names, r[2:6]) if v.lower().startswith('active'))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def start(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread = threading.Thread(target=self._run_nvml if self.nv else self._run_smi, daemon=True)
         self.thread.start()
 
     def stop(self):
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_min_mhz': min(self.sm) if self.sm else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
 # ----------------------------------------------------------------------------------------------
