@@ -194,6 +194,7 @@ def main():
     ap.add_argument('--warmup-ref', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true')
+    ap.add_argument('--no-skip-leg', action='store_true', help='skip the extra train leg with empty-space skipping')
     ap.add_argument('--eager', action='store_true', help='run the train step eagerly instead of as one CUDA graph')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='MLP arithmetic of the train step: bf16 tcgen05 kernels (default) or the fp32 SIMT parity path')
@@ -388,6 +389,40 @@ def main():
         ms_e2e = float(t[0])
     e2e = rays_total / (ms_e2e / 1e3)
 
+    # =========================== opt-in: the same step with empty-space skipping ====================
+    # cfg.b200.cull_in_training (eps = 1e-7): samples below the foreground-likelihood threshold skip the MLPs
+    # inside the step; gradients agree with the dense step to < 1e-6 relative
+    # (tests/test_gpu_tc_train.py::test_training_with_empty_space_skipping).  Reported next to `value`, never as it.
+    skip_result = None
+    if graphed is not None and args.precision == 'bf16' and not args.no_skip_leg:
+        cfg.b200.cull_mask_eps, cfg.b200.cull_in_training = 1e-7, True
+        try:
+            g_skip = GraphedTrainStep(net, crit, opt, frame_kw, bg01, N_PATCHES, PATCH, reducer=reducer, world=world)
+            for i in range(args.warmup):
+                g_skip(dev_batches[i], it_val)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(args.warmup, total_steps):
+                g_skip(dev_batches[i], it_val)
+            s1.record()
+            barrier()
+            ms_skip = s0.elapsed_time(s1)
+            if world > 1:
+                t = torch.tensor([ms_skip], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_skip = float(t[0])
+            kept = int(net.last_cull_count) if net.last_cull_count is not None else None
+            skip_result = {'cull_mask_eps': 1e-7, 'ms_per_step': ms_skip / args.steps, 'rays_per_sec': rays_total / (ms_skip / 1e3),
+                           'samples_kept_last_step_this_rank': kept,
+                           'samples_per_step_this_rank': N_PATCHES * PATCH * PATCH * N_SAMPLES,
+                           'gradient_rel_l2_vs_dense': '< 1e-6 (tests/test_gpu_tc_train.py::test_training_with_empty_space_skipping)'}
+            g_skip.graph = None
+        finally:
+            cfg.b200.cull_mask_eps, cfg.b200.cull_in_training = 0.0, False
+        if graphed is not None:
+            opt.lr_scale = graphed.sched[graphed._nf + 1:graphed._nf + 2]
+
     # =========================== rooflines from the per-op CUDA-event times ========================
     # Kernels inside a replayed graph cannot be bracketed by events; the same steps are therefore run once
     # more EAGERLY (same kernels, same inputs, per-op CUDA events on the launching stream).
@@ -434,6 +469,7 @@ def main():
         'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'step_mode': 'eager' if graphed is None else 'cuda_graph (training.GraphedTrainStep)',
+        'train_empty_space_skipping': skip_result,
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'ops_ms': op_table,
         'valid_rays_in_frame': int(n_valid),
     }

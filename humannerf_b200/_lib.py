@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-HN_ABI_VERSION = 2
+HN_ABI_VERSION = 3
 HN_MAX_LAYERS = 16
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
@@ -66,13 +66,13 @@ SIGNATURES = {
     'hn_motion_field_fwd': (_int, [_i64, _int, _int, _int] + [_p] * 13 + [_i64, _p]),
     'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 19),
     'hn_field_workspace_bytes': (_i64, [C.POINTER(FieldParams), _i64, _int, _int]),
-    'hn_field_fwd': (_int, [C.POINTER(FieldParams), _i64, _p, _p, _p, _int, _p, _p, _p, _p, _i64, _int, _int, _p, _p]),
+    'hn_field_fwd': (_int, [C.POINTER(FieldParams), _i64, _p, _p, _p, _int, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p]),
     'hn_field_bwd_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),
     'hn_field_bwd': (_int, [C.POINTER(FieldParams), C.POINTER(FieldGrads), _i64, _p, _p, _p, _int, _p, _p, _p, _p,
                             _p, _i64, _p, _i64, _p]),
     'hn_field_bwd_bf16_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),
     'hn_field_bwd_bf16': (_int, [C.POINTER(FieldParams), C.POINTER(FieldGrads), _i64, _p, _p, _p, _p, _int, _p, _p, _p,
-                                 _p, _p, _i64, _p, _p, _i64, _p]),
+                                 _p, _p, _i64, _p, _p, _i64, _p, _p]),
     'hn_field_packed_bytes': (_i64, [C.POINTER(FieldParams)]),
     'hn_field_pack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
     'hn_field_repack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),

@@ -165,6 +165,9 @@ _DEFAULTS: Dict[str, Any] = {
         # blend weights) is below this value skip the MLPs (raw = 0).  0 = off (dense, the parity path);
         # output error <= 2 * N_samples * eps
         'cull_mask_eps': 0.0,
+        # apply the skipping inside training steps too (bf16 path; device-side compaction, graph capturable);
+        # skipped samples contribute to no gradient - their true contributions are below eps * O(1)
+        'cull_in_training': False,
         # one-launch multi-tensor Adam (csrc/adam.cu) instead of torch.optim.Adam's per-group kernels
         'fused_adam': True,
     },

@@ -104,9 +104,13 @@ __device__ unsigned long long g_tc_prof[32];
 // ------------------------------------------------------------------------------------------
 template <bool kStore>
 __global__ void __launch_bounds__(kThreads, 1)
-field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, const float* __restrict__ x_skel,
+field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
+                const float* __restrict__ x_skel,
                 const float* __restrict__ hann_w, int ignore_non_rigid, float* __restrict__ raw,
                 float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs, int ablate) {
+  // n_dev (nullable): the number of samples actually present, read from device memory (empty-space skipping
+  // compacts the samples without telling the host); n_cap bounds it and sizes the buffers
+  const int64_t n_samples = n_dev ? min(max(__ldg(n_dev), (int64_t)0), n_cap) : n_cap;
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
   const uint8_t* image = packed + hdr->image_off;
@@ -518,7 +522,9 @@ int hn_field_fwd_fp32(const hn_field_params* p, int64_t n_samples, const float* 
 int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_skel, const float* cond,
                  const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
                  void* workspace, int64_t workspace_bytes, int save_for_backward, int precision,
-                 const void* packed, void* stream) {
+                 const void* packed, const int64_t* n_samples_dev, void* stream) {
+  if (precision == HN_PRECISION_FP32 && n_samples_dev)
+    return fail_arg("hn_field_fwd: a device-side sample count needs HN_PRECISION_BF16");
   if (precision == HN_PRECISION_FP32)
     return hn_field_fwd_fp32(p, n_samples, x_skel, cond, hann_w, ignore_non_rigid, raw, xyz, offsets, workspace,
                              workspace_bytes, save_for_backward, stream);
@@ -542,7 +548,7 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
   // default: the tile-pair kernel below; HN_TC_KERNEL=cluster selects the experimental cluster kernel
   // (mlp_tc_cl.cu: correct, but slower - its single tile per CTA exposes the ~2000-clk accumulator ->
   // epilogue -> operand hand-over latency of every layer)
-  if (use_cluster_kernel() && sms >= 2) {
+  if (use_cluster_kernel() && sms >= 2 && !n_samples_dev) {
     TrainBufs bufs;
     if (save_for_backward) {
       const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
@@ -558,14 +564,14 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemTotal), "hn_field_fwd/smem attr"));
     field_tc_kernel<true><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
-        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs, ablate);
+        pk, n_samples, n_samples_dev, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs, ablate);
   } else {
     TrainBufs bufs;
     memset(&bufs, 0, sizeof(bufs));
     HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemTotal), "hn_field_fwd/smem attr"));
     field_tc_kernel<false><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(
-        pk, n_samples, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs, ablate);
+        pk, n_samples, n_samples_dev, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets, bufs, ablate);
   }
   return launched("hn_field_fwd/tcgen05");
 }

@@ -35,9 +35,11 @@ __device__ __forceinline__ uint32_t mask_pack(uint32_t h2, uint32_t a_lo, uint32
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_samples, int mlp, const float* __restrict__ d_out,
+field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev, int mlp,
+                    const float* __restrict__ d_out,
                     int ld_out, int n_out, const TrainBufs bufs, const float* __restrict__ pos,
                     const float* __restrict__ hann_w, float* __restrict__ d_pos, int ld_dpos) {
+  const int64_t n_samples = n_dev ? min(max(__ldg(n_dev), (int64_t)0), n_cap) : n_cap;   // see field_tc_kernel
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
   const uint8_t* image = packed + hdr->image_off;
@@ -311,7 +313,7 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
                       const float* xyz, const float* cond, const float* hann_w, int ignore_non_rigid,
                       const float* d_raw, const float* d_xyz, const float* d_offsets, float* d_x_skel,
                       void* workspace, int64_t workspace_bytes, const void* packed, void* scratch,
-                      int64_t scratch_bytes, void* stream) {
+                      int64_t scratch_bytes, const int64_t* n_samples_dev, void* stream) {
   TcPlan plan;
   HN_TRY(make_tc_plan(p, plan));
   if (n_samples == 0) return 0;
@@ -342,13 +344,13 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   //    by the chain's epilogue (both encoding reads: skip layer and layer 0)
   if (d_xyz) HN_TRY(copy_cols(n, 3, d_xyz, 3, d_xyz_tot, 4, st));
   else HN_TRY(check_cuda(cudaMemsetAsync(d_xyz_tot, 0, (size_t)rows * 4 * sizeof(float), st), "hn_field_bwd_bf16/memset"));
-  field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4);
+  field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, n_samples_dev, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4);
   HN_TRY(launched("hn_field_bwd_bf16/canonical chain"));
   // 2. non-rigid MLP: its output gradient is d_xyz_tot + d_offsets; d_x_skel = d_xyz_tot + PE'(x_skel) . d(encoding)
   HN_TRY(copy_cols(n, 3, d_xyz_tot, 4, d_x_skel, 3, st));
   if (!ignore_non_rigid) {
     HN_TRY(add3(n, d_xyz_tot, 4, d_offsets, 3, dz_nr, 4, st));
-    field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3);
+    field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, n_samples_dev, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3);
     HN_TRY(launched("hn_field_bwd_bf16/non-rigid chain"));
   }
   // 3. weight / bias gradients from the images
@@ -385,7 +387,7 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
     }
   }
   if ((int)jobs.size() > kMaxWgradJobs) return fail_arg("hn_field_bwd_bf16: too many weight-gradient jobs");
-  if (!jobs.empty()) HN_TRY(launch_tile_wgrad(jobs.data(), (int)jobs.size(), n, st));
+  if (!jobs.empty()) HN_TRY(launch_tile_wgrad(jobs.data(), (int)jobs.size(), n, n_samples_dev, st));
   // 4. condition-code columns of the first non-rigid layer: the input is the same vector for every sample
   if (!ignore_non_rigid && p->cond_dim > 0 && g->nr_w[0] && g->nr_b[0]) {
     const int rows_w = p->nr_width, cols = p->cond_dim;

@@ -41,8 +41,14 @@ struct WgradJobTable {
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles, int tiles_per_slab, int slab_major) {
+tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles_cap, int n_slabs_cap,
+                  const int64_t* __restrict__ n_dev, int slab_major) {
   const WgradJob* jobs = tab.jobs;
+  // n_dev (nullable): number of samples actually present (device-side count, see field_tc_kernel); the slab
+  // decomposition keeps the host's slab COUNT and shrinks the slabs
+  int n_tiles = n_tiles_cap;
+  if (n_dev) n_tiles = (int)min((max(__ldg(n_dev), (int64_t)0) + 127) / 128, (int64_t)n_tiles_cap);
+  const int tiles_per_slab = max((n_tiles + n_slabs_cap - 1) / n_slabs_cap, 1);
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_full = s_base + kWgBarOff;
@@ -52,7 +58,7 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
   const uint32_t s_tmem_slot = s_drained + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWgBarOff + (2 * kWgStages + 2) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
+  const int n_slabs = n_slabs_cap;
   const int n_items = n_jobs * n_slabs;
 
   if (threadIdx.x == 0) {
@@ -159,10 +165,12 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const WgradJob job = jobs[slab_major ? item % n_jobs : item / n_slabs];
       const int m_tiles = (job.m + 127) / 128;
+      const int e_si = slab_major ? item / n_jobs : item % n_slabs;
+      const bool has_tiles = e_si * tiles_per_slab < n_tiles;      // an empty slab left the accumulators undefined
       mbar_wait(s_acc, acc_phase, 4);
       acc_phase ^= 1;
       tc_fence_after();
-      for (int mt = 0; mt < m_tiles; ++mt) {
+      for (int mt = 0; has_tiles && mt < m_tiles; ++mt) {
         const int r = mt * 128 + row;
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)mt * 256u;
         for (int c0 = 0; c0 < job.n; c0 += 16) {
@@ -226,7 +234,8 @@ __global__ void tile_unpack_kernel(int64_t n_samples, int n_feat, int f_pad, con
   }
 }
 
-int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, cudaStream_t st) {
+int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, const int64_t* n_samples_dev,
+                      cudaStream_t st) {
   if (n_jobs <= 0 || n_samples <= 0) return 0;
   if (n_jobs > kMaxWgradJobs) return fail_arg("tile_wgrad: at most %d jobs per launch", kMaxWgradJobs);
   WgradJobTable tab;
@@ -244,7 +253,7 @@ int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, 
   n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
   const int grid = std::min(n_jobs * n_slabs, sms);
   const char* ord = getenv("HN_WGRAD_SLAB_MAJOR");       // measurement aid (A/B of the item order)
-  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, tiles_per_slab, ord ? atoi(ord) : 0);
+  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, n_slabs, n_samples_dev, ord ? atoi(ord) : 0);
   return launched("tile_wgrad");
 }
 
@@ -297,7 +306,7 @@ int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, 
   for (int i = 0; i < n_jobs; ++i) HN_TRY(check_job(jobs_host[i]));
   cudaStream_t st = as_stream(stream);
   for (int i = 0; i < n_jobs; i += kMaxWgradJobs)
-    HN_TRY(launch_tile_wgrad(jobs_host + i, std::min(kMaxWgradJobs, n_jobs - i), n_samples, st));
+    HN_TRY(launch_tile_wgrad(jobs_host + i, std::min(kMaxWgradJobs, n_jobs - i), n_samples, nullptr, st));
   return 0;
 }
 

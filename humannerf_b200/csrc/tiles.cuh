@@ -19,6 +19,8 @@ __host__ __device__ __forceinline__ size_t tile_offset(int64_t s, int f, int f_p
 constexpr int kMaxWgradJobs = 48;   // per launch: the table is a kernel parameter (48 x 72 B < 4 KB)
 
 // jobs_host: HOST array of n_jobs <= kMaxWgradJobs jobs
-int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, cudaStream_t st);
+// n_samples_dev (nullable): device-side count of the samples actually present (<= n_samples)
+int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, const int64_t* n_samples_dev,
+                      cudaStream_t st);
 
 }  // namespace hn

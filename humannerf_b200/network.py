@@ -143,6 +143,7 @@ class Network(nn.Module):
         self._packed_field = ops.PackedField(self._spec)
         self._vol_cache = None
         self.last_cull_fraction = 0.0
+        self.last_cull_count = None
         self.motion_weights_vol = None
         self.boundary_tensors = {}
 
@@ -242,6 +243,7 @@ class Network(nn.Module):
         S = int(cfg.N_samples)
         heavy = bool(b200.get('heavy_outputs', True))
         cull_eps = float(b200.get('cull_mask_eps', 0.0))
+        cull_train = bool(b200.get('cull_in_training', False))
         ignore_nr = bool(cfg.ignore_non_rigid_motions)
         nr_w, nr_b, cn_w, cn_b = self._field_weights()
         packed = None
@@ -268,8 +270,25 @@ class Network(nn.Module):
                                                 rays_o=o_c, rays_d=d_c, z=z, want_weights=heavy)
             n = b - a
             xs_flat = x_skel.reshape(-1, 3)
-            keep_idx = None
-            if cull_eps > 0.0 and not torch.is_grad_enabled():
+            keep_idx, count = None, None
+            if cull_eps > 0.0 and torch.is_grad_enabled() and cull_train and precision == _lib.PRECISION_BF16:
+                # the same skipping inside a training step, without telling the host how many samples
+                # survive (fixed shapes: CUDA-graph capturable): the kept samples are compacted to the front
+                # of a P-row buffer and the tcgen05 kernels read the count from device memory.  A skipped
+                # sample contributes to no gradient; with mask < eps its true contributions are below
+                # eps * O(1) (d loss / d sigma carries the factor mask, and d loss / d mask reaches the
+                # parameters only through softmax / trilinear factors that are themselves below eps).
+                P = xs_flat.shape[0]
+                keep = mask.detach().reshape(-1) >= cull_eps
+                pos = torch.cumsum(keep.to(torch.int64), 0) - 1
+                count = (pos[-1:] + 1).contiguous()
+                slot = torch.where(keep, pos, torch.full_like(pos, P))
+                buf = torch.full((P + 1,), -1, dtype=torch.int64, device=dev)
+                buf.scatter_(0, slot, torch.arange(P, dtype=torch.int64, device=dev))
+                keep_idx = buf[:P].contiguous()
+                self.last_cull_count = count
+                xs_in = ops.gather_rows(xs_flat, keep_idx)
+            elif cull_eps > 0.0 and not torch.is_grad_enabled():
                 # empty-space skipping (opt-in): a sample's alpha is (1 - exp(-sigma delta)) *
                 # mask <= mask, so dropping the samples with mask < eps changes no compositing weight by
                 # more than eps and no output by more than 2 * S * eps.  They keep xyz = x_skel, offset = 0
@@ -281,7 +300,7 @@ class Network(nn.Module):
                 xs_in = xs_flat
             raw, xyz, offs = ops.canonical_field(self._spec, xs_in, cond, hann, nr_w, nr_b,
                                                  cn_w, cn_b, ignore_non_rigid=ignore_nr, precision=precision,
-                                                 packed=packed)
+                                                 packed=packed, count=count)
             if keep_idx is not None:
                 raw = ops.scatter_rows(raw, keep_idx, torch.zeros(n * S, 4, device=dev))
                 xyz = ops.scatter_rows(xyz, keep_idx, xs_flat)

@@ -286,7 +286,7 @@ class _CanonicalField(torch.autograd.Function):
     [nr_w..., nr_b..., cn_w..., cn_b...]."""
 
     @staticmethod
-    def forward(ctx, spec: FieldSpec, ignore_non_rigid: bool, precision: int, packed, need_grad: bool, x_skel,
+    def forward(ctx, spec: FieldSpec, ignore_non_rigid: bool, precision: int, packed, need_grad: bool, count, x_skel,
                 cond, hann_w, *flat):
         lib = _lib.load()
         nl, cl = spec.nr_layers, spec.cn_layers
@@ -306,10 +306,10 @@ class _CanonicalField(torch.autograd.Function):
         with torch.cuda.device(dev), _timed('field_fwd_bf16' if precision == _lib.PRECISION_BF16 else 'field_fwd_fp32'):
             check(lib.hn_field_fwd(C.byref(fp), P, ptr(x_skel), ptr(cond), ptr(hann_w), 1 if ignore_non_rigid else 0,
                                    ptr(raw), ptr(xyz), ptr(off), ptr(ws), wbytes, 1 if need_grad else 0, precision,
-                                   ptr(packed), stream_ptr()), 'field_fwd')
+                                   ptr(packed), ptr(count), stream_ptr()), 'field_fwd')
         if need_grad:
             ctx.spec, ctx.ignore, ctx.precision = spec, ignore_non_rigid, precision
-            ctx.ws, ctx.packed = ws, packed
+            ctx.ws, ctx.packed, ctx.count = ws, packed, count
             ctx.save_for_backward(x_skel, cond, hann_w, xyz, *flat)
         return raw, xyz, off
 
@@ -342,7 +342,7 @@ class _CanonicalField(torch.autograd.Function):
                 check(lib.hn_field_bwd_bf16(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(xyz), ptr(cond), ptr(hann_w),
                                             1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
                                             ptr(ctx.ws), ctx.ws.numel(), ptr(ctx.packed), ptr(scratch), sbytes,
-                                            stream_ptr()), 'field_bwd_bf16')
+                                            ptr(ctx.count), stream_ptr()), 'field_bwd_bf16')
         else:
             sbytes = int(lib.hn_field_bwd_scratch_bytes(C.byref(fp), P))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
@@ -350,20 +350,26 @@ class _CanonicalField(torch.autograd.Function):
                 check(lib.hn_field_bwd(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(cond), ptr(hann_w),
                                        1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
                                        ptr(ctx.ws), ctx.ws.numel(), ptr(scratch), sbytes, stream_ptr()), 'field_bwd')
-        ctx.ws = ctx.packed = None
-        return (None, None, None, None, None, d_x, None, None, *grads)
+        ctx.ws = ctx.packed = ctx.count = None
+        return (None, None, None, None, None, None, d_x, None, None, *grads)
 
 
 def canonical_field(spec: FieldSpec, x_skel, cond, hann_w, nr_w, nr_b, cn_w, cn_b, *,
-                    ignore_non_rigid=False, precision=_lib.PRECISION_FP32, packed=None):
-    """raw (P,4), xyz (P,3), offsets (P,3) for canonical-space samples x_skel (P,3)."""
+                    ignore_non_rigid=False, precision=_lib.PRECISION_FP32, packed=None, count=None):
+    """raw (P,4), xyz (P,3), offsets (P,3) for canonical-space samples x_skel (P,3).
+    `count` (bf16 path only): int64 device tensor with the number of valid leading rows of x_skel - the rest
+    of the P rows is capacity that the kernels neither read nor write (device-side empty-space skipping)."""
+    if count is not None:
+        if precision != _lib.PRECISION_BF16:
+            raise RuntimeError('humannerf_b200: a device-side sample count needs the bf16 path')
+        count = count.to(torch.int64).reshape(1).contiguous()
     flat = list(nr_w) + list(nr_b) + list(cn_w) + list(cn_b)
     cond = _f32c(cond).reshape(-1)
     hann_w = _f32c(hann_w).reshape(-1)
     # Function.forward always runs with grad mode off, so the decision to keep activations for the
     # backward pass is taken here
     need_grad = torch.is_grad_enabled() and (x_skel.requires_grad or any(t.requires_grad for t in flat))
-    return _CanonicalField.apply(spec, bool(ignore_non_rigid), int(precision), packed, need_grad, x_skel, cond,
+    return _CanonicalField.apply(spec, bool(ignore_non_rigid), int(precision), packed, need_grad, count, x_skel, cond,
                                  hann_w, *flat)
 
 
@@ -439,22 +445,46 @@ class _ScatterRows(torch.autograd.Function):
         n = index.shape[0]
         c = g.shape[-1]
         out = torch.empty(n, c, dtype=torch.float32, device=g.device)
+        g_base = None
         with torch.cuda.device(g.device):
             check(lib.hn_gather_rows(n, c, ptr(g.reshape(-1, c)), ptr(index), ptr(out), stream_ptr()), 'gather_rows')
-        return out, None, None
+            if ctx.needs_input_grad[2]:
+                # rows that were overwritten by `src` do not depend on `base`
+                g_base = g.clone()
+                zeros = torch.zeros(n, c, dtype=torch.float32, device=g.device)
+                check(lib.hn_scatter_rows(n, c, ptr(zeros), ptr(index), ptr(g_base), stream_ptr()), 'scatter_rows')
+        return out, None, g_base
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, index):
+        lib = _lib.load()
+        n, c = index.shape[0], src.shape[-1]
+        out = torch.empty(n, c, dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib.hn_gather_rows(n, c, ptr(src.reshape(-1, c)), ptr(index), ptr(out), stream_ptr()), 'gather_rows')
+        ctx.save_for_backward(index)
+        ctx.src_shape = src.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (index,) = ctx.saved_tensors
+        g = _f32c(g)
+        c = g.shape[-1]
+        out = torch.zeros(ctx.src_shape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            # the index holds every source row at most once (a compaction), so a plain scatter is the adjoint
+            check(lib.hn_scatter_rows(index.shape[0], c, ptr(g), ptr(index), ptr(out), stream_ptr()), 'scatter_rows')
+        return out, None
 
 
 def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
-    """out[r] = src[index[r]] for a (N, C) fp32 matrix (rows with a negative index come back as zeros).
-    Not differentiable (used by the no-grad empty-space skipping)."""
-    lib = _lib.load()
-    src = _f32c(src)
-    index = index.to(torch.int64).contiguous()
-    n, c = index.shape[0], src.shape[-1]
-    out = torch.empty(n, c, dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
-        check(lib.hn_gather_rows(n, c, ptr(src.reshape(-1, c)), ptr(index), ptr(out), stream_ptr()), 'gather_rows')
-    return out
+    """out[r] = src[index[r]] for a (N, C) fp32 matrix; rows with a negative index come back as zeros.
+    Differentiable in `src` provided no source row appears twice in `index` (compaction)."""
+    return _GatherRows.apply(_f32c(src), index.to(torch.int64).contiguous())
 
 
 def scatter_rows(src: torch.Tensor, index: torch.Tensor, base: torch.Tensor) -> torch.Tensor:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 2
+#define HN_ABI_VERSION 3
 #define HN_MAX_LAYERS 16
 
 /* ABI version of the loaded library (compare with HN_ABI_VERSION). */
@@ -159,12 +159,16 @@ int64_t hn_field_workspace_bytes(const hn_field_params* p, int64_t n_samples,
 /* cond (cond_dim), hann_w (nr_freqs) are device vectors.  ignore_non_rigid != 0 skips the
  * non-rigid MLP (cfg.ignore_non_rigid_motions, network.py:264,276-277): xyz = x_skel, offsets = 0.
  * Outputs: raw (P,4), xyz (P,3), offsets (P,3).
- * For HN_PRECISION_BF16, `packed` is the bf16 weight image made by hn_field_pack_bf16. */
+ * For HN_PRECISION_BF16, `packed` is the bf16 weight image made by hn_field_pack_bf16.
+ * n_samples_dev (nullable, HN_PRECISION_BF16 only): device int64 holding the number of samples actually
+ * present in the first rows of x_skel (<= n_samples, which then is the capacity every buffer is sized
+ * for).  Lets a caller compact samples on the device (empty-space skipping) without a host round trip,
+ * e.g. inside a CUDA graph; rows past the count are neither read nor written. */
 int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_skel,
                  const float* cond, const float* hann_w, int ignore_non_rigid,
                  float* raw, float* xyz, float* offsets,
                  void* workspace, int64_t workspace_bytes, int save_for_backward,
-                 int precision, const void* packed, void* stream);
+                 int precision, const void* packed, const int64_t* n_samples_dev, void* stream);
 
 /* Backward (HN_PRECISION_FP32 path).  d_raw (P,4), d_xyz (P,3) nullable, d_offsets (P,3) nullable.
  * Writes d_x_skel (P,3) and accumulates parameter gradients into `g`. `scratch` must hold
@@ -185,7 +189,8 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
                       const float* x_skel, const float* xyz, const float* cond, const float* hann_w,
                       int ignore_non_rigid, const float* d_raw, const float* d_xyz, const float* d_offsets,
                       float* d_x_skel, void* workspace, int64_t workspace_bytes, const void* packed,
-                      void* scratch, int64_t scratch_bytes, void* stream);
+                      void* scratch, int64_t scratch_bytes, const int64_t* n_samples_dev /*nullable, as in
+                      hn_field_fwd*/, void* stream);
 
 /* bf16 weight image for the tcgen05 kernel: weights re-tiled into the UMMA shared-memory
  * core-matrix layout, in consumption order, with the condition code folded into the first

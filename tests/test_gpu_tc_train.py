@@ -386,3 +386,86 @@ def test_experimental_cluster_kernel_parity():
                         os.path.join(root, 'tests')], env=env, cwd=root, capture_output=True, text=True, timeout=900)
     print(r.stdout[-1500:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_training_with_empty_space_skipping(ops):
+    """cfg.b200.cull_in_training: samples with foreground likelihood < eps = 1e-7 skip the MLPs inside a
+    training step (device-side compaction, sample count read from device memory by the tcgen05 kernels).
+    Against the dense bf16 step on the same inputs: per-ray outputs within 2 * S * eps, and the gradient of
+    every parameter tensor within 2e-3 relative L2 (the kept samples are the same, only regrouped into
+    different tiles: what remains is fp32 atomic ordering plus the skipped samples' < eps contributions).
+    Also runs the skipping step through the CUDA-graph path."""
+    import os
+    from humannerf_b200 import synthetic as syn
+    from humannerf_b200.config import make_cfg
+    from humannerf_b200.network import Network
+    from humannerf_b200.training import GraphedTrainStep
+    GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    g = np.load(os.path.join(GOLD, 'network_e2e.npz'))
+    st = np.load(os.path.join(GOLD, 'stages.npz'))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    cfg = make_cfg()
+    cfg.b200.mlp_precision = 'bf16'
+    cfg.b200.heavy_outputs = False
+    cfg.perturb = 1.0
+    sd = syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True)
+    fr = {k: T(v) for k, v in syn.make_frame(0).items()}
+    data = dict(rays=T(st['rays']), near=T(st['near']), far=T(st['far']), dst_Rs=fr['dst_Rs'], dst_Ts=fr['dst_Ts'],
+                cnl_gtfms=fr['cnl_gtfms'], motion_weights_priors=fr['motion_weights_priors'], dst_posevec=fr['dst_posevec'],
+                cnl_bbox_min_xyz=fr['cnl_bbox_min_xyz'], cnl_bbox_max_xyz=fr['cnl_bbox_max_xyz'],
+                cnl_bbox_scale_xyz=fr['cnl_bbox_scale_xyz'], bgcolor=T(g['bgcolor']))
+    res = {}
+    try:
+        for mode, eps in (('dense', 0.0), ('skip', 1e-7)):
+            cfg.b200.cull_mask_eps, cfg.b200.cull_in_training = eps, eps > 0
+            net = Network()
+            net.load_state_dict(sd)
+            net = net.to(DEV).train()
+            out = net(**data, iter_val=torch.full((1,), 30000), t_rand=T(st['t_rand']))
+            loss = (out['rgb'] * T(g['train_loss_w'])).sum() + 0.3 * out['alpha'].sum() + 0.1 * out['depth'].sum()
+            loss.backward()
+            torch.cuda.synchronize()
+            res[mode] = ({k: out[k].detach().clone() for k in ('rgb', 'alpha', 'depth')},
+                         {k: p.grad.detach().clone() for k, p in net.named_parameters()},
+                         None if net.last_cull_count is None else int(net.last_cull_count))
+    finally:
+        cfg.b200.cull_mask_eps, cfg.b200.cull_in_training = 0.0, False
+    n_samples = st['t_rand'].size
+    kept = res['skip'][2]
+    print(f'[parity] training skip: {kept} of {n_samples} samples kept ({100.0 * (1 - kept / n_samples):.1f} % skipped)')
+    assert 0 < kept < n_samples
+    bound = 2 * cfg.N_samples * 1e-7
+    for k in ('rgb', 'alpha'):
+        err = float((res['skip'][0][k] - res['dense'][0][k]).abs().max())
+        print(f'[parity] training skip vs dense {k}: max abs {err:.3e} (bound {bound:.1e})')
+        assert err <= bound
+    bad = []
+    for k, gd in res['dense'][1].items():
+        gs = res['skip'][1][k]
+        e = float((gs.double() - gd.double()).norm() / (gd.double().norm() + 1e-30))
+        print(f'[parity] training skip grad {k}: rel L2 vs dense {e:.3e}')
+        if not e < 2e-3:
+            bad.append((k, e))
+    assert not bad, bad
+
+
+def test_graphed_step_with_skipping(ops):
+    """The skipping step is captured in a CUDA graph (no host round trip for the sample count): three replays
+    give the same losses as three dense replays within 1e-3 relative."""
+    from humannerf_b200.config import get_cfg
+    from humannerf_b200.training import GraphedTrainStep
+    losses = {}
+    try:
+        for mode, eps in (('dense', 0.0), ('skip', 1e-7)):
+            net, opt, crit, kw, bg01, batches = _train_setup('bf16')
+            cfg = get_cfg()
+            cfg.b200.cull_mask_eps, cfg.b200.cull_in_training = eps, eps > 0
+            step = GraphedTrainStep(net, crit, opt, kw, bg01, 4, 16)
+            losses[mode] = [float(step(b, 60000 + i)) for i, b in enumerate(batches)]
+            torch.cuda.synchronize()
+    finally:
+        cfg = get_cfg()
+        cfg.b200.cull_mask_eps, cfg.b200.cull_in_training = 0.0, False
+    print(f'[parity] graphed skipping step losses dense {losses["dense"]} skip {losses["skip"]}')
+    for a, b in zip(losses['dense'], losses['skip']):
+        assert abs(a - b) <= 1e-3 * abs(a), (a, b)
