@@ -76,6 +76,8 @@ SIGNATURES = {
     'hn_field_packed_bytes': (_i64, [C.POINTER(FieldParams)]),
     'hn_field_pack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
     'hn_field_repack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
+    'hn_pose_fk_fwd': (_int, [_int, _p, _p, _p, _p, _p, _p, _p]),
+    'hn_pose_fk_bwd': (_int, [_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'hn_adam_plan_bytes': (_i64, [C.POINTER(AdamTensor), _int]),
     'hn_adam_n_chunks': (_i64, [C.POINTER(AdamTensor), _int]),
     'hn_adam_plan': (_int, [C.POINTER(AdamTensor), _int, _p, _i64]),

@@ -168,6 +168,9 @@ _DEFAULTS: Dict[str, Any] = {
         # apply the skipping inside training steps too (bf16 path; device-side compaction, graph capturable);
         # skipped samples contribute to no gradient - their true contributions are below eps * O(1)
         'cull_in_training': False,
+        # Rodrigues + corrected rotations + forward kinematics in one kernel (csrc/pose_fk.cu) when the pose
+        # decoder module exposes its axis-angle output ('rvec'); False = the torch modules of nn_util.py
+        'fused_front_end': True,
         # one-launch multi-tensor Adam (csrc/adam.cu) instead of torch.optim.Adam's per-group kernels
         'fused_adam': True,
     },

@@ -25,7 +25,7 @@ import torch.nn as nn
 from humannerf_b200 import _lib, ops
 from humannerf_b200.config import get_cfg
 from humannerf_b200.embedders.hannw_fourier import hann_window_weights
-from humannerf_b200.nn_util import MotionBasisComputer
+from humannerf_b200.nn_util import SMPL_PARENT, MotionBasisComputer
 
 
 def _load_symbol(module_name: str, symbol: str):
@@ -197,9 +197,16 @@ class Network(nn.Module):
         priors = motion_weights_priors[None, ...] if motion_weights_priors.dim() == 4 else motion_weights_priors
 
         # 1. pose refinement (network.py:667-695)
-        if (not cfg.pose_decoder_off) and it >= cfg.pose_decoder.get('kick_in_iter', 0):
-            refined = self.pose_decoder(dst_posevec)['Rs']
-            dst_Rs = torch.cat([dst_Rs[:, 0:1], self._multiply_corrected_Rs(dst_Rs[:, 1:], refined)], dim=1)
+        refine = (not cfg.pose_decoder_off) and it >= cfg.pose_decoder.get('kick_in_iter', 0)
+        fused_front = bool(b200.get('fused_front_end', True))
+        rvec = None
+        if refine:
+            pd_out = self.pose_decoder(dst_posevec)
+            if fused_front and 'rvec' in pd_out:
+                rvec = pd_out['rvec'].reshape(-1, 3)          # Rodrigues happens inside ops.pose_fk
+            else:
+                fused_front = False
+                dst_Rs = torch.cat([dst_Rs[:, 0:1], self._multiply_corrected_Rs(dst_Rs[:, 1:], pd_out['Rs'])], dim=1)
 
         # 2. condition code and hann window (network.py:697-738)
         nr_cfg = cfg.non_rigid_motion_mlp
@@ -219,7 +226,16 @@ class Network(nn.Module):
             else _lib.PRECISION_FP32
         if hasattr(self.mweight_vol_decoder, 'allow_tf32'):
             self.mweight_vol_decoder.allow_tf32 = precision == _lib.PRECISION_BF16
-        scale_Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts, cnl_gtfms)
+        if fused_front:
+            # Rodrigues + corrected rotations + the forward-kinematics chain in one launch (csrc/pose_fk.cu);
+            # the LU inverse (the reference's torch.inverse without its host-side check) and the product
+            # with the canonical transforms stay torch ops
+            _, G = ops.pose_fk(rvec, dst_Rs[0], dst_Ts[0], SMPL_PARENT[:dst_Rs.shape[1]])
+            inv = torch.linalg.inv_ex(G, check_errors=False).inverse
+            f = torch.matmul(cnl_gtfms[0], inv)
+            scale_Rs, Ts = f[None, :, :3, :3], f[None, :, :3, 3]
+        else:
+            scale_Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts, cnl_gtfms)
         vol = self._decode_volume(priors.float())[0]
         self.motion_weights_vol = vol
         # outputs of the replicated per-frame front end; the multi-GPU train step exchanges the

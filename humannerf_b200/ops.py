@@ -217,6 +217,47 @@ def motion_field(Rs, Ts, vol, bbox_min, bbox_scale, *, pts=None, rays_o=None, ra
 
 
 # ---------------------------------------------------------------------------
+# per-frame front end: Rodrigues + corrected rotations + forward kinematics
+# ---------------------------------------------------------------------------
+class _PoseFK(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rvec, dst_Rs, dst_Ts, parents):
+        lib = _lib.load()
+        J = dst_Rs.shape[0]
+        par = (C.c_int32 * J)(*[int(v) for v in parents])
+        Rs_out = torch.empty(J, 3, 3, dtype=torch.float32, device=dst_Rs.device)
+        G = torch.empty(J, 4, 4, dtype=torch.float32, device=dst_Rs.device)
+        with torch.cuda.device(dst_Rs.device):
+            check(lib.hn_pose_fk_fwd(J, par, ptr(rvec), ptr(dst_Rs), ptr(dst_Ts), ptr(Rs_out), ptr(G), stream_ptr()),
+                  'pose_fk_fwd')
+        ctx.par = par
+        if rvec is not None:
+            ctx.save_for_backward(rvec, dst_Rs, dst_Ts, Rs_out, G)
+        ctx.mark_non_differentiable(Rs_out)
+        return Rs_out, G
+
+    @staticmethod
+    def backward(ctx, _g_rs, g_G):
+        lib = _lib.load()
+        rvec, dst_Rs, dst_Ts, Rs_out, G = ctx.saved_tensors
+        J = dst_Rs.shape[0]
+        d_rvec = torch.empty_like(rvec)
+        with torch.cuda.device(dst_Rs.device):
+            check(lib.hn_pose_fk_bwd(J, ctx.par, ptr(rvec), ptr(dst_Rs), ptr(Rs_out), ptr(dst_Ts), ptr(G), ptr(_f32c(g_G)),
+                                     None, ptr(d_rvec), stream_ptr()), 'pose_fk_bwd')
+        return d_rvec, None, None, None
+
+
+def pose_fk(rvec: Optional[torch.Tensor], dst_Rs: torch.Tensor, dst_Ts: torch.Tensor, parents: Sequence[int]):
+    """Corrected local rotations (J,3,3) and global joint transforms G (J,4,4) from the axis-angle corrections
+    rvec (J-1,3) (None: no refinement), the frame's local rotations dst_Rs (J,3,3) and translations dst_Ts (J,3).
+    Differentiable in rvec."""
+    if rvec is not None:
+        rvec = _f32c(rvec).reshape(-1, 3)
+    return _PoseFK.apply(rvec, _f32c(dst_Rs), _f32c(dst_Ts), tuple(parents))
+
+
+# ---------------------------------------------------------------------------
 # canonical field (hann-PE -> non-rigid MLP -> PE -> canonical MLP)
 # ---------------------------------------------------------------------------
 class FieldSpec:

@@ -271,6 +271,22 @@ int hn_tile_wgrad(const hn_wgrad_job* jobs_host, int n_jobs, int64_t n_samples, 
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a5 + a6  per-frame front end: RodriguesModule (core/utils/network_util.py:57-83), corrected rotations
+ *          Rs[1:] = dst_Rs[1:] @ dR (core/nets/human_nerf/network.py:612-616) and the forward-kinematics
+ *          chain of MotionBasisComputer (network_util.py:125-146), one launch forward, one backward.
+ * parent_host: n_joints ints on the HOST (parent of every joint, parent[i] < i, parent[0] ignored).
+ * rvec (J-1,3) axis-angle corrections of joints 1..J-1 (nullable in the forward: no refinement),
+ * dst_Rs (J,3,3), dst_Ts (J,3).  Outputs: Rs_out (J,3,3) corrected local rotations, G (J,4,4) global
+ * joint transforms.  The caller inverts G (the reference uses an LU inverse) and multiplies with the
+ * canonical transforms.  Backward: d_G (J,4,4) and d_Rs_out (J,3,3, nullable) -> d_rvec (J-1,3).
+ */
+int hn_pose_fk_fwd(int n_joints, const int32_t* parent_host, const float* rvec, const float* dst_Rs,
+                   const float* dst_Ts, float* Rs_out, float* G, void* stream);
+int hn_pose_fk_bwd(int n_joints, const int32_t* parent_host, const float* rvec, const float* dst_Rs,
+                   const float* Rs_corr, const float* dst_Ts, const float* G, const float* d_G,
+                   const float* d_Rs_out, float* d_rvec, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a17  core/train/optimizers/human_nerf/optimizer.py:12-43 (Adam, one group per tensor) and
  *      core/train/lr_updaters/exp_decay.py:7-16 (per-step learning-rate decay)
  * Fused multi-tensor Adam: one launch for all tensors.  hn_adam_plan writes a plan (tensor table +

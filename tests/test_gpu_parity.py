@@ -634,3 +634,49 @@ def test_full_size_properties(ops, sd, frame):
         rgb16, acc16, depth16, *_ = ops.composite(raw16.view(R, S, 4), m, z, d, xyz16.view(R, S, 3), bg)
         report('full.bf16 rgb vs fp32', rgb16, rgb, 2e-2)
         report('full.bf16 alpha vs fp32', acc16, acc, 2e-2)
+
+
+def test_pose_fk_kernel_against_torch_modules(ops):
+    """a5 + a6: hn_pose_fk_fwd / bwd (Rodrigues + corrected rotations + forward kinematics in one launch)
+    against the torch restatement of the reference modules (nn_util.RodriguesModule / MotionBasisComputer,
+    themselves pinned to the reference by the golden tests).  Forward: 2e-6 abs; gradient of the axis-angle
+    corrections: 1e-4 relative."""
+    from humannerf_b200.nn_util import SMPL_PARENT, MotionBasisComputer, RodriguesModule
+    fr = syn.make_frame(3)
+    dst_Rs, dst_Ts = T(fr['dst_Rs'], DEV), T(fr['dst_Ts'], DEV)
+    cnl = T(fr['cnl_gtfms'], DEV)
+    g = torch.Generator().manual_seed(5)
+    for scale in (1e-5, 0.05):                         # the refiner's initial output scale, and a trained one
+        rvec0 = (torch.randn(23, 3, generator=g) * scale).to(DEV)
+        w_G = torch.randn(24, 4, 4, generator=g).to(DEV)
+        w_G[:, 3, :] = 0.0
+        # torch modules
+        rv = rvec0.clone().requires_grad_()
+        dR = RodriguesModule()(rv).view(23, 3, 3)
+        Rs = torch.cat([dst_Rs[0:1], torch.matmul(dst_Rs[1:], dR)], dim=0)
+        local = torch.zeros(24, 4, 4, device=DEV)
+        local[:, :3, :3], local[:, :3, 3], local[:, 3, 3] = Rs, dst_Ts, 1.0
+        glob = [local[0]]
+        for i in range(1, 24):
+            glob.append(torch.matmul(glob[SMPL_PARENT[i]], local[i]))
+        G_ref = torch.stack(glob, 0)
+        (G_ref * w_G).sum().backward()
+        # kernel
+        rk = rvec0.clone().requires_grad_()
+        Rs_k, G_k = ops.pose_fk(rk, dst_Rs, dst_Ts, SMPL_PARENT)
+        (G_k * w_G).sum().backward()
+        torch.cuda.synchronize()
+        report(f'pose_fk.Rs[scale={scale:g}]', Rs_k, Rs.detach(), 2e-6)
+        report(f'pose_fk.G[scale={scale:g}]', G_k, G_ref.detach(), 2e-6)
+        rel = float((rk.grad - rv.grad).norm() / rv.grad.norm())
+        print(f'[parity] pose_fk.d_rvec[scale={scale:g}]: rel L2 {rel:.3e}')
+        assert rel < 1e-4
+        # and through the whole motion-basis computation
+        sR, sT = MotionBasisComputer(24)(Rs.detach()[None], dst_Ts[None], cnl[None])
+        inv = torch.linalg.inv_ex(G_k.detach()).inverse
+        f = torch.matmul(cnl, inv)
+        report(f'pose_fk.scale_Rs[scale={scale:g}]', f[:, :3, :3], sR[0], 5e-6)
+        report(f'pose_fk.Ts[scale={scale:g}]', f[:, :3, 3], sT[0], 5e-6)
+    # no refinement: rvec = None
+    _, G0 = ops.pose_fk(None, dst_Rs, dst_Ts, SMPL_PARENT)
+    assert torch.isfinite(G0).all()
