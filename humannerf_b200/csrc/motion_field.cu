@@ -189,18 +189,21 @@ motion_field_bwd_kernel(int64_t n_pts, int S, int J, int V, const float* __restr
   for (int k = threadIdx.x; k < J * 12; k += blockDim.x) s_acc[k] = 0.0f;
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n_pts;
   const int lane = threadIdx.x & 31;
   float bm[3] = {__ldg(bbox_min), __ldg(bbox_min + 1), __ldg(bbox_min + 2)};
   float bs[3] = {__ldg(bbox_scale), __ldg(bbox_scale + 1), __ldg(bbox_scale + 2)};
   float p[3] = {0.f, 0.f, 0.f};
   float gx[3] = {0.f, 0.f, 0.f};
   float gm = 0.0f;
+  bool live = i < n_pts;
   if (live) {
-    load_point(i, S, pts, rays_o, rays_d, z, p);
     if (d_x_skel) { gx[0] = d_x_skel[i * 3 + 0]; gx[1] = d_x_skel[i * 3 + 1]; gx[2] = d_x_skel[i * 3 + 2]; }
     if (d_mask) gm = d_mask[i];
+    // a sample without upstream gradient (e.g. one that empty-space skipping kept out of the MLPs: sigma = 0
+    // gives d mask = 0 exactly) contributes nothing: skip its 24 lookups
+    if (!d_weights && gx[0] == 0.0f && gx[1] == 0.0f && gx[2] == 0.0f && gm == 0.0f) live = false;
   }
+  if (live) load_point(i, S, pts, rays_o, rays_d, z, p);
   const int64_t vstride = (int64_t)V * V * V;
   // pass 1: W and N - skipped when the caller hands back the forward outputs (x = N / max(W, 1e-4), W)
   float nx = 0.f, ny = 0.f, nz = 0.f, wsum = 0.f;
