@@ -380,8 +380,10 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
       } else if (l == skip) {
         add_job(dz, f_dz, mrows, bufs.h[m][l - 1], width, 0, width, width, gW[l], in_dim, pe_first ? pe : 0, -1, nullptr);
         add_job(dz, f_dz, mrows, bufs.pe[m], pe_pad, 0, pe_pad, pe, gW[l], in_dim, pe_first ? 0 : width, pe_pad - 1, gB[l]);
+      } else if (gW[l]) {
+        // weights and bias in one job: the bias gradient is the column sum of the dZ stages (bias_col = -2)
+        add_job(dz, f_dz, mrows, bufs.h[m][l - 1], width, 0, width, width, gW[l], in_dim, 0, gB[l] ? -2 : -1, gB[l]);
       } else {
-        add_job(dz, f_dz, mrows, bufs.h[m][l - 1], width, 0, width, width, gW[l], in_dim, 0, -1, nullptr);
         add_job(dz, f_dz, mrows, bufs.pe[m], pe_pad, pe_pad - 16, 16, 0, nullptr, 16, 0, 15, gB[l]);
       }
     }

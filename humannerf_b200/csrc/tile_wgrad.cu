@@ -64,7 +64,7 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(s_full + s * 8, 1);
-      mbar_init(s_empty + s * 8, 1);
+      mbar_init(s_empty + s * 8, 1 + 4);         // the MMA commit + one arrive per epilogue warp (bias column sums)
     }
     mbar_init(s_acc, 1);
     mbar_init(s_drained, 128);
@@ -162,11 +162,53 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t acc_phase = 0;
+    uint32_t e_stage = 0, e_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const WgradJob job = jobs[slab_major ? item % n_jobs : item / n_slabs];
       const int m_tiles = (job.m + 127) / 128;
       const int e_si = slab_major ? item / n_jobs : item % n_slabs;
       const bool has_tiles = e_si * tiles_per_slab < n_tiles;      // an empty slab left the accumulators undefined
+      // While the MMA warp works through the stages, these four otherwise idle warps read the dZ operand of
+      // every stage from shared memory and keep its column sums = the bias gradient (bias_col == -2), so no
+      // second job has to stream dZ from HBM again just for db.  Thread (warp w, lane l) owns the 8 features
+      // of 16-byte chunk l and the 16 samples of block w of the 64-sample stage.
+      {
+        const int t0 = e_si * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        const bool direct = job.bias_col == -2 && job.db != nullptr;
+        const int ew = warp - 2;
+        const bool own = direct && lane * 8 < job.m;
+        const uint32_t a_blk = (uint32_t)job.f_dz * 32u;
+        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = t0; t < t1; ++t) {
+          for (int q = 0; q < 128 / kWgStageSamples; ++q) {
+            {
+              // always wait for the stage, also when this job needs no sums: it keeps these warps in step with
+              // the ring (an early second arrive on the same `empty` phase would corrupt the barrier)
+              mbar_wait(s_full + e_stage * 8, e_phase, 5);
+              if (own) {
+                const uint32_t src = s_base + e_stage * kWgStageBytes + (uint32_t)ew * a_blk + (uint32_t)lane * 256u;
+#pragma unroll 4
+                for (int r = 0; r < 16; ++r) {
+                  uint32_t w0, w1, w2, w3;
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(src + r * 16u));
+                  bsum[0] += __uint_as_float(w0 << 16); bsum[1] += __uint_as_float(w0 & 0xFFFF0000u);
+                  bsum[2] += __uint_as_float(w1 << 16); bsum[3] += __uint_as_float(w1 & 0xFFFF0000u);
+                  bsum[4] += __uint_as_float(w2 << 16); bsum[5] += __uint_as_float(w2 & 0xFFFF0000u);
+                  bsum[6] += __uint_as_float(w3 << 16); bsum[7] += __uint_as_float(w3 & 0xFFFF0000u);
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + e_stage * 8);
+            if (++e_stage == kWgStages) { e_stage = 0; e_phase ^= 1; }
+          }
+        }
+        if (own && has_tiles) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (lane * 8 + i < job.m) atomicAdd(job.db + lane * 8 + i, bsum[i]);
+        }
+      }
       mbar_wait(s_acc, acc_phase, 4);
       acc_phase ^= 1;
       tc_fence_after();
@@ -183,7 +225,7 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
               const int c = c0 + j;
               const float val = __uint_as_float(v[j]);
               if (c < job.n_valid) atomicAdd(job.dw + (int64_t)r * job.dw_ld + job.dw_col0 + c, val);
-              else if (c == job.bias_col && job.db) atomicAdd(job.db + r, val);
+              else if (c == job.bias_col && job.bias_col >= 0 && job.db) atomicAdd(job.db + r, val);
             }
           }
         }

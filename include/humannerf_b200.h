@@ -256,7 +256,8 @@ typedef struct hn_wgrad_job {
   int32_t n;           /* width of the X window = MMA N (multiple of 16, <= 256) */
   int32_t n_valid;     /* columns of the window written to dW */
   int32_t dw_ld, dw_col0;
-  int32_t bias_col;    /* window column routed to db, or -1 */
+  int32_t bias_col;    /* >= 0: window column routed to db (the constant-1 column of an encoding block);
+                          -1: no db; -2: db = column sums of dZ, accumulated from the operand stages in shared memory */
   int32_t reserved;
 } hn_wgrad_job;
 

@@ -52,6 +52,8 @@ def test_tile_wgrad_against_matmul(ops):
     db2 = torch.zeros(256, device=DEV)
     dw_out = torch.zeros(3, 256, device=DEV)
     dw_half = torch.zeros(128, 128, device=DEV)
+    dw_direct, db_direct = torch.zeros(256, 256, device=DEV), torch.zeros(256, device=DEV)
+    dw_out2, db_out2 = torch.zeros(3, 256, device=DEV), torch.zeros(3, device=DEV)
     jobs = [
         dict(dz=dz_img, x=x_img, dw=dw_full, f_dz=256, f_x=256, m=256, x_f0=0, n=256, n_valid=256, dw_ld=319, dw_col0=63),
         dict(dz=dz_img, x=pe_img, dw=dw_full, db=db_full, f_dz=256, f_x=64, m=256, x_f0=0, n=64, n_valid=63, dw_ld=319,
@@ -62,6 +64,11 @@ def test_tile_wgrad_against_matmul(ops):
         dict(dz=dz3_img, x=x_img, dw=dw_out, f_dz=16, f_x=256, m=3, x_f0=0, n=256, n_valid=256, dw_ld=256, dw_col0=0),
         # one M tile, window in the middle of X
         dict(dz=dz_img, x=x_img, dw=dw_half, f_dz=256, f_x=256, m=128, x_f0=64, n=128, n_valid=128, dw_ld=128, dw_col0=0),
+        # weights + bias in one job: db = column sums of the dZ stages (bias_col = -2)
+        dict(dz=dz_img, x=x_img, dw=dw_direct, db=db_direct, f_dz=256, f_x=256, m=256, x_f0=0, n=256, n_valid=256, dw_ld=256,
+             dw_col0=0, bias_col=-2),
+        dict(dz=dz3_img, x=x_img, dw=dw_out2, db=db_out2, f_dz=16, f_x=256, m=3, x_f0=0, n=256, n_valid=256, dw_ld=256,
+             dw_col0=0, bias_col=-2),
     ]
     ops.tile_wgrad(jobs, P)
     torch.cuda.synchronize()
@@ -77,6 +84,10 @@ def test_tile_wgrad_against_matmul(ops):
     assert float(dw_bias_only.abs().max()) == 0.0
     check('dW out (m=3)', dw_out, dz3b.t() @ xb)
     check('dW window', dw_half, dzb[:, :128].t() @ xb[:, 64:192])
+    check('dW (direct-bias job)', dw_direct, dzb.t() @ xb)
+    check('db (column sums of the dZ stages)', db_direct, dzb.sum(0))
+    check('dW out (direct-bias job, m=3)', dw_out2, dz3b.t() @ xb)
+    check('db out (m=3)', db_out2, dz3b.sum(0))
     # accumulation: running the same jobs again doubles the result
     ops.tile_wgrad(jobs[:1], P)
     check('accumulate', dw_full[:, 63:], 2 * (dzb.t() @ xb))
