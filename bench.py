@@ -7,11 +7,17 @@
 Workload (BASELINE.json configs[1]/[2]): one training step = 6 patches of 32x32 rays of a synthetic
 512x512 frame (<= 6144 rays x 128 samples), forward + loss (0.2 MSE + 1.0 LPIPS-VGG16 with seeded
 random VGG weights, see humannerf_b200/training.py) + backward + Adam, ZJU-387 adventure.yaml
-network shapes, fixture ("dense") weights, synthetic 24-joint pose.  With N GPUs every rank renders
-its own 6 patches of the same frame (weak scaling; per-GPU work fixed) and the gradients are
-exchanged with one bucketed all-reduce at the replicated-input boundary (parallel.CutBReducer).
-The JSON line also carries the forward-render leg (512x512 frame, bf16 tcgen05 path) and the
-per-kernel rooflines measured with CUDA events inside the timed region.
+network shapes, fixture ("dense") weights, synthetic 24-joint pose; MLPs on the bf16 tcgen05 kernels
+(--precision fp32 selects the SIMT parity path).  The step is one CUDA-graph replay
+(training.GraphedTrainStep; --eager runs it op by op).  With N GPUs every rank renders its own 6 patches
+of the same frame (weak scaling; per-GPU work fixed) and the gradients are exchanged with one bucketed
+all-reduce at the replicated-input boundary (parallel.CutBReducer), captured inside the graph.
+
+`value` = rays/s of the dense step with inputs resident in HBM; `e2e` = the same from pinned host batches
+incl. the loss read-back.  The JSON line also carries: the per-kernel roofline of the MLP kernel group
+(per-op CUDA events of an eager re-run of the same steps, DRAM traffic from the committed ncu capture), the
+step with opt-in empty-space skipping, the forward-render leg (512x512 frame, rays sharded over the ranks +
+gather; dense and with skipping) and the CPU baseline (oracle port on all host cores, bounded sample).
 """
 import argparse
 import json
