@@ -196,7 +196,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--ref-patch', type=int, default=12, help='patch size of the bounded CPU sample')
+    ap.add_argument('--ref-patch', type=int, default=16, help='patch size of the bounded CPU sample (>= 16: the LPIPS VGG16 trunk pools four times)')
     ap.add_argument('--warmup-ref', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true')

@@ -157,3 +157,20 @@ def test_hann_window_weights():
     from humannerf_b200.embedders.fourier import get_embedder as ge
     fn, dim = ge(10, 0)
     assert dim == 63 and torch.allclose(fn(x), orc.fourier_pe(x, 10))
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours: the oracle port of the reference's
+    train step on all host cores) prints one JSON line with the contract's keys.  One bounded step."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup-ref', '0'], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
+    d = json.loads(line)
+    assert d['impl'] == 'reference' and d['metric'] == 'train_step_rays_per_sec' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
