@@ -25,58 +25,9 @@
 #include <cstdlib>
 
 #include "mlp_tc_plan.cuh"
+#include "mlp_tc_enc.cuh"
 
 namespace hn {
-
-// ------------------------------------------------------------------------------------------
-// positional encodings written straight into the A operand block (bf16, 8 columns per store);
-// `half` selects which of the two threads of a row stores a given 16-byte chunk
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store8(uint32_t region, int row, int chunk, const float* v, uint8_t* img_row) {
-  const uint32_t addr = region + (uint32_t)chunk * kLboA + (uint32_t)row * 16u;
-  const uint32_t a = pack_bf16(v[0], v[1]), b = pack_bf16(v[2], v[3]), c = pack_bf16(v[4], v[5]), d = pack_bf16(v[6], v[7]);
-  st_shared_v4(addr, a, b, c, d);
-  if (img_row) *reinterpret_cast<uint4*>(img_row + (size_t)chunk * 256) = make_uint4(a, b, c, d);
-}
-
-// byte offset of (row r of tile t, feature 0) inside a T16 image with F features per sample
-__device__ __forceinline__ size_t image_row_offset(int64_t tile, int r, int F) {
-  return (size_t)tile * 128 * F * 2 + (size_t)(r >> 4) * 16 * F * 2 + (size_t)(r & 15) * 16;
-}
-
-// columns: [optional x (3)], then per frequency sin(x,y,z), cos(x,y,z); zero padding up to `pad`
-// columns with a constant 1 in the last one (the bias column).
-template <bool kIncludeInput>
-__device__ __forceinline__ void write_encoding(uint32_t region, int row, int half, const float x[3], int n_freqs,
-                                               const float* __restrict__ weights, int pad, uint8_t* img_row) {
-  float pe[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) pe[i] = 0.0f;
-  int base = 0;
-  if (kIncludeInput) { pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2]; base = 3; }
-  float freq = 1.0f;
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    if (k < n_freqs) {
-      const float w = weights ? weights[k] : 1.0f;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        float s, c;
-        __sincosf(x[a] * freq, &s, &c);
-        pe[base + k * 6 + a] = w * s;
-        pe[base + k * 6 + 3 + a] = w * c;
-      }
-    }
-    freq *= 2.0f;
-  }
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    if (ch * 8 < pad && (ch & 1) == half) {
-      if (ch * 8 + 8 == pad) pe[ch * 8 + 7] = 1.0f;
-      store8(region, row, ch, pe + ch * 8, img_row);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // Cycle accounting of block 0 (measurement aid, active only with HN_TC_ABLATE & 8):
@@ -150,7 +101,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t
     }
     for (int t = 0; t < kTiles; ++t) {
       mbar_init(s_acc_full + t * 8, 1);
-      mbar_init(s_a_ready + t * 8, (kEpiWarps / kTiles) * 32);
+      mbar_init(s_a_ready + t * 8, kEpiWarps / kTiles);   // one arrive per epilogue warp of the tile
     }
     fence_barrier_init();
   }
@@ -299,7 +250,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t
         write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad,
                               store ? bufs.pe[0] + image_row_offset(tile_idx, row, nr_pad) : nullptr);
         fence_proxy_async();
-        mbar_arrive(bar_ready);
+        warp_arrive(bar_ready, lane);
         HN_EPROF_ADD(18, e_pe);
       }
 
@@ -311,7 +262,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t
           write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad,
                                store ? bufs.pe[1] + image_row_offset(tile_idx, row, cn_pad) : nullptr);
           fence_proxy_async();
-          mbar_arrive(bar_ready);
+          warp_arrive(bar_ready, lane);
           HN_EPROF_ADD(18, e_pe);
         }
         HN_EPROF_T(e_w);
@@ -324,7 +275,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t
           // measurement aid (HN_TC_ABLATE=1): barrier handshake only, accumulator never read
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(bar_ready);
+          warp_arrive(bar_ready, lane);
         } else if (!is_out) {
           const int n_full = (int)hdr->layer_n[layer];
           const int n_half = n_full >> 1;                          // columns owned by this thread
@@ -368,7 +319,7 @@ field_tc_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t
           }
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(bar_ready);
+          warp_arrive(bar_ready, lane);
           HN_EPROF_ADD(19, e_h);
         } else {
           uint32_t v[16];
@@ -440,7 +391,12 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
     }
     uint4 o;
     o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-    *reinterpret_cast<uint4*>(image + job.w_off + (size_t)kg * job.n * 16 + (size_t)n * 16) = o;
+    size_t dst = (size_t)kg * job.n * 16 + (size_t)n * 16;
+    if (job.split) {
+      const int nh = job.n >> 1, r = n >= nh ? 1 : 0;
+      dst = (size_t)r * (job.kc / 8) * nh * 16 + (size_t)kg * nh * 16 + (size_t)(n - r * nh) * 16;
+    }
+    *reinterpret_cast<uint4*>(image + job.w_off + dst) = o;
   }
 }
 
@@ -448,6 +404,11 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
 int launch_field_tcc(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const float* x_skel,
                      const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
                      const TrainBufs* bufs, int sms, cudaStream_t st);
+
+// mlp_tc_2sm.cu
+int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
+                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                     const TrainBufs* bufs, int sms, int ablate, cudaStream_t st);
 
 int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples) {
   TcPlan plan;
@@ -545,7 +506,18 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
   // (results are garbage) to expose how much of the kernel time the epilogue accounts for
   const char* abl = getenv("HN_TC_ABLATE");
   const int ablate = abl ? atoi(abl) : 0;
-  // default: the tile-pair kernel below; HN_TC_KERNEL=cluster selects the experimental cluster kernel
+  // default: the cta_group::2 kernel of mlp_tc_2sm.cu (CTA pairs share every weight chunk)
+  if (use_2sm_kernel()) {
+    if (sms < 2) return fail_arg("hn_field_fwd: the tcgen05 forward kernel needs a device with thread-block clusters");
+    TrainBufs bufs;
+    if (save_for_backward) {
+      const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
+      if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
+    }
+    return launch_field_tc2(plan, pk, n_samples, n_samples_dev, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets,
+                            save_for_backward ? &bufs : nullptr, sms, ablate, as_stream(stream));
+  }
+  // HN_TC_KERNEL=pair: the tile-pair kernel below; HN_TC_KERNEL=cluster: the experimental cluster kernel
   // (mlp_tc_cl.cu: correct, but slower - its single tile per CTA exposes the ~2000-clk accumulator ->
   // epilogue -> operand hand-over latency of every layer)
   if (use_cluster_kernel() && sms >= 2 && !n_samples_dev) {

@@ -1,0 +1,475 @@
+// Canonical field, tensor-core path (HN_PRECISION_BF16), default forward kernel: CTA PAIRS with
+// tcgen05.mma.cta_group::2.
+//
+// Same math, operand layouts, epilogue and weight stream as the tile-pair kernel of mlp_tc.cu (read its header
+// first); what changes is who shares the weights.  There the two tiles of ONE CTA share every weight chunk, the
+// 64 KB ring holds half a layer, and a ring slot only turns over after BOTH tiles have consumed it and the refill
+// (~1000 clk of L2 latency) has landed - so the tiles run in lock-step, both accumulators complete together and
+// the tensor pipe idles through both epilogues and the hand-over latency (measured: 39.8 % pipe active, a one-time
+// head start of one tile changes nothing).  Here
+//
+//   * a cluster of two CTAs (two SMs) works on FOUR 128-sample tiles: tile set X = {tile 0 of CTA 0, tile 0 of
+//     CTA 1}, tile set Y = {tile 1 of CTA 0, tile 1 of CTA 1}.  One M = 256 MMA covers a tile set: each SM's tensor
+//     core multiplies ITS 128 rows of A (its own shared memory) with the whole B operand, of which each SM holds
+//     HALF (rows [0, N/2) in CTA 0, [N/2, N) in CTA 1, same offsets) - the pair exchanges the halves in hardware;
+//   * each CTA therefore streams only its half of every chunk (hn_field_pack_bf16 stores forward chunks as two
+//     half images): the same 64 KB of ring per SM now hold 8 stages = 256 K-rows = a WHOLE layer, the L2 -> SM
+//     traffic per sample halves, and tile set X can run a layer ahead of Y: X's epilogue and hand-over overlap
+//     Y's MMAs and vice versa;
+//   * CTA 0 (the leader) issues all MMAs (warp 1: set X into TMEM columns [0,256), warp 18: set Y into [256,512)
+//     of BOTH CTAs' tensor memory) and commits with .multicast::cluster, so `empty` (ring slot free) and
+//     `acc_full` (accumulator complete) fire in both CTAs;
+//   * what the issuers wait for lives in the leader: `a_ready[t]` collects one mbarrier.arrive.release.cluster per
+//     epilogue warp of BOTH CTAs (remote for the peer), `full[s]` collects the leader's own bulk copy
+//     (complete_tx) and a forwarded arrive for the peer's half: a 1-D cp.async.bulk can only complete on a barrier
+//     of the CTA it writes to (scripts/micro/umma_2sm_proto.cu: naming the leader's barrier hangs), so the peer's
+//     copy completes on its own `floc[s]` and a relay thread (the peer's idle issuer warp) forwards it.
+//
+// Protocol pieces were checked in isolation by scripts/micro/umma_2sm.cu and umma_2sm_proto.cu.
+// Reference semantics: embedders/hannw_fourier.py:38-49, embedders/fourier.py:9-38,
+// non_rigid_motion_mlps/mlp_offset.py:74-114, canonical_mlps/mlp_rgb_sigma.py:132-206.
+#include <cstdlib>
+
+#include "mlp_tc_plan.cuh"
+#include "mlp_tc_enc.cuh"
+
+namespace hn {
+
+namespace s2 {
+constexpr int kStages2 = 8;                                            // barrier slots (the ring has 4 or 8 stages)
+constexpr uint32_t kRingBytes2 = 65536;                                // per CTA: 4 x 16 KB or 8 x 8 KB half chunks
+constexpr uint32_t kBarOff2 = kRingOff + kRingBytes2;
+// barriers: full[8] floc[8] empty[8] acc_full[2] a_ready[2] + tmem slot
+constexpr uint32_t kBarBytes2 = (3 * kStages2 + 2 * kTiles) * 8 + 8;
+constexpr uint32_t kTableOff2 = kBarOff2 + 256;
+constexpr uint32_t kSmemTotal2 = kTableOff2 + kMaxChunks * 16;
+constexpr int kSetRows = 2 * kTileM;                                   // rows of one tile set (MMA M)
+static_assert(kBarBytes2 <= 256, "barrier block");
+static_assert(kSmemTotal2 <= 232448, "shared memory budget");
+}  // namespace s2
+
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (256 rows, 128 per CTA) * B^T (N rows, N/2 per CTA); issued by one thread of the leader
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of the pair retire
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 256 (pair), N
+__device__ __forceinline__ uint32_t make_idesc2(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// Timeline of one pass of cluster 0 (measurement aid, HN_TC_ABLATE & 8): clock64 of the leader SM at
+//   [role 0/1 = issuer X/Y][layer][0] operand ready (after the a_ready wait), [1] last MMA + commits issued;
+//   [role 2/3 = epilogue thread of tile set X/Y (warp 2 / 10, lane 0)][layer][0] accumulator complete observed,
+//   [1] operand handed over (arrive done)
+__device__ long long g_tc2_trace[4][32][4];   // issuers: [2] cycles waiting for weights, [3] cycles issuing MMAs + commits
+constexpr int kTraceQuad = 6;      // which pass of cluster 0 is recorded
+
+// What the MMA issuers need per chunk, as a KERNEL PARAMETER (constant bank, warp-uniform loads): x = byte offset of
+// the chunk's first A core matrix inside its operand block, y = N | K steps << 16 | flags << 24 (TcChunk's last word).
+// The issuer warps run convergently with every operand in uniform registers and elect one lane per MMA: a lone
+// diverged thread pays a ~15-instruction ELECT / R2UR.BROADCAST waterfall per tcgen05 instruction plus ~100 dependent
+// vector instructions per chunk (measured: 580 clk per chunk + 61 clk per MMA, against 256 clk of tensor pipe time).
+struct IssueTab {
+  uint2 e[kMaxChunks];
+};
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred;
+}
+
+template <bool kStore>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
+                 const float* __restrict__ x_skel, const float* __restrict__ hann_w, int ignore_non_rigid,
+                 float* __restrict__ raw, float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs,
+                 int ablate, int n_stages) {
+  using namespace s2;
+  const uint32_t stage_bytes = kRingBytes2 / (uint32_t)n_stages;
+  // n_dev (nullable): the number of samples actually present, read from device memory (empty-space skipping
+  // compacts the samples without telling the host); n_cap bounds it and sizes the buffers
+  const int64_t n_samples = n_dev ? min(max(__ldg(n_dev), (int64_t)0), n_cap) : n_cap;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
+  const uint8_t* image = packed + hdr->image_off;
+
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_act_pe = s_base + kActHBytes;
+  const uint32_t s_ring = s_base + kRingOff;
+  const uint32_t s_full = s_base + kBarOff2;                 // leader: own bulk copy + forwarded arrive of the peer
+  const uint32_t s_floc = s_full + kStages2 * 8;             // peer: its own bulk copy
+  const uint32_t s_empty = s_floc + kStages2 * 8;            // both: multicast commits of the two issuers
+  const uint32_t s_acc_full = s_empty + kStages2 * 8;        // both: multicast commit at the end of a layer
+  const uint32_t s_a_ready = s_acc_full + kTiles * 8;        // leader: epilogue warps of both CTAs
+  const uint32_t s_tmem_slot = s_a_ready + kTiles * 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff2 + (3 * kStages2 + 2 * kTiles) * 8);
+  const TcChunk* table = reinterpret_cast<const TcChunk*>(smem + kTableOff2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t n_quads = (n_samples + 2 * kSetRows - 1) / (2 * kSetRows);       // 4 tiles = 512 samples per pass
+  const int64_t n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int nr_layers = (int)hdr->nr_layers;
+  const int n_layers = nr_layers + (int)hdr->cn_layers;
+  const int first_layer = ignore_non_rigid ? nr_layers : 0;
+  const uint32_t n_chunks = hdr->n_chunks;
+
+  // chunk table -> shared memory (every role reads it once per chunk)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(packed + hdr->table_off);
+    uint4* dst = reinterpret_cast<uint4*>(smem + kTableOff2);
+    for (uint32_t i = threadIdx.x; i < n_chunks; i += blockDim.x) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(s_full + s * 8, 2);
+      mbar_init(s_floc + s * 8, 1);
+      mbar_init(s_empty + s * 8, kTiles);                    // one commit per MMA issuer (tile set)
+    }
+    for (int t = 0; t < kTiles; ++t) {
+      mbar_init(s_acc_full + t * 8, 1);
+      mbar_init(s_a_ready + t * 8, 2 * (kEpiWarps / kTiles));   // one arrive per epilogue warp of the tile set
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {            // the same warp of both CTAs allocates collectively
+    tmem_alloc2(s_tmem_slot, kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();         // barrier inits visible before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // chunks of the skipped non-rigid MLP are skipped too
+  uint32_t first_chunk = 0;
+  if (ignore_non_rigid) {
+    int seen = 0;
+    for (uint32_t c = 0; c < n_chunks && seen < nr_layers; ++c) {
+      if (table[c].flags & 2) ++seen;
+      first_chunk = c + 1;
+    }
+  }
+
+  if (warp == 0) {
+    // ===================== TMA producer: this CTA's half of every chunk =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t s_done = leader ? s_full : s_floc;
+      for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        for (uint32_t c = first_chunk; c < n_chunks; ++c) {
+          const TcChunk ch = table[c];
+          const uint32_t half = ch.bytes >> 1;
+          mbar_wait(s_empty + stage * 8, phase ^ 1, 1);
+          mbar_expect_tx(s_done + stage * 8, half);
+          tma_bulk_g2s(s_ring + stage * stage_bytes, image + ch.w_off + rank * half, half, s_done + stage * 8);
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
+    if (leader) {
+      // ===================== MMA issuers (leader): warp 1 drives tile set X, warp 18 tile set Y =====================
+      // the whole warp runs this loop convergently; one elected lane issues the tcgen05 instructions
+      const uint32_t t = (warp == kMmaWarp0) ? 0u : 1u;
+      const uint32_t d_tmem = tmem_base + t * 256u;
+      const uint32_t bar_ready = s_a_ready + t * 8, bar_acc = s_acc_full + t * 8;
+      // descriptor halves: hi = SBO (128 B >> 4) | version 1 (bit 46 -> bit 14 of hi); lo = addr >> 4 | LBO >> 4 << 16
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t h_lo = (((s_base + t * kActHTile) & 0x3FFFFu) >> 4) | ((kLboA >> 4) << 16);
+      const uint32_t pe_lo = (((s_act_pe + t * kActPeTile) & 0x3FFFFu) >> 4) | ((kLboA >> 4) << 16);
+      const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
+      const uint32_t a_inc = (2u * kLboA) >> 4;                                      // one K step = two core matrices
+      uint32_t stage = 0, phase = 0, a_phase = 0, full_ok = 0;
+      int pass = 0, tr_layer = 0;
+      long long tr_wait = 0, tr_issue = 0;
+      for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters, ++pass) {
+        const bool trace = (ablate & 8) && cluster_id == 0 && pass == kTraceQuad && lane == 0;
+        tr_layer = 0;
+        for (uint32_t c = first_chunk; c < n_chunks; ++c) {
+          const uint2 e = itab.e[c];
+          const uint32_t n = e.y & 0xFFFFu, ksteps = (e.y >> 16) & 0xFFu, flags = e.y >> 24;
+          if (flags & 1u) {
+            // the A operand of this layer is complete in both CTAs (and the previous accumulator drained)
+            mbar_wait(bar_ready, a_phase, 2);
+            a_phase ^= 1;
+            if (trace) g_tc2_trace[t][tr_layer][0] = clock64();
+          }
+          const long long tw0 = trace ? clock64() : 0;
+          if (!full_ok) mbar_wait(s_full + stage * 8, phase, 3);
+          tc_fence_after();
+          const long long tw1 = trace ? clock64() : 0;
+          // probe the NEXT chunk's weights now: the round trip overlaps the MMA issue below
+          {
+            const uint32_t ns = stage + 1 == (uint32_t)n_stages ? 0u : stage + 1;
+            full_ok = mbar_test_wait(s_full + ns * 8, ns == 0u ? phase ^ 1u : phase);
+          }
+          const uint32_t idesc = make_idesc2(n);
+          uint32_t a_lo = ((flags & 4u) ? pe_lo : h_lo) + (e.x >> 4);
+          uint32_t b_lo = (ring_lo + stage * (stage_bytes >> 4)) | ((n >> 1) << 16);   // LBO = (n/2)*16 bytes
+          if (elect_one()) {
+            uint32_t acc = (flags & 1u) ? 0u : 1u;
+            for (uint32_t k = 0; k < ksteps; ++k) {
+              umma2_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+              acc = 1u;
+              a_lo += a_inc;
+              b_lo += n;                                   // two core-matrix groups of n/2 rows x 16 B, >> 4
+            }
+            umma2_commit_mc(s_empty + stage * 8);          // the slot is free in both CTAs once both issuers' MMAs retire
+            if (flags & 2u) umma2_commit_mc(bar_acc);      // accumulator of the layer is complete (both CTAs)
+          }
+          __syncwarp();
+          if (trace) {
+            const long long tw2 = clock64();
+            tr_wait += tw1 - tw0;
+            tr_issue += tw2 - tw1;
+            if (flags & 2u) {
+              g_tc2_trace[t][tr_layer][1] = tw2;
+              g_tc2_trace[t][tr_layer][2] = tr_wait;
+              g_tc2_trace[t][tr_layer][3] = tr_issue;
+              tr_wait = tr_issue = 0;
+            }
+          }
+          if (flags & 2u) ++tr_layer;
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0 && warp == kMmaWarp0) {
+      // ===================== relay (peer): forwards "my half of the chunk has landed" to the leader =====================
+      const uint32_t full_remote = mapa_cluster(s_full, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        for (uint32_t c = first_chunk; c < n_chunks; ++c) {
+          mbar_wait(s_floc + stage * 8, phase, 5);
+          mbar_arrive_remote(full_remote + stage * 8);
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2 .. 17) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int tile = ew >> 3;                     // tile set: 0 = X, 1 = Y
+    const int half = (ew >> 2) & 1;               // which half of the layer's columns / PE chunks
+    const int row = quarter * 32 + lane;          // row inside the tile == TMEM lane
+    const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)tile * 256u;
+    const uint32_t a_h = s_base + (uint32_t)tile * kActHTile;
+    const uint32_t a_pe = s_act_pe + (uint32_t)tile * kActPeTile;
+    const uint32_t bar_ready = mapa_cluster(s_a_ready + (uint32_t)tile * 8, 0);      // in the leader
+    const uint32_t bar_acc = s_acc_full + (uint32_t)tile * 8;
+    uint32_t acc_phase = 0;
+    float hw[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) hw[k] = (k < (int)hdr->nr_freqs && hann_w) ? __ldg(hann_w + k) : 0.0f;
+    const int nr_freqs = (int)hdr->nr_freqs, cn_freqs = (int)hdr->cn_freqs;
+    const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
+
+    int pass = 0;
+    for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters, ++pass) {
+      const bool trace = (ablate & 8) && blockIdx.x == 0 && pass == kTraceQuad && lane == 0 && half == 0 && quarter == 2;
+      // tile set X = tiles 4q, 4q+1 (CTA 0, CTA 1); tile set Y = tiles 4q+2, 4q+3
+      const int64_t tile_idx = quad * 4 + tile * 2 + (int64_t)rank;
+      const int64_t sample = tile_idx * kTileM + row;
+      const bool valid = sample < n_samples;
+      const bool store = kStore && tile_idx < bufs.n_tiles;      // the training images hold ceil(P/128) tiles
+      float x[3] = {0.f, 0.f, 0.f};
+      if (valid) { x[0] = x_skel[sample * 3 + 0]; x[1] = x_skel[sample * 3 + 1]; x[2] = x_skel[sample * 3 + 2]; }
+      float q[3] = {x[0], x[1], x[2]};            // position fed to the canonical encoding
+
+      if (!ignore_non_rigid) {
+        write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad,
+                              store ? bufs.pe[0] + image_row_offset(tile_idx, row, nr_pad) : nullptr);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(bar_ready);
+      }
+
+      for (int layer = first_layer; layer < n_layers; ++layer) {
+        const bool is_nr = layer < nr_layers;
+        const bool is_out = (layer == nr_layers - 1) || (layer == n_layers - 1);
+        if (layer == nr_layers) {
+          write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad,
+                               store ? bufs.pe[1] + image_row_offset(tile_idx, row, cn_pad) : nullptr);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(bar_ready);
+        }
+        mbar_wait(bar_acc, acc_phase, 4);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (trace) g_tc2_trace[2 + tile][layer][0] = clock64();
+        if (!is_out && (ablate & 1)) {
+          // measurement aid (HN_TC_ABLATE=1): barrier handshake only, accumulator never read
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(bar_ready);
+        } else if (!is_out) {
+          const int n_full = (int)hdr->layer_n[layer];
+          const int n_half = n_full >> 1;                          // columns owned by this thread
+          const int c_begin = half * n_half;
+          uint8_t* h_img = nullptr;
+          if (store)
+            h_img = (is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers]) + image_row_offset(tile_idx, row, n_full);
+          uint32_t v[2][32];
+          tmem_ld32(t_acc + (uint32_t)c_begin, v[0]);
+#pragma unroll 1
+          for (int c0 = 0; c0 < n_half; c0 += 64) {
+            // two 32-column groups per iteration so that the register buffers are indexed statically
+            tmem_ld_wait();
+            if (c0 + 32 < n_half) tmem_ld32(t_acc + (uint32_t)(c_begin + c0 + 32), v[1]);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const uint32_t* u = v[0] + g8 * 8;
+              const int chunk = ((c_begin + c0) >> 3) + g8;
+              const uint4 pk = make_uint4(pack_relu_bf16(__uint_as_float(u[0]), __uint_as_float(u[1])),
+                                          pack_relu_bf16(__uint_as_float(u[2]), __uint_as_float(u[3])),
+                                          pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
+                                          pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
+              st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
+              if (store) *reinterpret_cast<uint4*>(h_img + (size_t)chunk * 256) = pk;
+            }
+            if (c0 + 32 < n_half) {
+              tmem_ld_wait();
+              if (c0 + 64 < n_half) tmem_ld32(t_acc + (uint32_t)(c_begin + c0 + 64), v[0]);
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                const uint32_t* u = v[1] + g8 * 8;
+                const int chunk = ((c_begin + c0 + 32) >> 3) + g8;
+                const uint4 pk = make_uint4(pack_relu_bf16(__uint_as_float(u[0]), __uint_as_float(u[1])),
+                                            pack_relu_bf16(__uint_as_float(u[2]), __uint_as_float(u[3])),
+                                            pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
+                                            pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
+                st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
+                if (store) *reinterpret_cast<uint4*>(h_img + (size_t)chunk * 256) = pk;
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(bar_ready);
+          if (trace) g_tc2_trace[2 + tile][layer][1] = clock64();
+        } else {
+          uint32_t v[16];
+          tmem_ld16(t_acc, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (is_nr) {
+            // offsets -> xyz = x_skel + offset (fp32); feeds the canonical encoding
+            const float o0 = __uint_as_float(v[0]), o1 = __uint_as_float(v[1]), o2 = __uint_as_float(v[2]);
+            q[0] = x[0] + o0; q[1] = x[1] + o1; q[2] = x[2] + o2;
+            if (valid && half == 0) {
+              off_out[sample * 3 + 0] = o0; off_out[sample * 3 + 1] = o1; off_out[sample * 3 + 2] = o2;
+            }
+          } else if (valid && half == 0) {
+            float4 r;
+            r.x = __uint_as_float(v[0]); r.y = __uint_as_float(v[1]);
+            r.z = __uint_as_float(v[2]); r.w = __uint_as_float(v[3]);
+            reinterpret_cast<float4*>(raw)[sample] = r;
+            xyz_out[sample * 3 + 0] = q[0]; xyz_out[sample * 3 + 1] = q[1]; xyz_out[sample * 3 + 2] = q[2];
+            if (ignore_non_rigid) {
+              off_out[sample * 3 + 0] = 0.f; off_out[sample * 3 + 1] = 0.f; off_out[sample * 3 + 2] = 0.f;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peer may still arrive on / commit into this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+// Launch: persistent, exactly as many clusters as can be co-resident (GPC boundaries may leave a few SMs without
+// a partner, so this can be below sms / 2).  Returns <0 / cudaError_t like every entry point.
+int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
+                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                     const TrainBufs* bufs, int sms, int ablate, cudaStream_t st) {
+  using namespace s2;
+  static int max_clusters_cached = 0;
+  if (max_clusters_cached == 0) {
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+                      "hn_field_fwd/2sm smem attr"));
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+                      "hn_field_fwd/2sm smem attr"));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * (sms / 2)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemTotal2;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_kernel<false>, &cfg), "hn_field_fwd/2sm occupancy"));
+    if (n <= 0) return fail_arg("hn_field_fwd: no 2-CTA cluster of the tcgen05 kernel fits on this device");
+    max_clusters_cached = n;
+    if (getenv("HN_DEBUG")) fprintf(stderr, "humannerf_b200: %d co-resident 2-CTA clusters (%d SMs)\n", n, sms);
+  }
+  IssueTab itab;
+  memset(&itab, 0, sizeof(itab));
+  for (size_t c = 0; c < plan.chunks.size(); ++c) {
+    const TcChunk& ch = plan.chunks[c];
+    itab.e[c] = make_uint2(ch.a_off, (uint32_t)ch.n | ((uint32_t)ch.ksteps << 16) | ((uint32_t)ch.flags << 24));
+  }
+  const int64_t n_quads = ceil_div<int64_t>(n_samples, 2 * kSetRows);
+  const unsigned grid = 2u * (unsigned)std::min<int64_t>(n_quads, (int64_t)max_clusters_cached);
+  if (bufs) {
+    field_tc2_kernel<true><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
+                                                               ignore_non_rigid, raw, xyz, offsets, *bufs, ablate, tc2_stages());
+  } else {
+    TrainBufs none;
+    memset(&none, 0, sizeof(none));
+    field_tc2_kernel<false><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
+                                                                ignore_non_rigid, raw, xyz, offsets, none, ablate, tc2_stages());
+  }
+  return launched("hn_field_fwd/tcgen05 2sm");
+}
+
+}  // namespace hn
+
+/* measurement aid: copies the timeline of one pass of cluster 0 (HN_TC_ABLATE & 8): 4 x 32 x 2 clock values */
+extern "C" int hn_debug_tc2_trace(long long* out_host) {
+  using namespace hn;
+  if (!out_host) return fail_arg("hn_debug_tc2_trace: null");
+  return check_cuda(cudaMemcpyFromSymbol(out_host, g_tc2_trace, sizeof(long long) * 4 * 32 * 4), "hn_debug_tc2_trace/read");
+}

@@ -73,7 +73,7 @@ field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int
     }
     for (int t = 0; t < kTiles; ++t) {
       mbar_init(s_acc_full + t * 8, 1);
-      mbar_init(s_a_ready + t * 8, (kEpiWarps / kTiles) * 32);
+      mbar_init(s_a_ready + t * 8, kEpiWarps / kTiles);   // one arrive per epilogue warp of the tile
     }
     fence_barrier_init();
   }
@@ -178,7 +178,7 @@ field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int
         if (have_img)
           *reinterpret_cast<uint4*>(bufs.dz[mlp][out_layer] + image_row_offset_b(tile_idx, row, 16) + (size_t)half * 256) = pk;
         fence_proxy_async();
-        mbar_arrive(bar_ready);
+        warp_arrive(bar_ready, lane);
       }
 
       for (int r = r_first; r < r_last; ++r) {
@@ -222,7 +222,7 @@ field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int
           }
           tc_fence_before();
           fence_proxy_async();
-          if (!last) mbar_arrive(bar_ready);
+          if (!last) warp_arrive(bar_ready, lane);
         } else {
           // gradient of the encoding block, contracted with the encoding's derivative:
           //   d_pos[a] += [raw x] g[a] + sum_k w_k 2^k (cos(2^k x_a) g_sin(k,a) - sin(2^k x_a) g_cos(k,a))
@@ -269,7 +269,7 @@ field_tc_bwd_kernel(const uint8_t* __restrict__ packed, int64_t n_cap, const int
             atomicAdd(d_pos + sample * ld_dpos + 2, az);
           }
           tc_fence_before();
-          if (!last) mbar_arrive(bar_ready);
+          if (!last) warp_arrive(bar_ready, lane);
         }
       }
     }

@@ -53,14 +53,6 @@ static_assert(kBarBytes <= 256, "barrier block");
 static_assert(kSmemTotalC <= 232448, "shared memory budget");
 }  // namespace cl
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // half of a weight chunk into the same ring slot of BOTH CTAs of the cluster; completes `bytes` on the
 // `full` barrier (same offset) of each destination CTA
 __device__ __forceinline__ void tma_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {

@@ -91,18 +91,40 @@ struct PackJob {            // one per chunk, consumed by pack_weights_kernel
   int32_t transpose;        // 0: B[n][k] = src[n][col0 + k];  1: B[n][k] = src[row0 + k][col0 + n]
   int32_t src_row0;
   uint32_t w_off;           // destination byte offset inside the image
+  int32_t split;            // 1: the chunk is stored as two half images (rows [0,n/2) then [n/2,n)), one per CTA of a
+                            // cta_group::2 pair: addr = r*(kc/8)*(n/2)*16 + (k/8)*(n/2)*16 + n'*16
 };
 
 static inline int round16(int v) { return (v + 15) & ~15; }
 
-// HN_TC_KERNEL=cluster selects the experimental cluster forward kernel (read once per process: the weight
-// image's chunk table depends on it)
-static inline bool use_cluster_kernel() {
-  static const bool v = [] {
+// Forward kernel selection, read once per process (the forward part of the weight image depends on it):
+//   default            mlp_tc_2sm.cu  - CTA pairs, tcgen05.mma.cta_group::2, each CTA holds half of every weight chunk
+//   HN_TC_KERNEL=pair  mlp_tc.cu      - one CTA per SM, cta_group::1, two tiles share a 4 x 16 KB weight ring
+//   HN_TC_KERNEL=cluster mlp_tc_cl.cu - experimental multicast kernel (one tile per CTA)
+static inline int tc_kernel_mode() {
+  static const int v = [] {
     const char* e = getenv("HN_TC_KERNEL");
-    return e != nullptr && e[0] == 'c';
+    if (e != nullptr && e[0] == 'c') return 2;
+    if (e != nullptr && e[0] == 'p') return 1;
+    return 0;
   }();
   return v;
+}
+static inline bool use_cluster_kernel() { return tc_kernel_mode() == 2; }
+static inline bool use_2sm_kernel() { return tc_kernel_mode() == 0; }
+// Ring geometry of the cta_group::2 kernel: 64 KB per CTA as 4 stages x 16 KB (default: chunks of up to 32 KB per
+// pair = 4 MMAs at N = 256, so the ~500 clk an issuer spends per chunk stay below the chunk's tensor-pipe time) or,
+// with HN_TC_2SM_STAGES=8, 8 stages x 8 KB (the chunk table of the tile-pair kernel).
+static inline int tc2_stages() {
+  static const int v = [] {
+    const char* e = getenv("HN_TC_2SM_STAGES");
+    return (e != nullptr && atoi(e) == 8) ? 8 : 4;
+  }();
+  return v;
+}
+// largest forward chunk (bytes, both halves) for the selected forward kernel
+static inline uint32_t fwd_chunk_bytes() {
+  return use_2sm_kernel() ? 2u * (65536u / (uint32_t)tc2_stages()) : kStageBytes;
 }
 
 struct TcPlan {
@@ -142,7 +164,8 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
   auto add_segment = [&](std::vector<TcChunk>& table, const float* W, int ldw, int col0, int valid_k, int k_pad,
                          int valid_n, int n, bool in_pe, int a_col0, bool first, bool last, int bias_col,
                          const float* bias, const float* fold_w, int fold_ld, int fold_k, bool transpose, int row0) {
-    int kc_max = (int)(kStageBytes / (uint32_t)(n * 2)) / 16 * 16;
+    const uint32_t chunk_cap = (&table == &plan.chunks) ? fwd_chunk_bytes() : kStageBytes;
+    int kc_max = (int)(chunk_cap / (uint32_t)(n * 2)) / 16 * 16;
     if (kc_max > 240) kc_max = 240;                       // ksteps is a uint8
     // for the experimental cluster kernel (HN_TC_KERNEL=cluster, mlp_tc_cl.cu) forward chunks never span
     // more than one 32-column block of the A operand: it hands the operand over block by block
@@ -162,6 +185,7 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
       j.src = W; j.src_ld = ldw; j.valid_n = valid_n; j.n = n; j.kc = kc; j.w_off = w_off;
       j.valid_k = std::max(0, valid_k - k0);
       j.transpose = transpose ? 1 : 0;
+      j.split = (&table == &plan.chunks && use_2sm_kernel()) ? 1 : 0;
       if (transpose) { j.src_col0 = col0; j.src_row0 = row0 + k0; }
       else { j.src_col0 = col0 + k0; j.src_row0 = 0; }
       j.bias_row = -1;
@@ -255,7 +279,8 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
     return fail_arg("hn_field(bf16): too many weight chunks");
   for (const auto* tab : {&plan.chunks, &plan.bwd_chunks})
     for (const TcChunk& c : *tab)
-      if (c.bytes > kStageBytes || c.bytes % 16 || c.ksteps == 0) return fail_arg("hn_field(bf16): internal chunk size error");
+      if (c.bytes > (tab == &plan.chunks ? fwd_chunk_bytes() : kStageBytes) || c.bytes % 32 || c.ksteps == 0)
+        return fail_arg("hn_field(bf16): internal chunk size error");
   h.n_chunks = (uint32_t)plan.chunks.size();
   h.bwd_n_chunks = (uint32_t)plan.bwd_chunks.size();
   auto align = [](uint32_t v, uint32_t a) { return (v + a - 1) / a * a; };

@@ -42,6 +42,9 @@ int hn_has_tcgen05(void);
 int hn_debug_tc_prof(unsigned long long* out_host);
 /* same for the cluster kernel (16 counters) */
 int hn_debug_tcc_prof(unsigned long long* out_host);
+/* Measurement aid (HN_TC_ABLATE & 8): timeline of one pass of cluster 0 of the cta_group::2 forward kernel,
+ * 4 roles x 32 layers x 2 clock values (layout in csrc/mlp_tc_2sm.cu). */
+int hn_debug_tc2_trace(long long* out_host);
 
 /* ------------------------------------------------------------------------------------------
  * a1  core/utils/camera_util.py:132-159  get_rays_from_KRT

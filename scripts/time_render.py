@@ -43,6 +43,20 @@ print(f'frame {ev0.elapsed_time(ev1) / args.reps:.2f} ms, culled fraction {net.l
       f'{float((out["rgb"] - ref["rgb"]).abs().max()):.2e}, max |alpha - dense| {float((out["alpha"] - ref["alpha"]).abs().max()):.2e}')
 print({k: round(v[0] / args.reps, 3) for k, v in t.items()}, 'TFLOP/s', round(1184768.0 * P / (t['field_fwd_bf16'][0] / args.reps * 1e-3) / 1e12, 1))
 
+if int(os.environ.get('HN_TC_ABLATE', '0')) & 8 and not os.environ.get('HN_TC_KERNEL'):
+    import ctypes
+    from humannerf_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_longlong * 512)()
+    lib.hn_debug_tc2_trace.restype = ctypes.c_int
+    _lib.check(lib.hn_debug_tc2_trace(buf), 'trace')
+    v = np.array(list(buf), dtype=np.int64).reshape(4, 32, 4)
+    t0 = v[:, :, :2][v[:, :, :2] > 0].min()
+    print('timeline of one pass of cluster 0 (clk since the first event); per layer: issuer X [ready, issued]  issuer Y [ready, issued]  '
+          'epi X [acc seen, handed over]  epi Y [acc seen, handed over]')
+    for l in range(15):
+        print(f'  layer {l:2d}: ' + '   '.join(f'[{(v[r, l, 0] - t0) if v[r, l, 0] else -1:7d} {(v[r, l, 1] - t0) if v[r, l, 1] else -1:7d}]' for r in range(4)) + f'   X wait-w/issue {v[0, l, 2]:5d} {v[0, l, 3]:5d}  Y {v[1, l, 2]:5d} {v[1, l, 3]:5d}')
+    sys.exit(0)
 if int(os.environ.get('HN_TC_ABLATE', '0')) & 8:
     import ctypes
     from humannerf_b200 import _lib
