@@ -296,6 +296,13 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
     const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
 
     int pass = 0;
+    float xn[3] = {0.f, 0.f, 0.f};                // positions of the coming pass
+    {
+      const int64_t sample0 = (cluster_id * 4 + tile * 2 + (int64_t)rank) * kTileM + row;
+      if (cluster_id < n_quads && sample0 < n_samples) {
+        xn[0] = __ldg(x_skel + sample0 * 3 + 0); xn[1] = __ldg(x_skel + sample0 * 3 + 1); xn[2] = __ldg(x_skel + sample0 * 3 + 2);
+      }
+    }
     for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters, ++pass) {
       const bool trace = (ablate & 8) && blockIdx.x == 0 && pass == kTraceQuad && lane == 0 && half == 0 && quarter == 2;
       // tile set X = tiles 4q, 4q+1 (CTA 0, CTA 1); tile set Y = tiles 4q+2, 4q+3
@@ -303,9 +310,16 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
       const int64_t sample = tile_idx * kTileM + row;
       const bool valid = sample < n_samples;
       const bool store = kStore && tile_idx < bufs.n_tiles;      // the training images hold ceil(P/128) tiles
-      float x[3] = {0.f, 0.f, 0.f};
-      if (valid) { x[0] = x_skel[sample * 3 + 0]; x[1] = x_skel[sample * 3 + 1]; x[2] = x_skel[sample * 3 + 2]; }
+      const float x[3] = {xn[0], xn[1], xn[2]};
       float q[3] = {x[0], x[1], x[2]};            // position fed to the canonical encoding
+      {
+        // the next pass's positions are fetched now: ~1 us of HBM latency would otherwise open every pass
+        const int64_t sample_n = ((quad + n_clusters) * 4 + tile * 2 + (int64_t)rank) * kTileM + row;
+        const bool valid_n = quad + n_clusters < n_quads && sample_n < n_samples;
+        xn[0] = valid_n ? __ldg(x_skel + sample_n * 3 + 0) : 0.f;
+        xn[1] = valid_n ? __ldg(x_skel + sample_n * 3 + 1) : 0.f;
+        xn[2] = valid_n ? __ldg(x_skel + sample_n * 3 + 2) : 0.f;
+      }
 
       if (!ignore_non_rigid) {
         write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad,

@@ -24,37 +24,45 @@ __device__ __forceinline__ size_t image_row_offset(int64_t tile, int r, int F) {
 }
 
 // columns: [optional x (3)], then per frequency sin(x,y,z), cos(x,y,z); zero padding up to `pad`
-// columns with a constant 1 in the last one (the bias column).
+// columns with a constant 1 in the last one (the bias column).  The two threads of a row (kHalf) store alternate
+// 16-byte chunks, and each evaluates only the columns it stores (one MUFU per column; the column -> (frequency,
+// axis, sin / cos) map is static after unrolling).
+template <bool kIncludeInput, int kHalf>
+__device__ __forceinline__ void write_encoding_half(uint32_t region, int row, const float x[3], int n_freqs,
+                                                    const float* __restrict__ weights, int pad, uint8_t* img_row) {
+  constexpr int base = kIncludeInput ? 3 : 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ch = 2 * j + kHalf;
+    if (ch * 8 < pad) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = ch * 8 + i;
+        float val = 0.0f;
+        if (c < base) {
+          val = x[c < 3 ? c : 0];
+        } else {
+          const int cc = c - base, k = cc / 6, r = cc - 6 * k, a = r >= 3 ? r - 3 : r;
+          if (k < 10 && k < n_freqs) {
+            const float arg = x[a] * (float)(1 << k);
+            const float t = r >= 3 ? __cosf(arg) : __sinf(arg);
+            val = weights ? weights[k] * t : t;
+          }
+        }
+        v[i] = val;
+      }
+      if (ch * 8 + 8 == pad) v[7] = 1.0f;
+      store8(region, row, ch, v, img_row);
+    }
+  }
+}
+
 template <bool kIncludeInput>
 __device__ __forceinline__ void write_encoding(uint32_t region, int row, int half, const float x[3], int n_freqs,
                                                const float* __restrict__ weights, int pad, uint8_t* img_row) {
-  float pe[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) pe[i] = 0.0f;
-  int base = 0;
-  if (kIncludeInput) { pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2]; base = 3; }
-  float freq = 1.0f;
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    if (k < n_freqs) {
-      const float w = weights ? weights[k] : 1.0f;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        float s, c;
-        __sincosf(x[a] * freq, &s, &c);
-        pe[base + k * 6 + a] = w * s;
-        pe[base + k * 6 + 3 + a] = w * c;
-      }
-    }
-    freq *= 2.0f;
-  }
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    if (ch * 8 < pad && (ch & 1) == half) {
-      if (ch * 8 + 8 == pad) pe[ch * 8 + 7] = 1.0f;
-      store8(region, row, ch, pe + ch * 8, img_row);
-    }
-  }
+  if (half == 0) write_encoding_half<kIncludeInput, 0>(region, row, x, n_freqs, weights, pad, img_row);
+  else write_encoding_half<kIncludeInput, 1>(region, row, x, n_freqs, weights, pad, img_row);
 }
 
 }  // namespace hn

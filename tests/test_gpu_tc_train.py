@@ -384,14 +384,21 @@ def test_graphed_train_step_matches_eager(ops, precision):
     print(f'[parity] graphed step ({precision}): max parameter difference after 3 steps {worst:.3e}')
 
 
-def test_experimental_cluster_kernel_parity():
-    """The experimental cluster forward kernel (HN_TC_KERNEL=cluster, csrc/mlp_tc_cl.cu: TMA multicast of the
-    weight stream across a CTA pair, double-buffered TMEM accumulators, block-granular operand hand-over)
-    must pass the same forward parity and training tests as the default kernel.  The choice is read once
-    per process, hence the subprocess."""
+@pytest.mark.parametrize('variant', ['pair', 'cluster', '2sm-8-stages'])
+def test_other_forward_kernels_parity(variant):
+    """The default tcgen05 forward kernel is the cta_group::2 kernel of csrc/mlp_tc_2sm.cu with a 4 x 16 KB ring.
+    The other forward kernels must pass the same forward parity and training tests: HN_TC_KERNEL=pair (csrc/mlp_tc.cu,
+    one CTA per SM, cta_group::1), HN_TC_KERNEL=cluster (csrc/mlp_tc_cl.cu, experimental: TMA multicast of the
+    weight stream across a CTA pair, double-buffered TMEM accumulators, block-granular operand hand-over) and the
+    cta_group::2 kernel with an 8 x 8 KB ring (HN_TC_2SM_STAGES=8).  The choice is read once per process (the
+    forward part of the weight image depends on it), hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, HN_TC_KERNEL='cluster')
+    env = dict(os.environ)
+    if variant == '2sm-8-stages':
+        env['HN_TC_2SM_STAGES'] = '8'
+    else:
+        env['HN_TC_KERNEL'] = variant
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', '-k',
                         'field_bf16_forward or network_eval_bf16 or field_bf16_backward',
                         os.path.join(root, 'tests')], env=env, cwd=root, capture_output=True, text=True, timeout=900)
