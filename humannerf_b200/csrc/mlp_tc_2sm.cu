@@ -106,6 +106,21 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// Training: the operand block a warp has just written IS the T16 image of its rows (16 rows x 8 columns = 256
+// contiguous bytes in both).  A warp owns 2 sixteen-row groups x `n_blocks / 2` column chunks; lane l copies block
+// (group 2 * quarter + (l & 1), chunk `chunk`) with one shared -> global bulk copy (TMA) instead of every thread
+// storing 16 bytes per chunk.  Callers: fence.proxy.async by every writer and __syncwarp() first; the source is
+// reused only after cp.async.bulk.wait_group.read (bulk_wait_read0) by every lane and another __syncwarp().
+__device__ __forceinline__ void store_blocks(uint8_t* image, int64_t tile_idx, int F, uint32_t s_block, int quarter, int lane,
+                                             int chunk, int n_blocks) {
+  if (lane < n_blocks) {
+    const int g = 2 * quarter + (lane & 1);
+    bulk_s2g(image + (size_t)tile_idx * 128 * F * 2 + (size_t)g * F * 32 + (size_t)chunk * 256,
+             s_block + (uint32_t)chunk * kLboA + (uint32_t)g * 256u, 256u);
+  }
+  bulk_commit();
+}
+
 template <bool kStore>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
@@ -322,22 +337,24 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
       }
 
       if (!ignore_non_rigid) {
-        write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad,
-                              store ? bufs.pe[0] + image_row_offset(tile_idx, row, nr_pad) : nullptr);
+        if (kStore) { bulk_wait_read0(); __syncwarp(); }       // the block's previous image copy has left shared memory
+        write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad, nullptr);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_ready);
+        if (store) store_blocks(bufs.pe[0], tile_idx, nr_pad, a_pe, quarter, lane, (lane >> 1) * 2 + half, 2 * (nr_pad >> 4));
       }
 
       for (int layer = first_layer; layer < n_layers; ++layer) {
         const bool is_nr = layer < nr_layers;
         const bool is_out = (layer == nr_layers - 1) || (layer == n_layers - 1);
         if (layer == nr_layers) {
-          write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad,
-                               store ? bufs.pe[1] + image_row_offset(tile_idx, row, cn_pad) : nullptr);
+          if (kStore) { bulk_wait_read0(); __syncwarp(); }
+          write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad, nullptr);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(bar_ready);
+          if (store) store_blocks(bufs.pe[1], tile_idx, cn_pad, a_pe, quarter, lane, (lane >> 1) * 2 + half, 2 * (cn_pad >> 4));
         }
         mbar_wait(bar_acc, acc_phase, 4);
         acc_phase ^= 1;
@@ -353,9 +370,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           const int n_full = (int)hdr->layer_n[layer];
           const int n_half = n_full >> 1;                          // columns owned by this thread
           const int c_begin = half * n_half;
-          uint8_t* h_img = nullptr;
-          if (store)
-            h_img = (is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers]) + image_row_offset(tile_idx, row, n_full);
+          if (kStore) { bulk_wait_read0(); __syncwarp(); }     // the block's previous image copy has left shared memory
           uint32_t v[2][32];
           tmem_ld32(t_acc + (uint32_t)c_begin, v[0]);
 #pragma unroll 1
@@ -372,7 +387,6 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
                                           pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
                                           pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
               st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
-              if (store) *reinterpret_cast<uint4*>(h_img + (size_t)chunk * 256) = pk;
             }
             if (c0 + 32 < n_half) {
               tmem_ld_wait();
@@ -386,7 +400,6 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
                                             pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
                                             pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
                 st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
-                if (store) *reinterpret_cast<uint4*>(h_img + (size_t)chunk * 256) = pk;
               }
             }
           }
@@ -395,6 +408,9 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(bar_ready);
           if (trace) g_tc2_trace[2 + tile][layer][1] = clock64();
+          if (store)
+            store_blocks(is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers], tile_idx, n_full, a_h, quarter, lane,
+                         half * (n_half >> 3) + (lane >> 1), 2 * (n_half >> 3));
         } else {
           uint32_t v[16];
           tmem_ld16(t_acc, v);
@@ -420,6 +436,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
         }
       }
     }
+    if (kStore) bulk_wait0();                       // image copies complete before the CTA gives up its shared memory
   }
 
   tc_fence_before();
