@@ -32,52 +32,9 @@
 
 #include "mlp_tc_plan.cuh"
 #include "mlp_tc_enc.cuh"
+#include "mlp_tc_2sm.cuh"
 
 namespace hn {
-
-namespace s2 {
-constexpr int kStages2 = 8;                                            // barrier slots (the ring has 4 or 8 stages)
-constexpr uint32_t kRingBytes2 = 65536;                                // per CTA: 4 x 16 KB or 8 x 8 KB half chunks
-constexpr uint32_t kBarOff2 = kRingOff + kRingBytes2;
-// barriers: full[8] floc[8] empty[8] acc_full[2] a_ready[2] + tmem slot
-constexpr uint32_t kBarBytes2 = (3 * kStages2 + 2 * kTiles) * 8 + 8;
-constexpr uint32_t kTableOff2 = kBarOff2 + 256;
-constexpr uint32_t kSmemTotal2 = kTableOff2 + kMaxChunks * 16;
-constexpr int kSetRows = 2 * kTileM;                                   // rows of one tile set (MMA M)
-static_assert(kBarBytes2 <= 256, "barrier block");
-static_assert(kSmemTotal2 <= 232448, "shared memory budget");
-}  // namespace s2
-
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A (256 rows, 128 per CTA) * B^T (N rows, N/2 per CTA); issued by one thread of the leader
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of the pair retire
-__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 256 (pair), N
-__device__ __forceinline__ uint32_t make_idesc2(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
 
 // Timeline of one pass of cluster 0 (measurement aid, HN_TC_ABLATE & 8): clock64 of the leader SM at
 //   [role 0/1 = issuer X/Y][layer][0] operand ready (after the a_ready wait), [1] last MMA + commits issued;
@@ -85,41 +42,6 @@ __device__ __forceinline__ uint32_t make_idesc2(uint32_t n) {
 //   [1] operand handed over (arrive done)
 __device__ long long g_tc2_trace[4][32][4];   // issuers: [2] cycles waiting for weights, [3] cycles issuing MMAs + commits
 constexpr int kTraceQuad = 6;      // which pass of cluster 0 is recorded
-
-// What the MMA issuers need per chunk, as a KERNEL PARAMETER (constant bank, warp-uniform loads): x = byte offset of
-// the chunk's first A core matrix inside its operand block, y = N | K steps << 16 | flags << 24 (TcChunk's last word).
-// The issuer warps run convergently with every operand in uniform registers and elect one lane per MMA: a lone
-// diverged thread pays a ~15-instruction ELECT / R2UR.BROADCAST waterfall per tcgen05 instruction plus ~100 dependent
-// vector instructions per chunk (measured: 580 clk per chunk + 61 clk per MMA, against 256 clk of tensor pipe time).
-struct IssueTab {
-  uint2 e[kMaxChunks];
-};
-
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n" : "=r"(pred));
-  return pred;
-}
-
-// Training: the operand block a warp has just written IS the T16 image of its rows (16 rows x 8 columns = 256
-// contiguous bytes in both).  A warp owns 2 sixteen-row groups x `n_blocks / 2` column chunks; lane l copies block
-// (group 2 * quarter + (l & 1), chunk `chunk`) with one shared -> global bulk copy (TMA) instead of every thread
-// storing 16 bytes per chunk.  Callers: fence.proxy.async by every writer and __syncwarp() first; the source is
-// reused only after cp.async.bulk.wait_group.read (bulk_wait_read0) by every lane and another __syncwarp().
-__device__ __forceinline__ void store_blocks(uint8_t* image, int64_t tile_idx, int F, uint32_t s_block, int quarter, int lane,
-                                             int chunk, int n_blocks) {
-  if (lane < n_blocks) {
-    const int g = 2 * quarter + (lane & 1);
-    bulk_s2g(image + (size_t)tile_idx * 128 * F * 2 + (size_t)g * F * 32 + (size_t)chunk * 256,
-             s_block + (uint32_t)chunk * kLboA + (uint32_t)g * 256u, 256u);
-  }
-  bulk_commit();
-}
 
 template <bool kStore>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)

@@ -14,6 +14,7 @@
 //
 // Autograd of reference mlp_offset.py:74-114 and mlp_rgb_sigma.py:132-206 on the bf16 path.
 #include "mlp_tc_plan.cuh"
+#include "mlp_tc_enc.cuh"
 
 namespace hn {
 
@@ -22,16 +23,13 @@ int add3(int64_t n, const float* a, int64_t lda, const float* b, int64_t ldb, fl
          cudaStream_t st);
 int copy_cols(int64_t n, int n_cols, const float* src, int64_t src_ld, float* dst, int64_t dst_ld,
               cudaStream_t st);
+// mlp_tc_bwd_2sm.cu
+int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, int mlp,
+                         const float* d_out, int ld_out, int n_out, const TrainBufs& bufs, const float* pos,
+                         const float* hann_w, float* d_pos, int ld_dpos, int sms, cudaStream_t st);
 
 __device__ __forceinline__ size_t image_row_offset_b(int64_t tile, int r, int F) {
   return (size_t)tile * 128 * F * 2 + (size_t)(r >> 4) * 16 * F * 2 + (size_t)(r & 15) * 16;
-}
-
-// acc masked by a packed pair of bf16 activations (ReLU outputs: positive <=> bit pattern != 0)
-__device__ __forceinline__ uint32_t mask_pack(uint32_t h2, uint32_t a_lo, uint32_t a_hi) {
-  const float lo = (h2 & 0xFFFFu) ? __uint_as_float(a_lo) : 0.0f;
-  const float hi = (h2 >> 16) ? __uint_as_float(a_hi) : 0.0f;
-  return pack_bf16(lo, hi);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -344,14 +342,25 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   //    by the chain's epilogue (both encoding reads: skip layer and layer 0)
   if (d_xyz) HN_TRY(copy_cols(n, 3, d_xyz, 3, d_xyz_tot, 4, st));
   else HN_TRY(check_cuda(cudaMemsetAsync(d_xyz_tot, 0, (size_t)rows * 4 * sizeof(float), st), "hn_field_bwd_bf16/memset"));
-  field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, n_samples_dev, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4);
-  HN_TRY(launched("hn_field_bwd_bf16/canonical chain"));
+  // default: the cta_group::2 chain kernel (mlp_tc_bwd_2sm.cu); HN_TC_KERNEL=pair / cluster: the tile-pair kernel above
+  const bool two_sm = use_2sm_kernel();
+  if (two_sm && sms < 2) return fail_arg("hn_field_bwd_bf16: the tcgen05 chain kernel needs a device with thread-block clusters");
+  if (two_sm) {
+    HN_TRY(launch_field_tc2_bwd(plan, pk, n, n_samples_dev, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4, sms, st));
+  } else {
+    field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, n_samples_dev, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4);
+    HN_TRY(launched("hn_field_bwd_bf16/canonical chain"));
+  }
   // 2. non-rigid MLP: its output gradient is d_xyz_tot + d_offsets; d_x_skel = d_xyz_tot + PE'(x_skel) . d(encoding)
   HN_TRY(copy_cols(n, 3, d_xyz_tot, 4, d_x_skel, 3, st));
   if (!ignore_non_rigid) {
     HN_TRY(add3(n, d_xyz_tot, 4, d_offsets, 3, dz_nr, 4, st));
-    field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, n_samples_dev, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3);
-    HN_TRY(launched("hn_field_bwd_bf16/non-rigid chain"));
+    if (two_sm) {
+      HN_TRY(launch_field_tc2_bwd(plan, pk, n, n_samples_dev, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3, sms, st));
+    } else {
+      field_tc_bwd_kernel<<<grid, kThreads, kSmemTotal, st>>>(pk, n, n_samples_dev, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3);
+      HN_TRY(launched("hn_field_bwd_bf16/non-rigid chain"));
+    }
   }
   // 3. weight / bias gradients from the images
   std::vector<WgradJob> jobs;

@@ -65,4 +65,11 @@ __device__ __forceinline__ void write_encoding(uint32_t region, int row, int hal
   else write_encoding_half<kIncludeInput, 1>(region, row, x, n_freqs, weights, pad, img_row);
 }
 
+// acc masked by a packed pair of bf16 activations (ReLU outputs: positive <=> bit pattern != 0)
+__device__ __forceinline__ uint32_t mask_pack(uint32_t h2, uint32_t a_lo, uint32_t a_hi) {
+  const float lo = (h2 & 0xFFFFu) ? __uint_as_float(a_lo) : 0.0f;
+  const float hi = (h2 >> 16) ? __uint_as_float(a_hi) : 0.0f;
+  return pack_bf16(lo, hi);
+}
+
 }  // namespace hn

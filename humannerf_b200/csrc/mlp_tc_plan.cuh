@@ -122,7 +122,7 @@ static inline int tc2_stages() {
   }();
   return v;
 }
-// largest forward chunk (bytes, both halves) for the selected forward kernel
+// largest weight chunk (bytes, both halves) for the selected kernel family (forward and backward-data chain)
 static inline uint32_t fwd_chunk_bytes() {
   return use_2sm_kernel() ? 2u * (65536u / (uint32_t)tc2_stages()) : kStageBytes;
 }
@@ -164,7 +164,7 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
   auto add_segment = [&](std::vector<TcChunk>& table, const float* W, int ldw, int col0, int valid_k, int k_pad,
                          int valid_n, int n, bool in_pe, int a_col0, bool first, bool last, int bias_col,
                          const float* bias, const float* fold_w, int fold_ld, int fold_k, bool transpose, int row0) {
-    const uint32_t chunk_cap = (&table == &plan.chunks) ? fwd_chunk_bytes() : kStageBytes;
+    const uint32_t chunk_cap = fwd_chunk_bytes();      // forward and backward tables share the kernel family
     int kc_max = (int)(chunk_cap / (uint32_t)(n * 2)) / 16 * 16;
     if (kc_max > 240) kc_max = 240;                       // ksteps is a uint8
     // for the experimental cluster kernel (HN_TC_KERNEL=cluster, mlp_tc_cl.cu) forward chunks never span
@@ -185,7 +185,7 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
       j.src = W; j.src_ld = ldw; j.valid_n = valid_n; j.n = n; j.kc = kc; j.w_off = w_off;
       j.valid_k = std::max(0, valid_k - k0);
       j.transpose = transpose ? 1 : 0;
-      j.split = (&table == &plan.chunks && use_2sm_kernel()) ? 1 : 0;
+      j.split = use_2sm_kernel() ? 1 : 0;
       if (transpose) { j.src_col0 = col0; j.src_row0 = row0 + k0; }
       else { j.src_col0 = col0 + k0; j.src_row0 = 0; }
       j.bias_row = -1;
@@ -279,7 +279,7 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
     return fail_arg("hn_field(bf16): too many weight chunks");
   for (const auto* tab : {&plan.chunks, &plan.bwd_chunks})
     for (const TcChunk& c : *tab)
-      if (c.bytes > (tab == &plan.chunks ? fwd_chunk_bytes() : kStageBytes) || c.bytes % 32 || c.ksteps == 0)
+      if (c.bytes > fwd_chunk_bytes() || c.bytes % 32 || c.ksteps == 0)
         return fail_arg("hn_field(bf16): internal chunk size error");
   h.n_chunks = (uint32_t)plan.chunks.size();
   h.bwd_n_chunks = (uint32_t)plan.bwd_chunks.size();
