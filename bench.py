@@ -447,21 +447,21 @@ def main():
     sfx = '_' + args.precision
     fld_ms = op_ms.get('field_fwd' + sfx, (0, 0))[0] + op_ms.get('field_bwd' + sfx, (0, 0))[0]
     achieved_tf = FLOPS_FWD_BWD * samples_local / (fld_ms * 1e-3) / 1e12 if fld_ms > 0 else 0.0
-    kname = ('canonical field fwd+bwd: field_tc_kernel<store> + field_tc_bwd_kernel x2 + tile_wgrad_kernel (tcgen05, bf16)'
+    kname = ('canonical field fwd+bwd: field_tc2_kernel<store> + field_tc2_bwd_kernel x2 (cta_group::2 CTA pairs) + tile_wgrad_kernel (tcgen05, bf16)'
              if args.precision == 'bf16' else 'canonical field fwd+bwd (fp32 SIMT sgemm_kernel chain)')
     roofline = {'kernel': kname,
                 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peaks['tf_sustained'],
                 # dram__bytes_read + write of the four launches of one 6144-ray step, ncu --set full
-                # (profiles/r01d_ncu_full_summary.json): 4.81 + 6.53 + 2.45 + 11.20 GB
-                'traffic': 24.99e9 if args.precision == 'bf16' else None,
+                # (profiles/r01e_ncu_full_summary.json): 4.79 + 6.52 + 2.45 + 9.62 GB
+                'traffic': 23.38e9 if args.precision == 'bf16' else None,
                 'peak_source': peaks['source'] + ' (sustained bf16)',
                 'share_of_step': (fld_ms / roof_steps) / max(ms / args.steps, 1e-9),
                 'timed': 'per-op CUDA events' + (' in an eager re-run of the same steps (the timed region replays a CUDA graph)'
                                                  if graphed is not None else ' inside the timed region')}
     if args.precision == 'bf16' and fld_ms > 0:
         # the same kernel group seen from the memory side: the stored-activation design moves 32 KB / sample
-        gbs = 24.99e9 * (samples_local / roof_steps / (N_PATCHES * PATCH * PATCH * N_SAMPLES)) / (fld_ms / roof_steps * 1e-3) / 1e9
+        gbs = 23.38e9 * (samples_local / roof_steps / (N_PATCHES * PATCH * PATCH * N_SAMPLES)) / (fld_ms / roof_steps * 1e-3) / 1e9
         roofline['hbm_view'] = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                 'frac': gbs / peaks['hbm_gbs'], 'note': 'measured DRAM traffic (ncu) / measured time'}
     op_table = {k: {'ms_total': round(v[0], 3), 'calls': v[1]} for k, v in sorted(op_ms.items())}
@@ -508,14 +508,14 @@ def main():
         result['render'] = {
             'rays_per_sec': n_valid / (rms * 1e-3), 'samples_per_sec': n_valid * N_SAMPLES / (rms * 1e-3), 'ms_per_frame': rms,
             'rays': int(n_valid), 'scaling': 'strong (one frame, rays sharded over ranks + all_gather of 20 B/ray)', 'ops_ms_per_frame': {k: round(v[0] / reps, 3) for k, v in sorted(rop.items())},
-            'roofline_mlp': {'kernel': 'field_tc_kernel (tcgen05/TMEM fused PE+MLPs)', 'bound': 'tensor', 'achieved': tc_tf,
+            'roofline_mlp': {'kernel': 'field_tc2_kernel (tcgen05 cta_group::2 / TMEM, fused PE + MLPs on CTA pairs)', 'bound': 'tensor', 'achieved': tc_tf,
                              'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': tc_tf / peaks['tf'],
-                             'traffic': 174.2e6,       # per 32768-ray launch, ncu --set full (profiles/r01d_ncu_full_summary.json)
+                             'traffic': 176.0e6,       # per 32768-ray launch, ncu --set full (profiles/r01e_ncu_full_summary.json)
                              'peak_source': peaks['source'] + ' (burst bf16)'},
             'roofline_motion_field': {'kernel': 'motion_field_fwd_kernel<false> (weights output omitted: 28 B/sample); instruction-issue bound (ncu: issue slots 80 % busy), not HBM bound - see DESIGN.md 4.3',
                                       'bound': 'hbm', 'achieved': mf_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                       'frac': mf_gbs / peaks['hbm_gbs'],
-                                      'traffic': 33.3e6,    # per 32768-ray launch (profiles/r01d_ncu_full_summary.json)
+                                      'traffic': 33.1e6,    # per 32768-ray launch (profiles/r01e_ncu_full_summary.json)
                                       'issue_slots_busy_pct_ncu': 86.2, 'peak_source': peaks['source']},
         }
 

@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-HN_ABI_VERSION = 3
+HN_ABI_VERSION = 4
 HN_MAX_LAYERS = 16
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
@@ -65,7 +65,7 @@ SIGNATURES = {
     'hn_sample_z': (_int, [_i64, _int, _p, _p, _p, _p, _p, _p]),
     'hn_motion_field_workspace_bytes': (_i64, [_int, _int]),
     'hn_motion_field_fwd': (_int, [_i64, _int, _int, _int] + [_p] * 13 + [_i64, _p]),
-    'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 19),
+    'hn_motion_field_bwd': (_int, [_i64, _int, _int, _int] + [_p] * 19 + [_i64, _p]),
     'hn_field_workspace_bytes': (_i64, [C.POINTER(FieldParams), _i64, _int, _int]),
     'hn_field_fwd': (_int, [C.POINTER(FieldParams), _i64, _p, _p, _p, _int, _p, _p, _p, _p, _i64, _int, _int, _p, _p, _p]),
     'hn_field_bwd_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),

@@ -180,7 +180,8 @@ motion_field_bwd_kernel(int64_t n_pts, int S, int J, int V, const float* __restr
                         const float* __restrict__ d_x_skel, const float* __restrict__ d_mask,
                         const float* __restrict__ d_weights, const float* __restrict__ x_skel_fwd,
                         const float* __restrict__ mask_fwd, float* __restrict__ d_vol,
-                        float* __restrict__ d_Rs, float* __restrict__ d_Ts, const float4* __restrict__ table) {
+                        float* __restrict__ d_Rs, float* __restrict__ d_Ts, const float4* __restrict__ table,
+                        float4* __restrict__ d_table) {
   __shared__ float s_R[kMaxJoints * 9];
   __shared__ float s_T[kMaxJoints * 3];
   __shared__ float s_acc[kMaxJoints * 12];   // per-block dR (9) + dT (3) per joint
@@ -262,7 +263,16 @@ motion_field_bwd_kernel(int64_t n_pts, int S, int J, int V, const float* __restr
         dp[1] = w * dN[1] + dw * gyv * (bs[1] * half_v);
         dp[2] = w * dN[2] + dw * gzv * (bs[2] * half_v);
         contributes = true;
-        if (dw != 0.0f) {
+        if (dw != 0.0f && d_table) {
+          // gradient of the 8 corners of the cell as two 16-byte vector reductions into the corner-table layout
+          // (red.global.add.v4.f32: a quarter of the atomic operations); unpack_corners_grad_kernel folds it into d_vol
+          const int C = V + 1;
+          const int64_t cell = (((int64_t)j * C + (t.z0 + 1)) * C + (t.y0 + 1)) * C + (t.x0 + 1);
+          const float a0 = dw * uz, a1 = dw * t.tz;
+          const float b00 = a0 * uy, b01 = a0 * t.ty, b10 = a1 * uy, b11 = a1 * t.ty;
+          atomicAdd(d_table + 2 * cell, make_float4(b00 * ux, b00 * t.tx, b01 * ux, b01 * t.tx));
+          atomicAdd(d_table + 2 * cell + 1, make_float4(b10 * ux, b10 * t.tx, b11 * ux, b11 * t.tx));
+        } else if (dw != 0.0f) {
           float* gj = d_vol + j * vstride;
 #pragma unroll
           for (int dz = 0; dz < 2; ++dz) {
@@ -345,6 +355,29 @@ static int check_common(const char* who, int64_t n_rays, int S, int J, int V, co
 
 using namespace hn;
 
+namespace hn {
+// d_vol[j][z][y][x] += the 8 table entries that hold voxel (z, y, x) as a corner: corner k of cell
+// (z + 1 - (k >> 2), y + 1 - ((k >> 1) & 1), x + 1 - (k & 1)) (the inverse of pack_corners_kernel)
+__global__ void unpack_corners_grad_kernel(int J, int V, const float* __restrict__ d_table, float* __restrict__ d_vol) {
+  const int C = V + 1;
+  const int64_t voxels = (int64_t)J * V * V * V;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int x = (int)(r % V); r /= V;
+    const int y = (int)(r % V); r /= V;
+    const int z = (int)(r % V);
+    const int j = (int)(r / V);
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t cell = (((int64_t)j * C + (z + 1 - (k >> 2))) * C + (y + 1 - ((k >> 1) & 1))) * C + (x + 1 - (k & 1));
+      acc += __ldg(d_table + cell * 8 + k);
+    }
+    d_vol[i] += acc;
+  }
+}
+}  // namespace hn
+
 extern "C" {
 
 int64_t hn_motion_field_workspace_bytes(int n_joints, int vol_size) {
@@ -402,16 +435,34 @@ int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
                         const float* Ts, const float* vol, const float* bbox_min,
                         const float* bbox_scale, const float* d_x_skel, const float* d_mask,
                         const float* d_weights, const float* x_skel_fwd, const float* mask_fwd,
-                        float* d_vol, float* d_Rs, float* d_Ts, const void* table, void* stream) {
+                        float* d_vol, float* d_Rs, float* d_Ts, const void* table, void* grad_workspace,
+                        int64_t grad_workspace_bytes, void* stream) {
   HN_TRY(check_common("hn_motion_field_bwd", n_rays, n_samples, n_joints, vol_size, pts, rays_o, rays_d, z,
                       Rs, Ts, vol, bbox_min, bbox_scale));
   if (!d_vol || !d_Rs || !d_Ts) return fail_arg("hn_motion_field_bwd: null gradient output");
   int64_t n = n_rays * n_samples;
   if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  // with a scratch buffer of hn_motion_field_workspace_bytes the volume gradient is scattered as 16-byte vector
+  // reductions in the corner-table layout and folded into d_vol afterwards; without one: 8 scalar atomics per joint
+  float4* d_table = nullptr;
+  const int64_t tbytes = hn_motion_field_workspace_bytes(n_joints, vol_size);
+  if (grad_workspace) {
+    if (grad_workspace_bytes < tbytes) return fail_arg("hn_motion_field_bwd: gradient workspace too small");
+    d_table = static_cast<float4*>(grad_workspace);
+    HN_TRY(check_cuda(cudaMemsetAsync(d_table, 0, (size_t)tbytes, st), "hn_motion_field_bwd/memset"));
+  }
   unsigned grid = (unsigned)ceil_div<int64_t>(n, 256);
-  motion_field_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+  motion_field_bwd_kernel<<<grid, 256, 0, st>>>(
       n, n_samples, n_joints, vol_size, pts, rays_o, rays_d, z, Rs, Ts, vol, bbox_min, bbox_scale, d_x_skel,
-      d_mask, d_weights, x_skel_fwd, mask_fwd, d_vol, d_Rs, d_Ts, static_cast<const float4*>(table));
+      d_mask, d_weights, x_skel_fwd, mask_fwd, d_vol, d_Rs, d_Ts, static_cast<const float4*>(table), d_table);
+  if (d_table) {
+    HN_TRY(launched("hn_motion_field_bwd"));
+    const int64_t voxels = (int64_t)n_joints * vol_size * vol_size * vol_size;
+    unpack_corners_grad_kernel<<<(unsigned)std::min<int64_t>(ceil_div<int64_t>(voxels, 256), 4096), 256, 0, st>>>(
+        n_joints, vol_size, reinterpret_cast<const float*>(d_table), d_vol);
+    return launched("hn_motion_field_bwd/unpack");
+  }
   return launched("hn_motion_field_bwd");
 }
 

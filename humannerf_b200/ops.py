@@ -192,11 +192,14 @@ class _MotionField(torch.autograd.Function):
         d_vol = torch.zeros_like(vol)
         d_Rs = torch.zeros_like(Rs)
         d_Ts = torch.zeros_like(Ts)
+        # scratch for the vector-reduction scatter of the volume gradient (same size as the corner table)
+        gbytes = int(lib.hn_motion_field_workspace_bytes(J, V)) if n_rays * S >= 4096 else 0
+        gtable = torch.empty(gbytes, dtype=torch.uint8, device=dev) if gbytes > 0 else None
         with torch.cuda.device(dev), _timed('motion_field_bwd'):
             check(lib.hn_motion_field_bwd(n_rays, S, J, V, ptr(pts), ptr(rays_o), ptr(rays_d), ptr(z), ptr(Rs),
                                           ptr(Ts), ptr(vol), ptr(bbox_min), ptr(bbox_scale), ptr(g_x), ptr(g_m),
                                           ptr(g_w), ptr(x_skel), ptr(mask), ptr(d_vol), ptr(d_Rs), ptr(d_Ts),
-                                          ptr(ctx.table), stream_ptr()),
+                                          ptr(ctx.table), ptr(gtable), gbytes, stream_ptr()),
                   'motion_field_bwd')
         return None, None, None, None, d_Rs, d_Ts, d_vol, None, None, None
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 3
+#define HN_ABI_VERSION 4
 #define HN_MAX_LAYERS 16
 
 /* ABI version of the loaded library (compare with HN_ABI_VERSION). */
@@ -104,6 +104,9 @@ int hn_motion_field_fwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
  * gradients.  x_skel_fwd (P,3) and mask_fwd (P) are the forward's outputs (both nullable together):
  * when given, the kernel skips re-evaluating the 24 lookups that only rebuild them.
  * table (nullable): the corner table a forward call left in its workspace (same vol).
+ * grad_workspace (nullable, hn_motion_field_workspace_bytes): scratch in which the volume gradient is scattered
+ * as 16-byte vector reductions (corner-table layout) before it is folded into d_vol; without it the kernel
+ * issues 8 scalar atomics per sample and joint.
  * Accumulates (+=) into d_vol (J,V,V,V), d_Rs (J,3,3), d_Ts (J,3): caller zeroes.
  */
 int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_size,
@@ -112,7 +115,8 @@ int hn_motion_field_bwd(int64_t n_rays, int n_samples, int n_joints, int vol_siz
                         const float* bbox_min, const float* bbox_scale,
                         const float* d_x_skel, const float* d_mask, const float* d_weights,
                         const float* x_skel_fwd, const float* mask_fwd,
-                        float* d_vol, float* d_Rs, float* d_Ts, const void* table, void* stream);
+                        float* d_vol, float* d_Rs, float* d_Ts, const void* table,
+                        void* grad_workspace, int64_t grad_workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a11-a14  embedders/{hannw_fourier,fourier}.py, non_rigid_motion_mlps/mlp_offset.py:74-114,
