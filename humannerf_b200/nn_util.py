@@ -77,6 +77,9 @@ class ConvDecoder3D(nn.Module):
         self.block_conv = nn.Sequential(*layers)
         init_sequence(self.block_mlp)
         init_sequence(self.block_conv)
+        # same values and shapes as the reference, NDHWC strides: cuDNN's transposed-convolution engines work in
+        # NDHWC and would otherwise transpose the 63.6 M weights (and their gradients) on every call, ~0.5 ms per step
+        self.block_conv.to(memory_format=torch.channels_last_3d)
 
     def forward(self, embedding):
         return self.block_conv(self.block_mlp(embedding).view(-1, 1024, 1, 1, 1))

@@ -111,8 +111,12 @@ class FusedAdam(torch.optim.Optimizer):
         from humannerf_b200 import _lib
         self._lib = _lib
         ps = [p for g in self.param_groups for p in g['params']]
-        if not ps or any(not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() for p in ps):
-            raise RuntimeError('FusedAdam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)')
+        # dense = one storage element per tensor element: row-major, or channels_last_3d for the transposed-convolution
+        # weights of the volume decoder (the kernel walks storage order; gradients must share the parameter's strides)
+        def dense(p):
+            return p.is_contiguous() or (p.dim() == 5 and p.is_contiguous(memory_format=torch.channels_last_3d))
+        if not ps or any(not p.is_cuda or p.dtype != torch.float32 or not dense(p) for p in ps):
+            raise RuntimeError('FusedAdam: parameters must be dense fp32 CUDA tensors (no CPU fallback)')
         if len({(g['betas'], g['eps']) for g in self.param_groups}) != 1:
             raise RuntimeError('FusedAdam: betas / eps must be the same for every group')
         dev = ps[0].device
@@ -130,8 +134,9 @@ class FusedAdam(torch.optim.Optimizer):
         table = (_lib.AdamTensor * n_t)()
         for i, (p, o) in enumerate(zip(ps, offs)):
             n = p.numel()
-            self.state[p] = {'step': self.step_dev[i:i + 1], 'exp_avg': self._flat_m[o:o + n].view_as(p),
-                             'exp_avg_sq': self._flat_v[o:o + n].view_as(p)}
+            self.state[p] = {'step': self.step_dev[i:i + 1],
+                             'exp_avg': torch.as_strided(self._flat_m[o:o + n], p.shape, p.stride()),
+                             'exp_avg_sq': torch.as_strided(self._flat_v[o:o + n], p.shape, p.stride())}
             table[i].param, table[i].grad = p.data_ptr(), None
             table[i].exp_avg, table[i].exp_avg_sq = self._flat_m[o:o + n].data_ptr(), self._flat_v[o:o + n].data_ptr()
             table[i].numel = n
@@ -179,8 +184,8 @@ class FusedAdam(torch.optim.Optimizer):
                 host[i] = 0
                 flags[2 * i] = 0.0
                 continue
-            if g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
-                g = g.to(torch.float32).contiguous().view_as(p)
+            if g.dtype != torch.float32 or g.shape != p.shape or g.stride() != p.stride():
+                g = torch.empty_like(p).copy_(g.view_as(p) if g.shape != p.shape else g)   # the parameter's strides
             keep.append(g)
             host[i] = g.data_ptr()
             flags[2 * i] = 1.0
