@@ -67,6 +67,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
   const uint32_t s_acc_full = s_empty + kStages2 * 8;        // both: multicast commit at the end of a layer
   const uint32_t s_a_ready = s_acc_full + kTiles * 8;        // leader: epilogue warps of both CTAs
   const uint32_t s_tmem_slot = s_a_ready + kTiles * 8;
+  const uint32_t s_lead = s_tmem_slot + 8;                   // leader: tile set X has issued the first chunk of a layer
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff2 + (3 * kStages2 + 2 * kTiles) * 8);
   const TcChunk* table = reinterpret_cast<const TcChunk*>(smem + kTableOff2);
 
@@ -96,6 +97,8 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
       mbar_init(s_acc_full + t * 8, 1);
       mbar_init(s_a_ready + t * 8, 2 * (kEpiWarps / kTiles));   // one arrive per epilogue warp of the tile set
     }
+    mbar_init(s_lead, 1);
+    mbar_init(s_lead + 8, 1);                                  // ... and Y has seen it (X never runs two layers ahead)
     fence_barrier_init();
   }
   if (warp == 1) {            // the same warp of both CTAs allocates collectively
@@ -148,6 +151,12 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
       const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
       const uint32_t a_inc = (2u * kLboA) >> 4;                                      // one K step = two core matrices
       uint32_t stage = 0, phase = 0, a_phase = 0, full_ok = 0;
+      // tile set X leads Y by one chunk (measured: +3.5 %; 2 / 3 / 4 chunks: +1.6 / -1.2 / +1.9 %: the 4-stage ring
+      // then stalls X on refills).  HN_TC_ABLATE=4 switches the lead off, bits 4-6 set other leads (measurement aid)
+      const uint32_t lead_chunks = (ablate & 4) ? ((uint32_t)ablate >> 4) & 7u : 1u;
+      const bool lead = lead_chunks != 0;
+      uint32_t in_layer = 0;
+      uint32_t n_layers_issued = 0;
       int pass = 0, tr_layer = 0;
       long long tr_wait = 0, tr_issue = 0;
       for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters, ++pass) {
@@ -156,9 +165,19 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
         for (uint32_t c = first_chunk; c < n_chunks; ++c) {
           const uint2 e = itab.e[c];
           const uint32_t n = e.y & 0xFFFFu, ksteps = (e.y >> 16) & 0xFFu, flags = e.y >> 24;
+          in_layer = (flags & 1u) ? 1u : in_layer + 1u;
           if (flags & 1u) {
             // the A operand of this layer is complete in both CTAs (and the previous accumulator drained)
             mbar_wait(bar_ready, a_phase, 2);
+            // tile set Y starts every layer one chunk behind X (lead / ack mbarrier pair; X never runs two layers
+            // ahead): the two sets then leave the MMA phase staggered instead of neck and neck
+            if (lead && t == 1u) {
+              mbar_wait(s_lead, a_phase, 6);
+              if (elect_one()) mbar_arrive(s_lead + 8);
+              __syncwarp();
+            }
+            if (lead && t == 0u && n_layers_issued > 0) mbar_wait(s_lead + 8, a_phase ^ 1u, 7);
+            ++n_layers_issued;
             a_phase ^= 1;
             if (trace) g_tc2_trace[t][tr_layer][0] = clock64();
           }
@@ -184,6 +203,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
             }
             umma2_commit_mc(s_empty + stage * 8);          // the slot is free in both CTAs once both issuers' MMAs retire
             if (flags & 2u) umma2_commit_mc(bar_acc);      // accumulator of the layer is complete (both CTAs)
+            if (lead && t == 0u && (in_layer == lead_chunks || ((flags & 2u) && in_layer < lead_chunks))) mbar_arrive(s_lead);
           }
           __syncwarp();
           if (trace) {

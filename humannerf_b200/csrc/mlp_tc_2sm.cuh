@@ -11,7 +11,7 @@ constexpr int kStages2 = 8;                                            // barrie
 constexpr uint32_t kRingBytes2 = 65536;                                // per CTA: 4 x 16 KB or 8 x 8 KB half chunks
 constexpr uint32_t kBarOff2 = kRingOff + kRingBytes2;
 // barriers: full[8] floc[8] empty[8] acc_full[2] a_ready[2] + tmem slot
-constexpr uint32_t kBarBytes2 = (3 * kStages2 + 2 * kTiles) * 8 + 8;
+constexpr uint32_t kBarBytes2 = (3 * kStages2 + 2 * kTiles) * 8 + 8 + 16;   // + lead / ack barriers of the forward kernel
 constexpr uint32_t kTableOff2 = kBarOff2 + 256;
 constexpr uint32_t kSmemTotal2 = kTableOff2 + kMaxChunks * 16;
 constexpr int kSetRows = 2 * kTileM;                                   // rows of one tile set (MMA M)
