@@ -349,6 +349,12 @@ def main():
     for i in range(args.warmup):
         train_step(dev_batches[i], it_val)
     barrier()
+    if world > 1:
+        # the first multi-GPU run on a fresh box has shown a one-off ~45 ms stall a few replays after the first
+        # barrier (NCCL / peer-mapping lazy initialisation): settle with more untimed replays of the warm-up batches
+        for r in range(10):
+            train_step(dev_batches[r % max(args.warmup, 1)], it_val)
+        barrier()
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = _lib.launch_count()
