@@ -54,13 +54,15 @@ class PerceptualLoss(nn.Module):
         self.eval()
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        x, y = (x - self.shift) / self.scale, (y - self.shift) / self.scale
+        # prediction and target go through the trunk as ONE batch (half the launches of two passes; every op
+        # of the trunk is per image, so the values are those of lpips.py:78-92)
+        n = x.shape[0]
+        f = (torch.cat([x, y], 0) - self.shift) / self.scale
         total = 0.0
         for stage, lin in zip(self.stages, self.lins):
-            x, y = stage(x), stage(y)
-            nx = x / (torch.sqrt(torch.sum(x ** 2, dim=1, keepdim=True)) + 1e-10)
-            ny = y / (torch.sqrt(torch.sum(y ** 2, dim=1, keepdim=True)) + 1e-10)
-            total = total + lin((nx - ny) ** 2).mean([2, 3], keepdim=True)
+            f = stage(f)
+            nf = f / (torch.sqrt(torch.sum(f ** 2, dim=1, keepdim=True)) + 1e-10)
+            total = total + lin((nf[:n] - nf[n:]) ** 2).mean([2, 3], keepdim=True)
         return total
 
 

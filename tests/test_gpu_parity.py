@@ -222,6 +222,45 @@ def test_motion_field_backward(ops, frame):
     rel_max('motion_field.d_Rs(x only)', Rc2.grad, Rs.grad, 5e-3)
 
 
+def test_motion_field_backward_vector_scatter(ops, frame):
+    """From 4096 samples on, the backward scatters the volume gradient as 16-byte vector reductions into a corner-table
+    shaped scratch buffer and folds it into d_vol afterwards (hn_motion_field_bwd `grad_workspace`); below that it
+    issues scalar atomics.  72 rays x 128 samples (the golden rays, three times with shifted depths) against the
+    oracle's autograd, and the two scatter paths against each other through the C ABI."""
+    from humannerf_b200 import _lib
+    g, o, d, z = _mf_inputs(frame)
+    o, d = o.repeat(3, 1), d.repeat(3, 1)
+    z = torch.cat([z, z + 0.011, z - 0.007], 0)
+    R, S = z.shape
+    assert R * S >= 4096
+    bmin, bsc = T(frame['cnl_bbox_min_xyz']), T(frame['cnl_bbox_scale_xyz'])
+    Rs0, Ts0, vol0 = T(g['motion_scale_Rs']), T(g['motion_Ts']), T(g['vol'])[:24].contiguous()
+    gen = torch.Generator().manual_seed(17)
+    gx, gm = torch.randn(R, S, 3, generator=gen), torch.randn(R, S, 1, generator=gen)
+    Rs, Ts, vol = Rs0.clone().requires_grad_(), Ts0.clone().requires_grad_(), vol0.clone().requires_grad_()
+    pts = (o[:, None, :] + d[:, None, :] * z[..., None]).reshape(-1, 3)
+    xs, ms, _ = orc.sample_motion_fields(pts, Rs, Ts, torch.cat([vol, torch.zeros(1, 32, 32, 32)], 0), bmin, bsc)
+    ((xs.view(R, S, 3) * gx).sum() + (ms.view(R, S, 1) * gm).sum()).backward()
+    Rc, Tc, vc = Rs0.to(DEV).requires_grad_(), Ts0.to(DEV).requires_grad_(), vol0.to(DEV).requires_grad_()
+    x, m, _ = ops.motion_field(Rc, Tc, vc, bmin.to(DEV), bsc.to(DEV), rays_o=o.to(DEV), rays_d=d.to(DEV), z=z.to(DEV),
+                               want_weights=False)
+    ((x * gx.to(DEV)).sum() + (m * gm.to(DEV)).sum()).backward()
+    rel_max('motion_field.d_vol (vector scatter)', vc.grad, vol.grad, 2e-3)
+    rel_max('motion_field.d_Rs (vector scatter)', Rc.grad, Rs.grad, 5e-3)
+    rel_max('motion_field.d_Ts (vector scatter)', Tc.grad, Ts.grad, 5e-3)
+    # the scalar-atomic path on the same inputs, straight through the C ABI (no gradient workspace)
+    lib, ptr = _lib.load(), _lib.ptr
+    dv, dR, dT = torch.zeros_like(vc), torch.zeros_like(Rc), torch.zeros_like(Tc)
+    od, dd, zd, gxd, gmd = o.to(DEV), d.to(DEV), z.to(DEV).contiguous(), gx.to(DEV).contiguous(), gm.to(DEV).contiguous()
+    bmd, bsd = bmin.to(DEV), bsc.to(DEV)
+    _lib.check(lib.hn_motion_field_bwd(R, S, 24, 32, None, ptr(od), ptr(dd), ptr(zd), ptr(Rc.detach()), ptr(Tc.detach()),
+                                       ptr(vc.detach()), ptr(bmd), ptr(bsd), ptr(gxd), ptr(gmd), None, None, None,
+                                       ptr(dv), ptr(dR), ptr(dT), None, None, 0, _lib.stream_ptr()), 'motion_field_bwd')
+    torch.cuda.synchronize()
+    rel_max('motion_field.d_vol (scalar vs vector)', dv, vc.grad, 1e-4)
+    rel_max('motion_field.d_Rs (scalar vs vector)', dR, Rc.grad, 1e-4)
+
+
 # --------------------------------------------------------------------------------------
 # compositing
 # --------------------------------------------------------------------------------------
