@@ -11,7 +11,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 if [ "${HN_TC_PROFILE:-0}" = "1" ]; then FLAGS="$FLAGS -DHN_TC_PROFILE"; fi
 objs=()
 pids=()
-for f in api rays motion_field composite field_fp32 mlp_tc mlp_tc_2sm mlp_tc_cl mlp_tc_bwd mlp_tc_bwd_2sm tile_wgrad adam pose_fk; do
+for f in api rays motion_field composite field_fp32 mlp_tc mlp_tc_2sm mlp_tc_cl mlp_tc_bwd mlp_tc_bwd_2sm tile_wgrad adam pose_fk lpips_head; do
   $NVCC $FLAGS -c $SRC/$f.cu -o build/$f.o > build/$f.log 2>&1 &
   pids+=($!)
   objs+=(build/$f.o)

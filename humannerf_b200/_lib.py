@@ -91,6 +91,8 @@ SIGNATURES = {
     'hn_tile_wgrad': (_int, [C.POINTER(WgradJob), _int, _i64, _p, _p]),
     'hn_scatter_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
     'hn_gather_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
+    'hn_lpips_head_fwd': (_int, [_int, _int, _int, _p, _i64, _i64, _i64, _p, _p, _p]),
+    'hn_lpips_head_bwd': (_int, [_int, _int, _int, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
 }
 
 

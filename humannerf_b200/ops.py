@@ -584,3 +584,52 @@ def tile_wgrad(jobs: Sequence[dict], n_samples: int) -> None:
     scratch = torch.empty(len(jobs) * C.sizeof(_lib.WgradJob), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev), _timed('tile_wgrad'):
         check(lib.hn_tile_wgrad(arr, len(jobs), n_samples, ptr(scratch), stream_ptr()), 'tile_wgrad')
+
+
+# ---------------------------------------------------------------------------
+# LPIPS head of one trunk stage (a16)
+# ---------------------------------------------------------------------------
+class _LpipsHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, lin, out):
+        lib = _lib.load()
+        n2, C, H, W = feat.shape
+        n = n2 // 2
+        sn, sc, sh, sw = feat.stride()
+        if sh != W * sw:                       # positions must be one strided axis (true for NCHW and NHWC)
+            feat = feat.contiguous()
+            sn, sc, sh, sw = feat.stride()
+        res = out.clone() if out is not None else torch.zeros(n, dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device), _timed('lpips_head_fwd'):
+            check(lib.hn_lpips_head_fwd(n, C, H * W, ptr_any(feat), sn, sc, sw, ptr(lin), ptr(res), stream_ptr()), 'lpips_head_fwd')
+        ctx.save_for_backward(feat, lin)
+        ctx.has_out = out is not None
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        feat, lin = ctx.saved_tensors
+        n2, C, H, W = feat.shape
+        sn, sc, sh, sw = feat.stride()
+        g = _f32c(g)
+        d_feat = torch.empty_like(feat)        # preserves the strides of feat
+        with torch.cuda.device(feat.device), _timed('lpips_head_bwd'):
+            check(lib.hn_lpips_head_bwd(n2 // 2, C, H * W, ptr_any(feat), sn, sc, sw, ptr(lin), ptr(g), ptr_any(d_feat),
+                                        stream_ptr()), 'lpips_head_bwd')
+        return d_feat, None, (g if ctx.has_out else None)
+
+
+def ptr_any(t: torch.Tensor) -> int:
+    """Device pointer of a dense CUDA fp32 tensor with arbitrary (non-overlapping) strides."""
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError('humannerf_b200: expected a CUDA fp32 tensor (there is no CPU path)')
+    return t.data_ptr()
+
+
+def lpips_head(feat: torch.Tensor, lin: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LPIPS head of one trunk stage (third_parties/lpips/lpips.py:10-15, 78-92): `feat` (2n, C, H, W) holds the
+    features of n predictions followed by their n targets; returns `out` (n,) + the stage's spatially averaged,
+    `lin`-weighted squared difference of the unit-normalised features (`out` None: starts from zero)."""
+    return _LpipsHead.apply(feat.float(), _f32c(lin).reshape(-1), out)
+

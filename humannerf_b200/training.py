@@ -59,7 +59,14 @@ class PerceptualLoss(nn.Module):
         n = x.shape[0]
         f = (torch.cat([x, y], 0) - self.shift) / self.scale
         total = 0.0
-        for stage, lin in zip(self.stages, self.lins):
+        if f.is_cuda:
+            # normalise -> squared difference -> lin -> spatial mean: one kernel per stage (hn_lpips_head_fwd / _bwd)
+            acc = None
+            for stage, lin in zip(self.stages, self.lins):
+                f = stage(f)
+                acc = ops.lpips_head(f, lin.weight, acc)
+            return acc.view(n, 1, 1, 1)
+        for stage, lin in zip(self.stages, self.lins):       # CPU tensors: host-logic tests and the oracle arm
             f = stage(f)
             nf = f / (torch.sqrt(torch.sum(f ** 2, dim=1, keepdim=True)) + 1e-10)
             total = total + lin((nf[:n] - nf[n:]) ** 2).mean([2, 3], keepdim=True)

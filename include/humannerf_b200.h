@@ -239,6 +239,21 @@ int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* 
                    float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a16  trainer.py:97-113 get_img_rebuild_loss -> third_parties/lpips/lpips.py:10-15, 78-92
+ * The LPIPS head of one trunk stage, fused: unit-normalise the channel vector of every position
+ * (x / (||x|| + 1e-10)), squared difference of prediction and target, non-negative 1x1 `lin` weights (C),
+ * spatial mean.  feat: (2 * n_pairs, C, positions) features of one trunk stage with element strides
+ * (stride_n, stride_c, stride_p) - prediction images first, then their targets.
+ *   out[i] += lpips_stage(feat[i], feat[n_pairs + i])           (accumulates: one call per stage)
+ * Backward: d_feat (same strides as feat, both halves) = d_out[i] * d out[i] / d feat.
+ */
+int hn_lpips_head_fwd(int n_pairs, int channels, int positions, const float* feat, int64_t stride_n,
+                      int64_t stride_c, int64_t stride_p, const float* lin, float* out, void* stream);
+int hn_lpips_head_bwd(int n_pairs, int channels, int positions, const float* feat, int64_t stride_n,
+                      int64_t stride_c, int64_t stride_p, const float* lin, const float* d_out,
+                      float* d_feat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * T16 tile images (bf16) and tensor-core weight gradients
  *
  * The tcgen05 kernels keep activations H and pre-activation gradients dZ in HBM as "T16 tile

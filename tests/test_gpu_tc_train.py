@@ -406,6 +406,33 @@ def test_other_forward_kernels_parity(variant):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize('shape,channels_last', [((12, 64, 32, 32), False), ((12, 512, 2, 2), True), ((4, 100, 5, 3), True)])
+def test_lpips_head_matches_torch(ops, shape, channels_last):
+    """hn_lpips_head_fwd / _bwd (one kernel per trunk stage) against the reference's expression
+    (third_parties/lpips/lpips.py:10-15, 78-92: normalize_tensor, squared difference, 1x1 lin, spatial_average) and its
+    autograd, for NCHW and NHWC feature strides, accumulating into a previous stage's result."""
+    gen = torch.Generator().manual_seed(sum(shape))
+    f0 = torch.relu(torch.randn(*shape, generator=gen)).to(DEV)
+    if channels_last:
+        f0 = f0.contiguous(memory_format=torch.channels_last)
+    lin = (torch.rand(1, shape[1], 1, 1, generator=gen) * 2.0 / shape[1]).to(DEV)
+    prev0 = torch.rand(shape[0] // 2, generator=gen).to(DEV)
+    gout = torch.randn(shape[0] // 2, generator=gen).to(DEV)
+    n = shape[0] // 2
+    fa, pa = f0.clone().requires_grad_(), prev0.clone().requires_grad_()
+    got = ops.lpips_head(fa, lin, pa)
+    (got * gout).sum().backward()
+    fb, pb = f0.clone().double().requires_grad_(), prev0.clone().double().requires_grad_()
+    nf = fb / (torch.sqrt(torch.sum(fb ** 2, dim=1, keepdim=True)) + 1e-10)
+    want = pb + torch.nn.functional.conv2d((nf[:n] - nf[n:]) ** 2, lin.double()).mean([2, 3]).view(n)
+    (want * gout.double()).sum().backward()
+    assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-7
+    err = float((fa.grad.double() - fb.grad).abs().max()) / (float(fb.grad.abs().max()) + 1e-30)
+    print(f'[parity] lpips head {shape}: value err {float((got.double() - want).abs().max()):.2e}, grad max-norm rel err {err:.2e}')
+    assert err <= 2e-5, err
+    assert float((pa.grad.double() - pb.grad).abs().max()) <= 1e-6
+
+
 def test_training_with_empty_space_skipping(ops):
     """cfg.b200.cull_in_training: samples with foreground likelihood < eps = 1e-7 skip the MLPs inside a
     training step (device-side compaction, sample count read from device memory by the tcgen05 kernels).
