@@ -173,6 +173,9 @@ _DEFAULTS: Dict[str, Any] = {
         'fused_front_end': True,
         # one-launch multi-tensor Adam (csrc/adam.cu) instead of torch.optim.Adam's per-group kernels
         'fused_adam': True,
+        # TF32 in the cuDNN transposed convolutions of the motion-weight volume decoder: 'auto' = on with the bf16
+        # MLP path (2e-2 parity bound), off with the fp32 path (TF32 moves the blend weights by 1e-4); True / False
+        'decoder_tf32': 'auto',
     },
 }
 

@@ -225,7 +225,8 @@ class Network(nn.Module):
         precision = _lib.PRECISION_BF16 if str(b200.get('mlp_precision', 'fp32')).lower() == 'bf16' \
             else _lib.PRECISION_FP32
         if hasattr(self.mweight_vol_decoder, 'allow_tf32'):
-            self.mweight_vol_decoder.allow_tf32 = precision == _lib.PRECISION_BF16
+            tf32 = b200.get('decoder_tf32', 'auto')
+            self.mweight_vol_decoder.allow_tf32 = (precision == _lib.PRECISION_BF16) if tf32 == 'auto' else bool(tf32)
         if fused_front:
             # Rodrigues + corrected rotations + the forward-kinematics chain in one launch (csrc/pose_fk.cu);
             # the LU inverse (the reference's torch.inverse without its host-side check) and the product

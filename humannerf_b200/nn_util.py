@@ -82,7 +82,14 @@ class ConvDecoder3D(nn.Module):
         self.block_conv.to(memory_format=torch.channels_last_3d)
 
     def forward(self, embedding):
-        return self.block_conv(self.block_mlp(embedding).view(-1, 1024, 1, 1, 1))
+        h = self.block_mlp(embedding)                         # (B, 1024): a 1 x 1 x 1 volume
+        # First transposed convolution (k4, s2, p1) on a 1^3 input: output voxel o takes tap k = o + 1, so only the
+        # central 2^3 of the 4^3 taps are ever used - a (B, 1024) x (1024, 512 * 8) product.  cuDNN would transpose
+        # and stream all 33.5 M weights three times per training step; the other taps get exactly zero gradient.
+        conv0 = self.block_conv[0]
+        assert conv0.kernel_size == (4, 4, 4) and conv0.stride == (2, 2, 2) and conv0.padding == (1, 1, 1)
+        x = torch.einsum('bc,cozyx->bozyx', h, conv0.weight[:, :, 1:3, 1:3, 1:3]) + conv0.bias.view(1, -1, 1, 1, 1)
+        return self.block_conv[1:](x)
 
 
 class RodriguesModule(nn.Module):

@@ -204,6 +204,10 @@ def test_network_train_bf16(ops, monkeypatch):
     T = lambda a: Tc(a).to(DEV)
     cfg = make_cfg()
     cfg.b200.mlp_precision = 'bf16'
+    # the checker emulates the rounding points of the MLP kernels only: the volume decoder runs in fp32 here (its
+    # TF32 mode moves the blend weights by 1e-4, which the 2^9 encoding frequency turns into extra ReLU-mask flips;
+    # the default TF32 decoder is covered by the forward bound of test_network_eval_bf16 and the graphed-step tests)
+    cfg.b200.decoder_tf32 = False
     cfg.perturb = 1.0
     sd = syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True)
     net = Network()
