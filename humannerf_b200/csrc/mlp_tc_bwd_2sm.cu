@@ -179,9 +179,24 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
         if (have_img) store_blocks(bufs.dz[mlp][out_layer], tile_idx, 16, a_h, quarter, lane, half, 2);
       }
 
+      // The stored activations that mask the accumulators come from HBM (~1 us): the two 16-row groups of this
+      // warp's rows of the NEXT masking round are pulled into L2 one round ahead (one 8 KB bulk prefetch per group)
+      auto prefetch_mask_rows = [&](int r_from) {
+        if (!have_img || half != 0 || lane >= 2) return;
+        for (int rr = r_from; rr < r_last; ++rr) {
+          const BwdRound nx = hdr->rounds[rr];
+          if (nx.epi != 0) continue;
+          const int F = nx.n;
+          bulk_prefetch_l2(bufs.h[mlp][nx.layer] + (size_t)tile_idx * 128 * F * 2 + (size_t)(2 * quarter + lane) * F * 32,
+                           (uint32_t)F * 32u);
+          return;
+        }
+      };
+      prefetch_mask_rows(r_first);
       for (int r = r_first; r < r_last; ++r) {
         const BwdRound rd = hdr->rounds[r];
         const bool last = r == r_last - 1;
+        if (rd.epi == 0) prefetch_mask_rows(r + 1);
         if (rd.epi == 0) {
           const int n_full = rd.n, n_half = n_full >> 1, c_begin = half * n_half;
           const size_t row_off = image_row_offset(tile_idx, row, n_full);
