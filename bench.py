@@ -182,15 +182,17 @@ def reference_arm(args):
 
 
 def workload_config(n_gpus):
-    return {'workload': 'ZJU-387 adventure.yaml train step: 6 patches x 32x32 rays x 128 samples per GPU per step '
+    return {'workload': f'ZJU-387 adventure.yaml train step: 6 patches x {PATCH}x{PATCH} rays x 128 samples per GPU per step '
                         '(fwd + 0.2 MSE + 1.0 LPIPS(VGG16, seeded random weights) + bwd + Adam), synthetic 512x512 frame, '
                         'fixture weights; render leg = one 512x512 frame (all bbox rays), bf16 tcgen05 MLP path',
             'rays_per_step_per_gpu': N_PATCHES * PATCH * PATCH, 'samples_per_ray': N_SAMPLES,
             'parallelism': f'dp{n_gpus} (rays/patches sharded, 1 bucketed cut-B gradient all-reduce per step)',
-            'l2_policy': 'inputs change every step (new patches); activations 9.5 GB/step exceed the 126 MB L2'}
+            'l2_policy': 'inputs change every step (new patches); activations '
+                         f'{N_PATCHES * PATCH * PATCH * N_SAMPLES * 12.1e3 / 1e9:.1f} GB/step exceed the 126 MB L2'}
 
 
 def main():
+    global PATCH
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -201,10 +203,15 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true')
     ap.add_argument('--no-skip-leg', action='store_true', help='skip the extra train leg with empty-space skipping')
+    ap.add_argument('--patch', type=int, default=PATCH,
+                    help='patch side of the train step: 32 = default.yaml / BASELINE.json cfg2 (default), 20 = what '
+                         'zju_mocap/387/single_gpu.yaml sets (SURVEY 8d asks for both; >= 16 for the LPIPS trunk)')
     ap.add_argument('--eager', action='store_true', help='run the train step eagerly instead of as one CUDA graph')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='MLP arithmetic of the train step: bf16 tcgen05 kernels (default) or the fp32 SIMT parity path')
     args = ap.parse_args()
+    assert args.patch >= 16, 'the LPIPS VGG16 trunk pools four times'
+    PATCH = args.patch
     if args.impl == 'reference':
         if args.steps > 6:
             args.steps = 6

@@ -513,6 +513,7 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     if (save_for_backward) {
       const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
       if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
+      if (!use_relu_bits()) memset(bufs.bits, 0, sizeof(bufs.bits));
     }
     return launch_field_tc2(plan, pk, n_samples, n_samples_dev, x_skel, hann_w, ignore_non_rigid ? 1 : 0, raw, xyz, offsets,
                             save_for_backward ? &bufs : nullptr, sms, ablate, as_stream(stream));

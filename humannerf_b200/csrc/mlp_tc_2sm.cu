@@ -313,11 +313,18 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           const int n_half = n_full >> 1;                          // columns owned by this thread
           const int c_begin = half * n_half;
           if (kStore) { bulk_wait_read0(); __syncwarp(); }     // the block's previous image copy has left shared memory
+          // training: this thread's record of the layer's 1-bit ReLU mask image (the backward chain masks with it)
+          uint8_t* bits_rec = nullptr;
+          if (kStore && store) {
+            uint8_t* b = is_nr ? bufs.bits[0][layer] : bufs.bits[1][layer - nr_layers];
+            if (b) bits_rec = b + relu_bits_offset(tile_idx, half, row, n_half);
+          }
           uint32_t v[2][32];
           tmem_ld32(t_acc + (uint32_t)c_begin, v[0]);
 #pragma unroll 1
           for (int c0 = 0; c0 < n_half; c0 += 64) {
             // two 32-column groups per iteration so that the register buffers are indexed statically
+            uint32_t m0 = 0u, m1 = 0u;
             tmem_ld_wait();
             if (c0 + 32 < n_half) tmem_ld32(t_acc + (uint32_t)(c_begin + c0 + 32), v[1]);
 #pragma unroll
@@ -329,6 +336,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
                                           pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
                                           pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
               st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
+              if (kStore) m0 = relu_bits_step(relu_bits_step(relu_bits_step(relu_bits_step(m0, pk.x), pk.y), pk.z), pk.w);
             }
             if (c0 + 32 < n_half) {
               tmem_ld_wait();
@@ -342,8 +350,10 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
                                             pack_relu_bf16(__uint_as_float(u[4]), __uint_as_float(u[5])),
                                             pack_relu_bf16(__uint_as_float(u[6]), __uint_as_float(u[7])));
                 st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
+                if (kStore) m1 = relu_bits_step(relu_bits_step(relu_bits_step(relu_bits_step(m1, pk.x), pk.y), pk.z), pk.w);
               }
             }
+            if (kStore && bits_rec) *reinterpret_cast<uint2*>(bits_rec + (c0 >> 6) * 8) = make_uint2(m0, m1);
           }
           tc_fence_before();
           fence_proxy_async();

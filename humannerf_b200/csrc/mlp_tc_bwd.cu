@@ -345,6 +345,8 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   // default: the cta_group::2 chain kernel (mlp_tc_bwd_2sm.cu); HN_TC_KERNEL=pair / cluster: the tile-pair kernel above
   const bool two_sm = use_2sm_kernel();
   if (two_sm && sms < 2) return fail_arg("hn_field_bwd_bf16: the tcgen05 chain kernel needs a device with thread-block clusters");
+  // only the cta_group::2 forward writes the 1-bit ReLU mask images (and only unless HN_TC_RELU_BITS=0)
+  if (!two_sm || !use_relu_bits()) memset(bufs.bits, 0, sizeof(bufs.bits));
   if (two_sm) {
     HN_TRY(launch_field_tc2_bwd(plan, pk, n, n_samples_dev, 1, d_raw, 4, 4, bufs, xyz, nullptr, d_xyz_tot, 4, sms, st));
   } else {

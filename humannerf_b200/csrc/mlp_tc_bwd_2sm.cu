@@ -7,7 +7,10 @@
 //   * dZ of the previous layer is written in place as the next A operand; its T16 image for the weight-gradient
 //     kernel leaves shared memory as 256-byte bulk copies (one per lane, store_blocks) instead of a 16-byte store
 //     per thread and chunk;
-//   * the stored activations that mask the accumulator (ReLU') are still read per thread (16 bytes per chunk).
+//   * ReLU': kBits = true (default) masks the accumulator with the 1-bit mask image the forward kernel wrote
+//     (relu_bits_* in mlp_tc_plan.cuh): one 4..16-byte record per thread and round, fetched a round ahead, instead
+//     of re-reading the bf16 activations (16 bytes per thread and 8-column chunk, 4.4 GB per 786 k samples);
+//     kBits = false (HN_TC_RELU_BITS=0) keeps the activation read.
 // Autograd of reference mlp_offset.py:74-114 and mlp_rgb_sigma.py:132-206 on the bf16 path.
 #include "mlp_tc_plan.cuh"
 #include "mlp_tc_enc.cuh"
@@ -15,6 +18,7 @@
 
 namespace hn {
 
+template <bool kBits>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restrict__ packed, int64_t n_cap,
                      const int64_t* __restrict__ n_dev, int mlp, const float* __restrict__ d_out, int ld_out, int n_out,
@@ -192,12 +196,78 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
           return;
         }
       };
-      prefetch_mask_rows(r_first);
+      // kBits: this thread's record of a masking round's 1-bit ReLU mask image (one word per 32 columns).  It is
+      // pulled into L2 a round ahead (no registers held) and loaded before the wait for the round's accumulator.
+      uint32_t mb[4] = {0u, 0u, 0u, 0u};
+      auto bits_record = [&](int r_from) -> const uint32_t* {
+        if (!have_img) return nullptr;
+        for (int rr = r_from; rr < r_last; ++rr) {
+          const BwdRound nx = hdr->rounds[rr];
+          if (nx.epi != 0) continue;
+          return reinterpret_cast<const uint32_t*>(bufs.bits[mlp][nx.layer] + relu_bits_offset(tile_idx, half, row, nx.n >> 1));
+        }
+        return nullptr;
+      };
+      auto prefetch_bits = [&](int r_from) {
+        const uint32_t* rec = bits_record(r_from);
+        if (rec) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+      };
+      if (kBits) prefetch_bits(r_first);
+      else prefetch_mask_rows(r_first);
       for (int r = r_first; r < r_last; ++r) {
         const BwdRound rd = hdr->rounds[r];
         const bool last = r == r_last - 1;
-        if (rd.epi == 0) prefetch_mask_rows(r + 1);
-        if (rd.epi == 0) {
+        if (!kBits && rd.epi == 0) prefetch_mask_rows(r + 1);
+        if (kBits && rd.epi == 0) {
+          const int n_full = rd.n, n_half = n_full >> 1, c_begin = half * n_half;
+          {
+            const uint32_t* rec = bits_record(r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mb[i] = (rec && i * 32 < n_half) ? __ldg(rec + i) : 0u;
+          }
+          prefetch_bits(r + 1);
+          mbar_wait(bar_acc, acc_phase, 4);
+          acc_phase ^= 1;
+          tc_fence_after();
+          bulk_wait_read0();                                     // the block's previous image copy has left shared memory
+          __syncwarp();
+          uint32_t v[2][32];
+          tmem_ld32(t_acc + (uint32_t)c_begin, v[0]);
+#pragma unroll 1
+          for (int c0 = 0; c0 < n_half; c0 += 64) {
+            // two 32-column groups per iteration (static register indexing); mb[0] / mb[1] are their mask words
+            tmem_ld_wait();
+            if (c0 + 32 < n_half) tmem_ld32(t_acc + (uint32_t)(c_begin + c0 + 32), v[1]);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const uint32_t* u = v[0] + g8 * 8;
+              const int chunk = ((c_begin + c0) >> 3) + g8;
+              st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u,
+                           mask_pack_bits(mb[0], g8 * 4 + 0, u[0], u[1]), mask_pack_bits(mb[0], g8 * 4 + 1, u[2], u[3]),
+                           mask_pack_bits(mb[0], g8 * 4 + 2, u[4], u[5]), mask_pack_bits(mb[0], g8 * 4 + 3, u[6], u[7]));
+            }
+            if (c0 + 32 < n_half) {
+              tmem_ld_wait();
+              if (c0 + 64 < n_half) tmem_ld32(t_acc + (uint32_t)(c_begin + c0 + 64), v[0]);
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                const uint32_t* u = v[1] + g8 * 8;
+                const int chunk = ((c_begin + c0 + 32) >> 3) + g8;
+                st_shared_v4(a_h + (uint32_t)chunk * kLboA + (uint32_t)row * 16u,
+                             mask_pack_bits(mb[1], g8 * 4 + 0, u[0], u[1]), mask_pack_bits(mb[1], g8 * 4 + 1, u[2], u[3]),
+                             mask_pack_bits(mb[1], g8 * 4 + 2, u[4], u[5]), mask_pack_bits(mb[1], g8 * 4 + 3, u[6], u[7]));
+              }
+            }
+            mb[0] = mb[2]; mb[1] = mb[3];
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (!last && lane == 0) mbar_arrive_remote(bar_ready);
+          if (have_img)
+            store_blocks(bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane, half * (n_half >> 3) + (lane >> 1),
+                         2 * (n_half >> 3));
+        } else if (rd.epi == 0) {
           const int n_full = rd.n, n_half = n_full >> 1, c_begin = half * n_half;
           const size_t row_off = image_row_offset(tile_idx, row, n_full);
           const uint8_t* h_img = have_img ? bufs.h[mlp][rd.layer] + row_off : nullptr;
@@ -309,7 +379,9 @@ int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_sa
   using namespace s2;
   static int max_clusters_cached = 0;
   if (max_clusters_cached == 0) {
-    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+                      "hn_field_bwd_bf16/2sm smem attr"));
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
                       "hn_field_bwd_bf16/2sm smem attr"));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -322,7 +394,7 @@ int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_sa
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_bwd_kernel, &cfg), "hn_field_bwd_bf16/2sm occupancy"));
+    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_bwd_kernel<false>, &cfg), "hn_field_bwd_bf16/2sm occupancy"));
     if (n <= 0) return fail_arg("hn_field_bwd_bf16: no 2-CTA cluster of the tcgen05 kernel fits on this device");
     max_clusters_cached = n;
   }
@@ -334,8 +406,13 @@ int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_sa
   }
   const int64_t n_quads = ceil_div<int64_t>(n_samples, 2 * kSetRows);
   const unsigned grid = 2u * (unsigned)std::min<int64_t>(n_quads, (int64_t)max_clusters_cached);
-  field_tc2_bwd_kernel<<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, mlp, d_out, ld_out, n_out,
-                                                           bufs, pos, hann_w, d_pos, ld_dpos, tc2_stages());
+  // the 1-bit mask images exist when the cta_group::2 forward wrote them (hn_field_bwd_bf16 nulls the pointers otherwise)
+  if (bufs.bits[mlp][0])
+    field_tc2_bwd_kernel<true><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, mlp, d_out, ld_out,
+                                                                   n_out, bufs, pos, hann_w, d_pos, ld_dpos, tc2_stages());
+  else
+    field_tc2_bwd_kernel<false><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, mlp, d_out, ld_out,
+                                                                    n_out, bufs, pos, hann_w, d_pos, ld_dpos, tc2_stages());
   return launched(mlp == 1 ? "hn_field_bwd_bf16/canonical chain (2sm)" : "hn_field_bwd_bf16/non-rigid chain (2sm)");
 }
 

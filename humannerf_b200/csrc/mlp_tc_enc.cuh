@@ -72,4 +72,18 @@ __device__ __forceinline__ uint32_t mask_pack(uint32_t h2, uint32_t a_lo, uint32
   return pack_bf16(lo, hi);
 }
 
+
+// ReLU-mask words (relu_bits_* in mlp_tc_plan.cuh).  h2 = two non-negative bf16 (cvt.relu: sign bit clear), so
+// h + 0x7FFF carries into bit 15 exactly when h != 0 and never into the other half.  After the 16 words of a
+// 32-column group have been shifted in, word j sits at bit j (low half = even column) and bit 16 + j (odd column).
+__device__ __forceinline__ uint32_t relu_bits_step(uint32_t m, uint32_t h2) {
+  return (m >> 1) | ((h2 + 0x7FFF7FFFu) & 0x80008000u);
+}
+// acc masked by bits j / 16 + j of a mask word
+__device__ __forceinline__ uint32_t mask_pack_bits(uint32_t m, int j, uint32_t a_lo, uint32_t a_hi) {
+  const float lo = (m & (1u << j)) ? __uint_as_float(a_lo) : 0.0f;
+  const float hi = (m & (0x10000u << j)) ? __uint_as_float(a_hi) : 0.0f;
+  return pack_bf16(lo, hi);
+}
+
 }  // namespace hn

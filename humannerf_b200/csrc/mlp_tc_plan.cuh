@@ -73,8 +73,19 @@ struct TrainBufs {
   uint8_t* pe[2];                    // [mlp]            F = pe_pad
   uint8_t* h[2][HN_MAX_LAYERS];      // [mlp][layer]     F = width      (hidden layers)
   uint8_t* dz[2][HN_MAX_LAYERS];     // [mlp][layer]     F = width, 16 for the output layer
+  uint8_t* bits[2][HN_MAX_LAYERS];   // [mlp][layer]     ReLU masks of the hidden layers, 1 bit per unit (relu_bits_* below);
+                                     //                  null: the backward chain reads the mask from h instead
   int64_t n_tiles;                   // tiles that exist in the images
 };
+
+// ReLU-mask image of a hidden layer (cta_group::2 kernels).  The epilogue thread (row, half) of the forward kernel and
+// of the backward chain own the same n_half = F / 2 columns of a row; its record holds one 32-bit word per 32 columns:
+// bit j = column 2j of the group is active, bit 16 + j = column 2j + 1 (the order the packed bf16 pairs produce).
+// Records are [tile][half][row] so that a warp reads / writes contiguous memory: 1/16 of the bytes of the bf16 image.
+__host__ __device__ inline int relu_bits_record_bytes(int n_half) { return 8 * ((n_half + 63) / 64); }
+__host__ __device__ inline size_t relu_bits_offset(int64_t tile, int half, int row, int n_half) {
+  return (size_t)((tile * 2 + half) * 128 + row) * (size_t)relu_bits_record_bytes(n_half);
+}
 
 struct PackJob {            // one per chunk, consumed by pack_weights_kernel
   const float* src;         // weight matrix (rows = out features), nullptr = all zero
@@ -119,6 +130,16 @@ static inline int tc2_stages() {
   static const int v = [] {
     const char* e = getenv("HN_TC_2SM_STAGES");
     return (e != nullptr && atoi(e) == 8) ? 8 : 4;
+  }();
+  return v;
+}
+// cta_group::2 training kernels: the forward writes 1-bit ReLU masks next to the bf16 activation images and the
+// backward chain masks with them instead of re-reading the activations (16 x fewer bytes on that read);
+// HN_TC_RELU_BITS=0 keeps the activation read (measurement aid / A-B switch)
+static inline bool use_relu_bits() {
+  static const bool v = [] {
+    const char* e = getenv("HN_TC_RELU_BITS");
+    return e == nullptr || atoi(e) != 0;
   }();
   return v;
 }
@@ -312,6 +333,10 @@ inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* 
       b.dz[m][l] = take(n_tiles * 128 * (outl ? 16 : plan.width[m]) * 2);
     }
   }
+  // after everything else: the offsets of the images above do not depend on the mask images
+  for (int m = 0; m < 2; ++m)
+    for (int l = 0; l + 1 < plan.layers[m]; ++l)
+      b.bits[m][l] = take(n_tiles * 2 * 128 * relu_bits_record_bytes(plan.width[m] / 2));
   if (out) *out = b;
   return off;
 }

@@ -188,7 +188,8 @@ int hn_field_bwd(const hn_field_params* p, const hn_field_grads* g, int64_t n_sa
                  void* scratch, int64_t scratch_bytes, void* stream);
 
 /* Backward on the tensor cores (HN_PRECISION_BF16).  `workspace` is the one hn_field_fwd filled with
- * save_for_backward != 0 and precision BF16 (T16 images of every activation), `packed` the image the
+ * save_for_backward != 0 and precision BF16 (T16 images of every activation plus, from the cta_group::2
+ * forward kernel, a 1-bit ReLU mask image per hidden layer that the chains mask with), `packed` the image the
  * forward used, `xyz` the forward's xyz output.  Runs the fused backward-data chains (tcgen05), the
  * encoding backward, and hn_tile_wgrad jobs for every weight / bias; accumulates into `g`. */
 int64_t hn_field_bwd_bf16_scratch_bytes(const hn_field_params* p, int64_t n_samples);

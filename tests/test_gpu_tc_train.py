@@ -388,7 +388,38 @@ def test_graphed_train_step_matches_eager(ops, precision):
     print(f'[parity] graphed step ({precision}): max parameter difference after 3 steps {worst:.3e}')
 
 
-@pytest.mark.parametrize('variant', ['pair', 'cluster', '2sm-8-stages'])
+@pytest.mark.parametrize('P,ignore', [(128 * 9 + 77, 0), (2048, 1)])
+def test_relu_mask_images_match_activation_read(tmp_path, P, ignore):
+    """The cta_group::2 forward writes 1-bit ReLU mask images (relu_bits_* in csrc/mlp_tc_plan.cuh) and the backward
+    chain masks with them; HN_TC_RELU_BITS=0 makes the chain read the stored bf16 activations instead (what it did
+    before).  Both must give the same pre-activation gradients, hence the same parameter and position gradients up to
+    the summation order of the fp32 atomics (1e-5 relative L2; one wrong mask bit moves a tensor by >= 1e-3).
+    The switch is read once per process, so the activation-read arm runs in a subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'tests'))
+    import relu_bits_ab as ab
+    assert os.environ.get('HN_TC_RELU_BITS', '1') != '0' and os.environ.get('HN_TC_KERNEL', '') in ('', '2sm')
+    got = ab.field_grads(P, ignore)
+    out = str(tmp_path / 'read_h.npz')
+    env = dict(os.environ, HN_TC_RELU_BITS='0')
+    r = subprocess.run([sys.executable, os.path.join(root, 'tests', 'relu_bits_ab.py'), str(P), str(ignore), out],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = np.load(out)
+    assert set(want.files) == set(got)
+    assert np.array_equal(got['raw'], want['raw'])
+    worst = 0.0
+    for k in want.files:
+        a, b = got[k].astype(np.float64), want[k].astype(np.float64)
+        rel = float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+        worst = max(worst, rel)
+        assert rel < 1e-5, (k, rel)
+    assert any(float(np.abs(want[k]).max()) > 0 for k in want.files if k != 'raw')
+    print(f'[parity] ReLU mask images vs activation read [P={P},ignore={ignore}]: worst rel L2 over {len(want.files)} tensors {worst:.2e}')
+
+
+@pytest.mark.parametrize('variant', ['pair', 'cluster', '2sm-8-stages', 'read-activations'])
 def test_other_forward_kernels_parity(variant):
     """The default tcgen05 forward kernel is the cta_group::2 kernel of csrc/mlp_tc_2sm.cu with a 4 x 16 KB ring.
     The other forward kernels must pass the same forward parity and training tests: HN_TC_KERNEL=pair (csrc/mlp_tc.cu,
@@ -401,6 +432,8 @@ def test_other_forward_kernels_parity(variant):
     env = dict(os.environ)
     if variant == '2sm-8-stages':
         env['HN_TC_2SM_STAGES'] = '8'
+    elif variant == 'read-activations':
+        env['HN_TC_RELU_BITS'] = '0'      # backward chain masks with the stored activations instead of the 1-bit images
     else:
         env['HN_TC_KERNEL'] = variant
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', '-k',
