@@ -40,6 +40,8 @@ MF_BYTES_NOW = 28.0            # ... when the weights output is omitted
 MF_ONCE = 3146880.0
 H = W = 512
 N_PATCHES, PATCH, N_SAMPLES = 6, 32, 128
+# DRAM bytes (ncu, read + write) of the bf16 field kernels for one 786 432-sample step; scales with the samples
+FIELD_TRAFFIC = 19.46e9 if os.environ.get('HN_TC_RELU_BITS', '1') != '0' else 23.38e9
 
 
 def load_peaks():
@@ -466,15 +468,16 @@ def main():
                 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peaks['tf_sustained'],
                 # dram__bytes_read + write of the four launches of one 6144-ray step, ncu --set full
-                # (profiles/r01e_ncu_full_summary.json): 4.79 + 6.52 + 2.45 + 9.62 GB
-                'traffic': 23.38e9 if args.precision == 'bf16' else None,
+                # (profiles/r01g_ncu_full_summary.json): 5.06 (forward) + 3.48 + 1.29 (chains) + 9.62 (wgrad) GB;
+                # with HN_TC_RELU_BITS=0 the chains read the activations again: 23.38 GB (r01e)
+                'traffic': (FIELD_TRAFFIC * N_PATCHES * PATCH * PATCH * N_SAMPLES / 786432) if args.precision == 'bf16' else None,
                 'peak_source': peaks['source'] + ' (sustained bf16)',
                 'share_of_step': (fld_ms / roof_steps) / max(ms / args.steps, 1e-9),
                 'timed': 'per-op CUDA events' + (' in an eager re-run of the same steps (the timed region replays a CUDA graph)'
                                                  if graphed is not None else ' inside the timed region')}
     if args.precision == 'bf16' and fld_ms > 0:
         # the same kernel group seen from the memory side: the stored-activation design moves 32 KB / sample
-        gbs = 23.38e9 * (samples_local / roof_steps / (N_PATCHES * PATCH * PATCH * N_SAMPLES)) / (fld_ms / roof_steps * 1e-3) / 1e9
+        gbs = FIELD_TRAFFIC * (samples_local / roof_steps / 786432) / (fld_ms / roof_steps * 1e-3) / 1e9
         roofline['hbm_view'] = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                 'frac': gbs / peaks['hbm_gbs'], 'note': 'measured DRAM traffic (ncu) / measured time'}
     op_table = {k: {'ms_total': round(v[0], 3), 'calls': v[1]} for k, v in sorted(op_ms.items())}
