@@ -284,7 +284,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_ready);
-        if (store) store_blocks(bufs.pe[0], tile_idx, nr_pad, a_pe, quarter, lane, (lane >> 1) * 2 + half, 2 * (nr_pad >> 4));
+        if (store) store_blocks(bufs.leader_stores != 0, bufs.pe[0], tile_idx, nr_pad, a_pe, quarter, lane, half, 2, nr_pad >> 4);
       }
 
       for (int layer = first_layer; layer < n_layers; ++layer) {
@@ -296,7 +296,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(bar_ready);
-          if (store) store_blocks(bufs.pe[1], tile_idx, cn_pad, a_pe, quarter, lane, (lane >> 1) * 2 + half, 2 * (cn_pad >> 4));
+          if (store) store_blocks(bufs.leader_stores != 0, bufs.pe[1], tile_idx, cn_pad, a_pe, quarter, lane, half, 2, cn_pad >> 4);
         }
         mbar_wait(bar_acc, acc_phase, 4);
         acc_phase ^= 1;
@@ -361,8 +361,8 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           if (lane == 0) mbar_arrive_remote(bar_ready);
           if (trace) g_tc2_trace[2 + tile][layer][1] = clock64();
           if (store)
-            store_blocks(is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers], tile_idx, n_full, a_h, quarter, lane,
-                         half * (n_half >> 3) + (lane >> 1), 2 * (n_half >> 3));
+            store_blocks(bufs.leader_stores != 0, is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers], tile_idx, n_full, a_h,
+                         quarter, lane, half * (n_half >> 3), 1, n_half >> 3);
         } else {
           uint32_t v[16];
           tmem_ld16(t_acc, v);

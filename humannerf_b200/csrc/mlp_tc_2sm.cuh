@@ -71,18 +71,35 @@ __device__ __forceinline__ uint32_t elect_one() {
 }
 
 // Training: the operand block a warp has just written IS the T16 image of its rows (16 rows x 8 columns = 256
-// contiguous bytes in both).  A warp owns 2 sixteen-row groups x `n_blocks / 2` column chunks; lane l copies block
-// (group 2 * quarter + (l & 1), chunk `chunk`) with one shared -> global bulk copy (TMA) instead of every thread
-// storing 16 bytes per chunk.  Callers: fence.proxy.async by every writer and __syncwarp() first; the source is
-// reused only after cp.async.bulk.wait_group.read (bulk_wait_read0) by every lane and another __syncwarp().
-__device__ __forceinline__ void store_blocks(uint8_t* image, int64_t tile_idx, int F, uint32_t s_block, int quarter, int lane,
-                                             int chunk, int n_blocks) {
-  if (lane < n_blocks) {
-    const int g = 2 * quarter + (lane & 1);
-    bulk_s2g(image + (size_t)tile_idx * 128 * F * 2 + (size_t)g * F * 32 + (size_t)chunk * 256,
-             s_block + (uint32_t)chunk * kLboA + (uint32_t)g * 256u, 256u);
+// contiguous bytes in both).  A warp owns 2 sixteen-row groups (2 * quarter, 2 * quarter + 1) x `n_chunks` column
+// chunks chunk0, chunk0 + stride, ...; every block leaves with one 256-byte shared -> global bulk copy (TMA).
+//   leader = true:  one elected lane (elect.sync picks the same lane every time) issues all of them in a loop over
+//                   uniform addresses and owns the bulk async-group;
+//   leader = false: lane l copies block (group l & 1, chunk number l >> 1) - per-lane addresses, which ptxas wraps in a
+//                   9-instruction R2UR waterfall iteration per lane.
+// Callers: fence.proxy.async by every writer and __syncwarp() first; the source is reused only after
+// cp.async.bulk.wait_group.read (bulk_wait_read0) by every lane and another __syncwarp().
+__device__ __forceinline__ void store_blocks(bool leader, uint8_t* image, int64_t tile_idx, int F, uint32_t s_block, int quarter,
+                                             int lane, int chunk0, int stride, int n_chunks) {
+  uint8_t* g0 = image + (size_t)tile_idx * 128 * F * 2 + (size_t)(2 * quarter) * F * 32;
+  const uint32_t s0 = s_block + (uint32_t)(2 * quarter) * 256u;
+  if (leader) {
+    if (elect_one()) {
+      for (int i = 0; i < n_chunks; ++i) {
+        const int chunk = chunk0 + i * stride;
+        bulk_s2g(g0 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA, 256u);
+        bulk_s2g(g0 + (size_t)F * 32 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA + 256u, 256u);
+      }
+      bulk_commit();
+    }
+    __syncwarp();
+  } else {
+    if (lane < 2 * n_chunks) {
+      const int chunk = chunk0 + (lane >> 1) * stride, g = lane & 1;
+      bulk_s2g(g0 + (size_t)g * F * 32 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA + (uint32_t)g * 256u, 256u);
+    }
+    bulk_commit();
   }
-  bulk_commit();
 }
 
 }  // namespace hn

@@ -180,7 +180,7 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_ready);
-        if (have_img) store_blocks(bufs.dz[mlp][out_layer], tile_idx, 16, a_h, quarter, lane, half, 2);
+        if (have_img) store_blocks(bufs.leader_stores != 0, bufs.dz[mlp][out_layer], tile_idx, 16, a_h, quarter, lane, half, 1, 1);
       }
 
       // The stored activations that mask the accumulators come from HBM (~1 us): the two 16-row groups of this
@@ -265,8 +265,8 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
           __syncwarp();
           if (!last && lane == 0) mbar_arrive_remote(bar_ready);
           if (have_img)
-            store_blocks(bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane, half * (n_half >> 3) + (lane >> 1),
-                         2 * (n_half >> 3));
+            store_blocks(bufs.leader_stores != 0, bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane,
+                         half * (n_half >> 3), 1, n_half >> 3);
         } else if (rd.epi == 0) {
           const int n_full = rd.n, n_half = n_full >> 1, c_begin = half * n_half;
           const size_t row_off = image_row_offset(tile_idx, row, n_full);
@@ -308,8 +308,8 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
           __syncwarp();
           if (!last && lane == 0) mbar_arrive_remote(bar_ready);
           if (have_img)
-            store_blocks(bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane, half * (n_half >> 3) + (lane >> 1),
-                         2 * (n_half >> 3));
+            store_blocks(bufs.leader_stores != 0, bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane,
+                         half * (n_half >> 3), 1, n_half >> 3);
         } else {
           // gradient of the encoding block, contracted with the encoding's derivative:
           //   d_pos[a] += [raw x] g[a] + sum_k w_k 2^k (cos(2^k x_a) g_sin(k,a) - sin(2^k x_a) g_cos(k,a))

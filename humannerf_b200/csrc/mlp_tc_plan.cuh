@@ -76,6 +76,8 @@ struct TrainBufs {
   uint8_t* bits[2][HN_MAX_LAYERS];   // [mlp][layer]     ReLU masks of the hidden layers, 1 bit per unit (relu_bits_* below);
                                      //                  null: the backward chain reads the mask from h instead
   int64_t n_tiles;                   // tiles that exist in the images
+  int32_t leader_stores;             // cta_group::2 kernels: 1 = one elected lane per warp issues the warp's image copies
+  int32_t reserved;
 };
 
 // ReLU-mask image of a hidden layer (cta_group::2 kernels).  The epilogue thread (row, half) of the forward kernel and
@@ -139,6 +141,16 @@ static inline int tc2_stages() {
 static inline bool use_relu_bits() {
   static const bool v = [] {
     const char* e = getenv("HN_TC_RELU_BITS");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return v;
+}
+// cta_group::2 training kernels: the 256-byte shared -> global bulk copies of a warp's image blocks are issued by ONE
+// elected lane in a loop over uniform addresses (default) instead of one copy per lane - per-lane addresses make
+// ptxas wrap every UBLKCP in a 9-instruction R2UR waterfall iteration.  HN_TC_LEADER_STORES=0: one copy per lane.
+static inline bool use_leader_stores() {
+  static const bool v = [] {
+    const char* e = getenv("HN_TC_LEADER_STORES");
     return e == nullptr || atoi(e) != 0;
   }();
   return v;
@@ -325,6 +337,7 @@ inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* 
   TrainBufs b;
   memset(&b, 0, sizeof(b));
   b.n_tiles = n_tiles;
+  b.leader_stores = use_leader_stores() ? 1 : 0;
   for (int m = 0; m < 2; ++m) {
     b.pe[m] = take(n_tiles * 128 * plan.pe_pad[m] * 2);
     for (int l = 0; l < plan.layers[m]; ++l) {

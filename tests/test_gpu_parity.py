@@ -639,7 +639,8 @@ def test_full_size_properties(ops, sd, frame):
     assert o.shape[0] > 150000                      # ~196k valid rays with this camera
     assert bool((idx[1:] > idx[:-1]).all())         # pixel order kept
     o, d, nr, fr_ = o[:R].contiguous(), d[:R].contiguous(), nr[:R], fr_[:R]
-    z = ops.sample_z(nr, fr_, S, torch.rand(R, S, device=DEV))
+    # seeded jitter: the bf16-vs-fp32 maximum over 32768 rays below varies between 1.5e-2 and 2.0e-2 from draw to draw
+    z = ops.sample_z(nr, fr_, S, torch.rand(R, S, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0)))
     assert bool((z[:, 1:] >= z[:, :-1]).all()) and bool((z[:, :1] >= nr).all()) and bool((z[:, -1:] <= fr_).all())
     net, cfg = _network(sd, mlp_precision='fp32')
     fr = {k: T(v, DEV) for k, v in frame.items()}
