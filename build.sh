@@ -6,7 +6,7 @@ SRC=humannerf_b200/csrc
 OUT=humannerf_b200/lib
 mkdir -p "$OUT" build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v"
+FLAGS="${HN_EXTRA_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v"
 # HN_TC_PROFILE=1 ./build.sh compiles the per-role cycle counters into the tcgen05 forward kernel (measurement builds only)
 if [ "${HN_TC_PROFILE:-0}" = "1" ]; then FLAGS="$FLAGS -DHN_TC_PROFILE"; fi
 objs=()

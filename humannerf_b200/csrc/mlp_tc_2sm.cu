@@ -43,12 +43,13 @@ namespace hn {
 __device__ long long g_tc2_trace[4][32][4];   // issuers: [2] cycles waiting for weights, [3] cycles issuing MMAs + commits
 constexpr int kTraceQuad = 6;      // which pass of cluster 0 is recorded
 
-template <bool kStore>
+// kStore: training (activation / mask images are written); kSt: image store mode of store_blocks (1 or 4)
+template <bool kStore, int kSt>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
                  const float* __restrict__ x_skel, const float* __restrict__ hann_w, int ignore_non_rigid,
                  float* __restrict__ raw, float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs,
-                 int ablate, int n_stages) {
+                 const __grid_constant__ ImageMaps maps, int ablate, int n_stages) {
   using namespace s2;
   const uint32_t stage_bytes = kRingBytes2 / (uint32_t)n_stages;
   // n_dev (nullable): the number of samples actually present, read from device memory (empty-space skipping
@@ -246,6 +247,8 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
     const uint32_t bar_ready = mapa_cluster(s_a_ready + (uint32_t)tile * 8, 0);      // in the leader
     const uint32_t bar_acc = s_acc_full + (uint32_t)tile * 8;
     uint32_t acc_phase = 0;
+    constexpr int st_mode = kSt;                                     // image store mode (store_blocks)
+    const uint32_t st_bar = 1u + (uint32_t)(tile * 2 + half);        // named barrier of this (tile, column half)
     float hw[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) hw[k] = (k < (int)hdr->nr_freqs && hann_w) ? __ldg(hann_w + k) : 0.0f;
@@ -279,25 +282,28 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
       }
 
       if (!ignore_non_rigid) {
-        if (kStore) { bulk_wait_read0(); __syncwarp(); }       // the block's previous image copy has left shared memory
+        if (kStore) block_reusable(st_mode, st_bar);           // the block's previous image copy has left shared memory
         write_encoding<false>(a_pe, row, half, x, nr_freqs, hw, nr_pad, nullptr);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_ready);
-        if (store) store_blocks(bufs.leader_stores != 0, bufs.pe[0], tile_idx, nr_pad, a_pe, quarter, lane, half, 2, nr_pad >> 4);
+        if (store) store_blocks(st_mode, &maps.m[2], -1, st_bar, bufs.pe[0], tile_idx, nr_pad, a_pe, quarter, lane, half, 2, nr_pad >> 4);
       }
 
       for (int layer = first_layer; layer < n_layers; ++layer) {
         const bool is_nr = layer < nr_layers;
         const bool is_out = (layer == nr_layers - 1) || (layer == n_layers - 1);
         if (layer == nr_layers) {
-          if (kStore) { bulk_wait_read0(); __syncwarp(); }
+          if (kStore) block_reusable(st_mode, st_bar);
           write_encoding<true>(a_pe, row, half, q, cn_freqs, nullptr, cn_pad, nullptr);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(bar_ready);
-          if (store) store_blocks(bufs.leader_stores != 0, bufs.pe[1], tile_idx, cn_pad, a_pe, quarter, lane, half, 2, cn_pad >> 4);
+          if (store) store_blocks(st_mode, &maps.m[3], -1, st_bar, bufs.pe[1], tile_idx, cn_pad, a_pe, quarter, lane, half, 2, cn_pad >> 4);
         }
+        // training: the image copies of the block this layer overwrites have left shared memory - checked (and, with
+        // tensor-map stores, agreed among the four warps) while the layer's MMAs run, not after them
+        if (kStore && !is_out && !(ablate & 1)) block_reusable(st_mode, st_bar);
         mbar_wait(bar_acc, acc_phase, 4);
         acc_phase ^= 1;
         tc_fence_after();
@@ -312,7 +318,6 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           const int n_full = (int)hdr->layer_n[layer];
           const int n_half = n_full >> 1;                          // columns owned by this thread
           const int c_begin = half * n_half;
-          if (kStore) { bulk_wait_read0(); __syncwarp(); }     // the block's previous image copy has left shared memory
           // training: this thread's record of the layer's 1-bit ReLU mask image (the backward chain masks with it)
           uint8_t* bits_rec = nullptr;
           if (kStore && store) {
@@ -361,8 +366,9 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           if (lane == 0) mbar_arrive_remote(bar_ready);
           if (trace) g_tc2_trace[2 + tile][layer][1] = clock64();
           if (store)
-            store_blocks(bufs.leader_stores != 0, is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers], tile_idx, n_full, a_h,
-                         quarter, lane, half * (n_half >> 3), 1, n_half >> 3);
+            store_blocks(st_mode, &maps.m[is_nr ? 0 : 1], 2 * (is_nr ? layer : layer - nr_layers), st_bar,
+                         is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers], tile_idx, n_full, a_h, quarter, lane,
+                         half * (n_half >> 3), 1, n_half >> 3);
         } else {
           uint32_t v[16];
           tmem_ld16(t_acc, v);
@@ -408,9 +414,11 @@ int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_sample
   using namespace s2;
   static int max_clusters_cached = 0;
   if (max_clusters_cached == 0) {
-    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
                       "hn_field_fwd/2sm smem attr"));
-    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+                      "hn_field_fwd/2sm smem attr"));
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
                       "hn_field_fwd/2sm smem attr"));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -423,7 +431,7 @@ int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_sample
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_kernel<false>, &cfg), "hn_field_fwd/2sm occupancy"));
+    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_kernel<false, 1>, &cfg), "hn_field_fwd/2sm occupancy"));
     if (n <= 0) return fail_arg("hn_field_fwd: no 2-CTA cluster of the tcgen05 kernel fits on this device");
     max_clusters_cached = n;
     if (getenv("HN_DEBUG")) fprintf(stderr, "humannerf_b200: %d co-resident 2-CTA clusters (%d SMs)\n", n, sms);
@@ -436,14 +444,23 @@ int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_sample
   }
   const int64_t n_quads = ceil_div<int64_t>(n_samples, 2 * kSetRows);
   const unsigned grid = 2u * (unsigned)std::min<int64_t>(n_quads, (int64_t)max_clusters_cached);
-  if (bufs) {
-    field_tc2_kernel<true><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
-                                                               ignore_non_rigid, raw, xyz, offsets, *bufs, ablate, tc2_stages());
+  ImageMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (bufs && bufs->leader_stores == 4) {
+    HN_TRY(make_image_maps(plan, *bufs, &maps));
+    field_tc2_kernel<true, 4><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
+                                                                  ignore_non_rigid, raw, xyz, offsets, *bufs, maps, ablate,
+                                                                  tc2_stages());
+  } else if (bufs) {
+    field_tc2_kernel<true, 1><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
+                                                                  ignore_non_rigid, raw, xyz, offsets, *bufs, maps, ablate,
+                                                                  tc2_stages());
   } else {
     TrainBufs none;
     memset(&none, 0, sizeof(none));
-    field_tc2_kernel<false><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
-                                                                ignore_non_rigid, raw, xyz, offsets, none, ablate, tc2_stages());
+    field_tc2_kernel<false, 1><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
+                                                                   ignore_non_rigid, raw, xyz, offsets, none, maps, ablate,
+                                                                   tc2_stages());
   }
   return launched("hn_field_fwd/tcgen05 2sm");
 }

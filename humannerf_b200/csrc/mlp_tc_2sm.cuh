@@ -72,34 +72,52 @@ __device__ __forceinline__ uint32_t elect_one() {
 
 // Training: the operand block a warp has just written IS the T16 image of its rows (16 rows x 8 columns = 256
 // contiguous bytes in both).  A warp owns 2 sixteen-row groups (2 * quarter, 2 * quarter + 1) x `n_chunks` column
-// chunks chunk0, chunk0 + stride, ...; every block leaves with one 256-byte shared -> global bulk copy (TMA).
-//   leader = true:  one elected lane (elect.sync picks the same lane every time) issues all of them in a loop over
-//                   uniform addresses and owns the bulk async-group;
-//   leader = false: lane l copies block (group l & 1, chunk number l >> 1) - per-lane addresses, which ptxas wraps in a
-//                   9-instruction R2UR waterfall iteration per lane.
-// Callers: fence.proxy.async by every writer and __syncwarp() first; the source is reused only after
-// cp.async.bulk.wait_group.read (bulk_wait_read0) by every lane and another __syncwarp().
-__device__ __forceinline__ void store_blocks(bool leader, uint8_t* image, int64_t tile_idx, int F, uint32_t s_block, int quarter,
-                                             int lane, int chunk0, int stride, int n_chunks) {
-  uint8_t* g0 = image + (size_t)tile_idx * 128 * F * 2 + (size_t)(2 * quarter) * F * 32;
-  const uint32_t s0 = s_block + (uint32_t)(2 * quarter) * 256u;
-  if (leader) {
-    if (elect_one()) {
+// chunks chunk0, chunk0 + stride, ...; the four warps (quarters) of a (tile, column half) own those chunks completely.
+//   mode = 4 (default): a chunk of all 128 rows ([128][16 B] = 2 KB, dense in shared memory) leaves with ONE tensor copy
+//                   through `tmap` (ImageMaps: its 8 sixteen-row pieces land F * 32 bytes apart); the four warps meet
+//                   on the named barrier `bar_id`, then an elected lane of quarter 0 issues the group's copies.
+//                   Measured with equal bytes: 8 x fewer TMA requests are worth 0.36 ms per training step;
+//   mode = 1:       256-byte bulk copies (the largest piece contiguous on both sides without a tensor map), all of a
+//                   warp's copies issued by one elected lane in a loop over uniform addresses;
+//                   (one copy per lane, the first version, made ptxas wrap every UBLKCP in a 9-instruction R2UR
+//                   waterfall iteration: 7.23 -> 6.96 ms per training step when the elected lane took over).
+// Callers: fence.proxy.async by every writer first; the source is reused only after block_reusable() below.
+__device__ __forceinline__ void store_blocks(int mode, const CUtensorMap* tmap, int slot, uint32_t bar_id, uint8_t* image,
+                                             int64_t tile_idx, int F, uint32_t s_block, int quarter, int lane, int chunk0,
+                                             int stride, int n_chunks) {
+  if (mode == 4) {
+    named_bar_sync(bar_id, 128);                       // all 128 rows of the group's chunks are written and fenced
+    if (quarter == 0 && elect_one()) {
       for (int i = 0; i < n_chunks; ++i) {
         const int chunk = chunk0 + i * stride;
-        bulk_s2g(g0 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA, 256u);
-        bulk_s2g(g0 + (size_t)F * 32 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA + 256u, 256u);
+        if (slot >= 0) tma_store_4d(tmap, s_block + (uint32_t)chunk * kLboA, 0, chunk, (int)(tile_idx * 8), slot);
+        else tma_store_3d(tmap, s_block + (uint32_t)chunk * kLboA, 0, chunk, (int)(tile_idx * 8));
       }
       bulk_commit();
     }
     __syncwarp();
-  } else {
-    if (lane < 2 * n_chunks) {
-      const int chunk = chunk0 + (lane >> 1) * stride, g = lane & 1;
-      bulk_s2g(g0 + (size_t)g * F * 32 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA + (uint32_t)g * 256u, 256u);
+    return;
+  }
+  uint8_t* g0 = image + (size_t)tile_idx * 128 * F * 2 + (size_t)(2 * quarter) * F * 32;
+  const uint32_t s0 = s_block + (uint32_t)(2 * quarter) * 256u;
+  if (elect_one()) {
+    for (int i = 0; i < n_chunks; ++i) {
+      const int chunk = chunk0 + i * stride;
+      bulk_s2g(g0 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA, 256u);
+      bulk_s2g(g0 + (size_t)F * 32 + (size_t)chunk * 256, s0 + (uint32_t)chunk * kLboA + 256u, 256u);
     }
     bulk_commit();
   }
+  __syncwarp();
+}
+
+// The image copies that read this warp's rows of an operand block have left shared memory (call before overwriting).
+// Mode 1: every lane waits for its own copies; mode 4: the issuing lane (quarter 0) waits, the group's named
+// barrier tells the other three warps.
+__device__ __forceinline__ void block_reusable(int mode, uint32_t bar_id) {
+  bulk_wait_read0();
+  if (mode == 4) named_bar_sync(bar_id, 128);
+  else __syncwarp();
 }
 
 }  // namespace hn

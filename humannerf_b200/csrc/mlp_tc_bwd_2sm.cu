@@ -18,12 +18,12 @@
 
 namespace hn {
 
-template <bool kBits>
+template <bool kBits, int kSt>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restrict__ packed, int64_t n_cap,
                      const int64_t* __restrict__ n_dev, int mlp, const float* __restrict__ d_out, int ld_out, int n_out,
-                     const TrainBufs bufs, const float* __restrict__ pos, const float* __restrict__ hann_w,
-                     float* __restrict__ d_pos, int ld_dpos, int n_stages) {
+                     const TrainBufs bufs, const __grid_constant__ ImageMaps maps, const float* __restrict__ pos,
+                     const float* __restrict__ hann_w, float* __restrict__ d_pos, int ld_dpos, int n_stages) {
   using namespace s2;
   const int64_t n_samples = n_dev ? min(max(__ldg(n_dev), (int64_t)0), n_cap) : n_cap;   // see field_tc2_kernel
   const uint32_t stage_bytes = kRingBytes2 / (uint32_t)n_stages;
@@ -161,6 +161,8 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
     const uint32_t bar_ready = mapa_cluster(s_a_ready + (uint32_t)tile * 8, 0);      // in the leader
     const uint32_t bar_acc = s_acc_full + (uint32_t)tile * 8;
     uint32_t acc_phase = 0;
+    constexpr int st_mode = kSt;                                     // image store mode (store_blocks: 1 or 4)
+    const uint32_t st_bar = 1u + (uint32_t)(tile * 2 + half);        // named barrier of this (tile, column half)
 
     for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters) {
       const int64_t tile_idx = quad * 4 + tile * 2 + (int64_t)rank;
@@ -174,13 +176,12 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
         if (valid && half == 0)
           for (int c = 0; c < n_out && c < 8; ++c) g[c] = d_out[sample * ld_out + c];
         const uint4 pk = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
-        bulk_wait_read0();                                       // image copies of the previous pass have left the block
-        __syncwarp();
+        block_reusable(st_mode, st_bar);                         // image copies of the previous pass have left the block
         st_shared_v4(a_h + (uint32_t)half * kLboA + (uint32_t)row * 16u, pk.x, pk.y, pk.z, pk.w);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_ready);
-        if (have_img) store_blocks(bufs.leader_stores != 0, bufs.dz[mlp][out_layer], tile_idx, 16, a_h, quarter, lane, half, 1, 1);
+        if (have_img) store_blocks(st_mode, &maps.m[4 + mlp], -1, st_bar, bufs.dz[mlp][out_layer], tile_idx, 16, a_h, quarter, lane, half, 1, 1);
       }
 
       // The stored activations that mask the accumulators come from HBM (~1 us): the two 16-row groups of this
@@ -226,11 +227,10 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
             for (int i = 0; i < 4; ++i) mb[i] = (rec && i * 32 < n_half) ? __ldg(rec + i) : 0u;
           }
           prefetch_bits(r + 1);
-          mbar_wait(bar_acc, acc_phase, 4);
+          block_reusable(st_mode, st_bar);                       // the block's previous image copy has left shared memory
+          mbar_wait(bar_acc, acc_phase, 4);                      // (checked while the round's MMAs run)
           acc_phase ^= 1;
           tc_fence_after();
-          bulk_wait_read0();                                     // the block's previous image copy has left shared memory
-          __syncwarp();
           uint32_t v[2][32];
           tmem_ld32(t_acc + (uint32_t)c_begin, v[0]);
 #pragma unroll 1
@@ -265,8 +265,8 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
           __syncwarp();
           if (!last && lane == 0) mbar_arrive_remote(bar_ready);
           if (have_img)
-            store_blocks(bufs.leader_stores != 0, bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane,
-                         half * (n_half >> 3), 1, n_half >> 3);
+            store_blocks(st_mode, &maps.m[mlp], 2 * (int)rd.layer + 1, st_bar, bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h,
+                         quarter, lane, half * (n_half >> 3), 1, n_half >> 3);
         } else if (rd.epi == 0) {
           const int n_full = rd.n, n_half = n_full >> 1, c_begin = half * n_half;
           const size_t row_off = image_row_offset(tile_idx, row, n_full);
@@ -276,11 +276,10 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
           for (int g8 = 0; g8 < 4; ++g8)
             hq[g8] = h_img ? __ldg(reinterpret_cast<const uint4*>(h_img + (size_t)((c_begin >> 3) + g8) * 256))
                            : make_uint4(0u, 0u, 0u, 0u);
+          block_reusable(st_mode, st_bar);                       // the block's previous image copy has left shared memory
           mbar_wait(bar_acc, acc_phase, 4);
           acc_phase ^= 1;
           tc_fence_after();
-          bulk_wait_read0();                                     // the block's previous image copy has left shared memory
-          __syncwarp();
 #pragma unroll 1
           for (int c0 = 0; c0 < n_half; c0 += 32) {
             uint32_t v[32];
@@ -308,8 +307,8 @@ field_tc2_bwd_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __res
           __syncwarp();
           if (!last && lane == 0) mbar_arrive_remote(bar_ready);
           if (have_img)
-            store_blocks(bufs.leader_stores != 0, bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h, quarter, lane,
-                         half * (n_half >> 3), 1, n_half >> 3);
+            store_blocks(st_mode, &maps.m[mlp], 2 * (int)rd.layer + 1, st_bar, bufs.dz[mlp][rd.layer], tile_idx, n_full, a_h,
+                         quarter, lane, half * (n_half >> 3), 1, n_half >> 3);
         } else {
           // gradient of the encoding block, contracted with the encoding's derivative:
           //   d_pos[a] += [raw x] g[a] + sum_k w_k 2^k (cos(2^k x_a) g_sin(k,a) - sin(2^k x_a) g_cos(k,a))
@@ -379,10 +378,11 @@ int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_sa
   using namespace s2;
   static int max_clusters_cached = 0;
   if (max_clusters_cached == 0) {
-    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
-                      "hn_field_bwd_bf16/2sm smem attr"));
-    HN_TRY(check_cuda(cudaFuncSetAttribute(field_tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
-                      "hn_field_bwd_bf16/2sm smem attr"));
+    const void* variants[4] = {(const void*)field_tc2_bwd_kernel<true, 4>, (const void*)field_tc2_bwd_kernel<true, 1>,
+                               (const void*)field_tc2_bwd_kernel<false, 4>, (const void*)field_tc2_bwd_kernel<false, 1>};
+    for (const void* f : variants)
+      HN_TRY(check_cuda(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2),
+                        "hn_field_bwd_bf16/2sm smem attr"));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * (sms / 2)));
@@ -394,7 +394,7 @@ int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_sa
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_bwd_kernel<false>, &cfg), "hn_field_bwd_bf16/2sm occupancy"));
+    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_tc2_bwd_kernel<false, 1>, &cfg), "hn_field_bwd_bf16/2sm occupancy"));
     if (n <= 0) return fail_arg("hn_field_bwd_bf16: no 2-CTA cluster of the tcgen05 kernel fits on this device");
     max_clusters_cached = n;
   }
@@ -406,13 +406,19 @@ int launch_field_tc2_bwd(const TcPlan& plan, const uint8_t* packed, int64_t n_sa
   }
   const int64_t n_quads = ceil_div<int64_t>(n_samples, 2 * kSetRows);
   const unsigned grid = 2u * (unsigned)std::min<int64_t>(n_quads, (int64_t)max_clusters_cached);
+  ImageMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (bufs.leader_stores == 4) HN_TRY(make_image_maps(plan, bufs, &maps));
   // the 1-bit mask images exist when the cta_group::2 forward wrote them (hn_field_bwd_bf16 nulls the pointers otherwise)
-  if (bufs.bits[mlp][0])
-    field_tc2_bwd_kernel<true><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, mlp, d_out, ld_out,
-                                                                   n_out, bufs, pos, hann_w, d_pos, ld_dpos, tc2_stages());
-  else
-    field_tc2_bwd_kernel<false><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, mlp, d_out, ld_out,
-                                                                    n_out, bufs, pos, hann_w, d_pos, ld_dpos, tc2_stages());
+  const bool bits = bufs.bits[mlp][0] != nullptr, maps4 = bufs.leader_stores == 4;
+#define HN_BWD2_LAUNCH(B, S)                                                                                              \
+  field_tc2_bwd_kernel<B, S><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, mlp, d_out, ld_out, \
+                                                                 n_out, bufs, maps, pos, hann_w, d_pos, ld_dpos, tc2_stages())
+  if (bits && maps4) HN_BWD2_LAUNCH(true, 4);
+  else if (bits) HN_BWD2_LAUNCH(true, 1);
+  else if (maps4) HN_BWD2_LAUNCH(false, 4);
+  else HN_BWD2_LAUNCH(false, 1);
+#undef HN_BWD2_LAUNCH
   return launched(mlp == 1 ? "hn_field_bwd_bf16/canonical chain (2sm)" : "hn_field_bwd_bf16/non-rigid chain (2sm)");
 }
 

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
+
 #include "tc_common.cuh"
 #include "tiles.cuh"
 
@@ -80,6 +82,17 @@ struct TrainBufs {
   int32_t reserved;
 };
 
+// Tensor maps over the T16 images for the 2 KB image stores of the cta_group::2 training kernels (store mode 4): an
+// operand chunk in shared memory ([128 rows][16 B] = 8 sixteen-row groups x 256 B) is one dense TMA box whose 8
+// pieces land F * 32 bytes apart in the image.  View of an image: dim0 = the 128 bf16 of a 256-byte block, dim1 = column
+// chunk (stride 256 B), dim2 = sixteen-row group (stride F * 32 B); the hidden-layer images of one MLP (h0, dz0, h1,
+// dz1, ... - carve_train_bufs places them back to back) share one rank-4 map with dim3 = image slot.
+//   [m] hidden images of MLP m (slot 2l = h[m][l], 2l + 1 = dz[m][l]);  [2 + m] encoding image pe[m];
+//   [4 + m] output-layer dZ image (F = 16)
+struct alignas(64) ImageMaps {
+  CUtensorMap m[6];
+};
+
 // ReLU-mask image of a hidden layer (cta_group::2 kernels).  The epilogue thread (row, half) of the forward kernel and
 // of the backward chain own the same n_half = F / 2 columns of a row; its record holds one 32-bit word per 32 columns:
 // bit j = column 2j of the group is active, bit 16 + j = column 2j + 1 (the order the packed bf16 pairs produce).
@@ -145,13 +158,12 @@ static inline bool use_relu_bits() {
   }();
   return v;
 }
-// cta_group::2 training kernels: the 256-byte shared -> global bulk copies of a warp's image blocks are issued by ONE
-// elected lane in a loop over uniform addresses (default) instead of one copy per lane - per-lane addresses make
-// ptxas wrap every UBLKCP in a 9-instruction R2UR waterfall iteration.  HN_TC_LEADER_STORES=0: one copy per lane.
-static inline bool use_leader_stores() {
-  static const bool v = [] {
+// cta_group::2 training kernels, image store mode (store_blocks in mlp_tc_2sm.cuh): 4 (default) = one 2 KB tensor-map
+// copy per 8-column chunk of a tile, 1 (HN_TC_LEADER_STORES=1) = 256-byte bulk copies issued by one elected lane per warp
+static inline int use_leader_stores() {
+  static const int v = [] {
     const char* e = getenv("HN_TC_LEADER_STORES");
-    return e == nullptr || atoi(e) != 0;
+    return (e != nullptr && atoi(e) == 1) ? 1 : 4;
   }();
   return v;
 }
@@ -337,7 +349,7 @@ inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* 
   TrainBufs b;
   memset(&b, 0, sizeof(b));
   b.n_tiles = n_tiles;
-  b.leader_stores = use_leader_stores() ? 1 : 0;
+  b.leader_stores = use_leader_stores();
   for (int m = 0; m < 2; ++m) {
     b.pe[m] = take(n_tiles * 128 * plan.pe_pad[m] * 2);
     for (int l = 0; l < plan.layers[m]; ++l) {
@@ -352,6 +364,52 @@ inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* 
       b.bits[m][l] = take(n_tiles * 2 * 128 * relu_bits_record_bytes(plan.width[m] / 2));
   if (out) *out = b;
   return off;
+}
+
+// Encodes the ImageMaps of a carved training workspace (host; the driver entry point comes from the runtime, libcuda
+// is not linked).  Returns 0 or a negative argument error.
+inline int make_image_maps(const TcPlan& plan, const TrainBufs& b, ImageMaps* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return fail_arg("tensor-map image stores: cuTensorMapEncodeTiled is not available from this driver");
+  memset(out, 0, sizeof(*out));
+  const cuuint64_t groups = (cuuint64_t)b.n_tiles * 8;
+  auto enc = [&](CUtensorMap* m, void* base, int F, int slots) -> int {
+    if (!base || F < 8 || (F & 7) || (reinterpret_cast<uintptr_t>(base) & 255)) return fail_arg("tensor-map image stores: bad image (F = %d)", F);
+    const cuuint64_t gdim[4] = {128, (cuuint64_t)(F / 8), groups, (cuuint64_t)std::max(slots, 1)};
+    const cuuint64_t gstr[3] = {256, (cuuint64_t)F * 32, groups * (cuuint64_t)F * 32};
+    const cuuint32_t box[4] = {128, 1, 8, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, slots > 0 ? 4 : 3, base, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail_arg("tensor-map image stores: cuTensorMapEncodeTiled failed (%d, F = %d)", (int)r, F);
+    return 0;
+  };
+  for (int m = 0; m < 2; ++m) {
+    const int L = plan.layers[m], F = plan.width[m];
+    if (L < 1) continue;
+    const int64_t img = b.n_tiles * 128 * (int64_t)F * 2;
+    if (L > 1) {
+      // the hidden images must sit back to back: h0, dz0, h1, dz1, ...
+      for (int l = 0; l + 1 < L; ++l)
+        if (b.h[m][l] != b.h[m][0] + (int64_t)(2 * l) * img || b.dz[m][l] != b.h[m][0] + (int64_t)(2 * l + 1) * img)
+          return fail_arg("tensor-map image stores: unexpected layout of the training workspace");
+      HN_TRY(enc(&out->m[m], b.h[m][0], F, 2 * (L - 1)));
+    }
+    HN_TRY(enc(&out->m[2 + m], b.pe[m], plan.pe_pad[m], 0));
+    HN_TRY(enc(&out->m[4 + m], b.dz[m][L - 1], 16, 0));
+  }
+  return 0;
 }
 
 }  // namespace hn

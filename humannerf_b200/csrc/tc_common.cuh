@@ -122,6 +122,22 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 __device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
+// shared -> global tensor copies (TMA store through a CUtensorMap, dense box in shared memory) in the calling
+// thread's bulk async-group
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t ssrc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1),
+               "r"(c2), "r"(ssrc)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t ssrc, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(ssrc)
+               : "memory");
+}
+// named barrier over `threads` threads (multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 // ask the TMA unit to pull `bytes` (multiple of 16) of global memory into L2
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");

@@ -402,7 +402,8 @@ def test_relu_mask_images_match_activation_read(tmp_path, P, ignore):
     assert os.environ.get('HN_TC_RELU_BITS', '1') != '0' and os.environ.get('HN_TC_KERNEL', '') in ('', '2sm')
     got = ab.field_grads(P, ignore)
     out = str(tmp_path / 'read_h.npz')
-    env = dict(os.environ, HN_TC_RELU_BITS='0')
+    # ... and with the image stores as 256-byte bulk copies instead of 2 KB tensor-map copies (store_blocks modes 1 / 4)
+    env = dict(os.environ, HN_TC_RELU_BITS='0', HN_TC_LEADER_STORES='1')
     r = subprocess.run([sys.executable, os.path.join(root, 'tests', 'relu_bits_ab.py'), str(P), str(ignore), out],
                        env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
