@@ -319,7 +319,7 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
     return fail_arg("hn_field_bwd_bf16: null pointer or negative size");
   if (!ignore_non_rigid && ((p->cond_dim > 0 && !cond) || !hann_w)) return fail_arg("hn_field_bwd_bf16: cond / hann_w missing");
   TrainBufs bufs;
-  const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
+  const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs, true);
   if (workspace_bytes < need) return fail_arg("hn_field_bwd_bf16: workspace is not a bf16 training workspace of this size");
   if (scratch_bytes < bwd_scratch_bytes(n_samples)) return fail_arg("hn_field_bwd_bf16: scratch too small");
   cudaStream_t st = as_stream(stream);

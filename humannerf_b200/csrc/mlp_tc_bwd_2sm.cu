@@ -5,8 +5,9 @@
 // streams half), the leader CTA's two issuer warps run warp-uniform with the chunk schedule in kernel parameters,
 // and what the issuers wait for (`a_ready`, `full`) collects remote arrives from the peer.
 //   * dZ of the previous layer is written in place as the next A operand; its T16 image for the weight-gradient
-//     kernel leaves shared memory as 256-byte bulk copies (one per lane, store_blocks) instead of a 16-byte store
-//     per thread and chunk;
+//     kernel leaves shared memory through the TMA (store_blocks in mlp_tc_2sm.cuh: one 2 KB tensor-map copy per
+//     8-column chunk of a tile by default, kSt = 4; 256-byte bulk copies with kSt = 1) instead of a 16-byte store per
+//     thread and chunk;
 //   * ReLU': kBits = true (default) masks the accumulator with the 1-bit mask image the forward kernel wrote
 //     (relu_bits_* in mlp_tc_plan.cuh): one 4..16-byte record per thread and round, fetched a round ahead, instead
 //     of re-reading the bf16 activations (16 bytes per thread and 8-column chunk, 4.4 GB per 786 k samples);

@@ -158,14 +158,16 @@ static inline bool use_relu_bits() {
   }();
   return v;
 }
-// cta_group::2 training kernels, image store mode (store_blocks in mlp_tc_2sm.cuh): 4 (default) = one 2 KB tensor-map
-// copy per 8-column chunk of a tile, 1 (HN_TC_LEADER_STORES=1) = 256-byte bulk copies issued by one elected lane per warp
-static inline int use_leader_stores() {
-  static const int v = [] {
+// cta_group::2 training kernels, image store mode (store_blocks in mlp_tc_2sm.cuh): 4 = one 2 KB tensor-map copy per
+// 8-column chunk of a tile, 1 = 256-byte bulk copies issued by one elected lane per warp.  Default: the backward chains
+// use 4 (3.40 -> 3.32 ms per step), the forward 1 (1.44 ms; 1.59 ms with 4: its epilogue already spills, and the two
+// named barriers per layer cost more than the 8 x fewer TMA requests save).  HN_TC_LEADER_STORES=1 / 4 forces both.
+static inline int use_leader_stores(bool backward) {
+  static const int forced = [] {
     const char* e = getenv("HN_TC_LEADER_STORES");
-    return (e != nullptr && atoi(e) == 1) ? 1 : 4;
+    return e == nullptr ? 0 : (atoi(e) == 1 ? 1 : 4);
   }();
-  return v;
+  return forced != 0 ? forced : (backward ? 4 : 1);
 }
 // largest weight chunk (bytes, both halves) for the selected kernel family (forward and backward-data chain)
 static inline uint32_t fwd_chunk_bytes() {
@@ -338,7 +340,7 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
 }
 
 // Carves the training buffers out of `base` (may be null to only measure). Returns the bytes used.
-inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* base, TrainBufs* out) {
+inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* base, TrainBufs* out, bool backward = false) {
   const int64_t n_tiles = ceil_div<int64_t>(std::max<int64_t>(n_samples, 1), 128);
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
@@ -349,7 +351,7 @@ inline int64_t carve_train_bufs(const TcPlan& plan, int64_t n_samples, uint8_t* 
   TrainBufs b;
   memset(&b, 0, sizeof(b));
   b.n_tiles = n_tiles;
-  b.leader_stores = use_leader_stores();
+  b.leader_stores = use_leader_stores(backward);
   for (int m = 0; m < 2; ++m) {
     b.pe[m] = take(n_tiles * 128 * plan.pe_pad[m] * 2);
     for (int l = 0; l < plan.layers[m]; ++l) {
