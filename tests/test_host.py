@@ -174,3 +174,36 @@ def test_bench_reference_arm_runs_on_cpu():
     assert d['impl'] == 'reference' and d['metric'] == 'train_step_rays_per_sec' and d['value'] > 0
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_first_deconv_function_matches_conv_transpose():
+    """`nn_util._FirstDeconv` (the volume decoder's first ConvTranspose3d(k4, s2, p1) on its 1^3 input as a product
+    with the central 2^3 taps, reference `core/utils/network_util.py:12-50`) against torch's full transposed
+    convolution in float64: same output, same gradients for the embedding and every parameter - in particular exactly
+    zero for the 56 taps the 1^3 input cannot reach - and the weight gradient comes back in the parameter's NDHWC
+    strides (FusedAdam reads it in place)."""
+    import torch
+    from humannerf_b200.nn_util import ConvDecoder3D
+    torch.manual_seed(0)
+    dec = ConvDecoder3D(embedding_size=32, volume_size=8, voxel_channels=5).double()
+    emb = torch.randn(1, 32, dtype=torch.double, requires_grad=True)
+    out = dec(emb)
+    g = torch.randn_like(out)
+    out.backward(g)
+    got = {k: v.grad.clone() for k, v in dec.named_parameters()}
+    got_emb = emb.grad.clone()
+    w0 = dec.block_conv[0].weight
+    assert w0.grad.stride() == w0.stride() and not w0.is_contiguous()
+    for p_ in dec.parameters():
+        p_.grad = None
+    emb.grad = None
+    h = dec.block_mlp(emb)
+    ref = dec.block_conv(h.view(1, -1, 1, 1, 1))
+    assert float((ref - out).abs().max()) < 1e-12
+    ref.backward(g)
+    for k, v in dec.named_parameters():
+        assert float((v.grad - got[k]).abs().max()) <= 1e-10 * max(1.0, float(v.grad.abs().max())), k
+    assert float((emb.grad - got_emb).abs().max()) < 1e-10
+    outer = got['block_conv.0.weight'].clone()
+    outer[:, :, 1:3, 1:3, 1:3] = 0
+    assert float(outer.abs().max()) == 0.0
