@@ -57,6 +57,13 @@ def test_field_plan_sizes():
     per_sample = lib.hn_field_workspace_bytes(ctypes.byref(fp), 1000, 1, 0) - 256
     # non-rigid 108+128*3+164+128*2+4, canonical 64+256*4+320+256*3+4 floats per sample
     assert per_sample == 1000 * 4 * ((108 + 128 * 3 + 164 + 128 * 2 + 4) + (64 + 256 * 4 + 320 + 256 * 3 + 4))
+    # bf16 training workspace: T16 images of 8 tiles of 128 rows (encoding blocks, hidden activations H and
+    # pre-activation gradients dZ per layer, 16-wide output dZ) plus the 1-bit ReLU mask images of the hidden layers
+    # (one 8- / 16-byte record per row and column half)
+    rows = 1024
+    images = rows * 2 * ((48 + 6 * 2 * 128 + 16) + (64 + 8 * 2 * 256 + 16))
+    masks = rows * 2 * (6 * 8 + 8 * 16)
+    assert lib.hn_field_workspace_bytes(ctypes.byref(fp), 1000, 1, _lib.PRECISION_BF16) == images + masks + 256
     packed = lib.hn_field_packed_bytes(ctypes.byref(fp))
     # bf16 image (hidden layers carry one extra 16-row K step for the folded bias):
     nr = 48 * 128 + 3 * (128 + 16) * 128 + (128 + 48) * 128 + (128 + 16) * 128 + (128 + 16) * 16
