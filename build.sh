@@ -7,11 +7,9 @@ OUT=humannerf_b200/lib
 mkdir -p "$OUT" build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="${HN_EXTRA_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v"
-# HN_TC_PROFILE=1 ./build.sh compiles the per-role cycle counters into the tcgen05 forward kernel (measurement builds only)
-if [ "${HN_TC_PROFILE:-0}" = "1" ]; then FLAGS="$FLAGS -DHN_TC_PROFILE"; fi
 objs=()
 pids=()
-for f in api rays motion_field composite field_fp32 mlp_tc mlp_tc_2sm mlp_tc_cl mlp_tc_bwd mlp_tc_bwd_2sm tile_wgrad adam pose_fk lpips_head; do
+for f in api rays motion_field composite field_fp32 mlp_tc_entry mlp_tc_2sm mlp_tc_bwd_entry mlp_tc_bwd_2sm tile_wgrad adam pose_fk lpips_head; do
   $NVCC $FLAGS -c $SRC/$f.cu -o build/$f.o > build/$f.log 2>&1 &
   pids+=($!)
   objs+=(build/$f.o)

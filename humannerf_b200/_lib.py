@@ -55,9 +55,6 @@ SIGNATURES = {
     'hn_last_error': (C.c_char_p, []),
     'hn_launch_count': (_i64, []),
     'hn_has_tcgen05': (_int, []),
-    'hn_debug_tc_prof': (_int, [_p]),
-    'hn_debug_tcc_prof': (_int, [_p]),
-    'hn_debug_tc2_trace': (_int, [_p]),
     'hn_gen_rays': (_int, [_int, _int, _p, _p, _p, _p, _p]),
     'hn_rays_bbox': (_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     'hn_compact_rays_workspace_bytes': (_i64, [_i64]),

@@ -1,12 +1,17 @@
 // Canonical field, tensor-core path (HN_PRECISION_BF16), default forward kernel: CTA PAIRS with
 // tcgen05.mma.cta_group::2.
 //
-// Same math, operand layouts, epilogue and weight stream as the tile-pair kernel of mlp_tc.cu (read its header
-// first); what changes is who shares the weights.  There the two tiles of ONE CTA share every weight chunk, the
-// 64 KB ring holds half a layer, and a ring slot only turns over after BOTH tiles have consumed it and the refill
-// (~1000 clk of L2 latency) has landed - so the tiles run in lock-step, both accumulators complete together and
-// the tensor pipe idles through both epilogues and the hand-over latency (measured: 39.8 % pipe active, a one-time
-// head start of one tile changes nothing).  Here
+// One persistent kernel runs  hann-PE -> non-rigid MLP -> xyz = x_skel + offset -> PE -> canonical MLP -> raw  with
+// every activation held on chip:
+//   * bf16 operands, fp32 accumulation in TMEM; the A operand (activations) lives in shared memory in the UMMA
+//     no-swizzle K-major core-matrix layout and is rewritten in place by 16 epilogue warps
+//     (TMEM -> registers -> ReLU -> bf16 -> st.shared);
+//   * biases ride in the GEMM: the positional-encoding block of A carries a constant-1 column and the weight image
+//     the bias in the matching K row, so the epilogue has no loads;
+//   * the B operand (weights) is pre-tiled by hn_field_pack_bf16 into exactly the shared-memory image the MMA wants
+//     and streamed with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a ring - no tensor maps.
+// The predecessor (round 1, one CTA per SM, cta_group::1, two tiles sharing a 4 x 16 KB ring) ran its tiles in
+// lock-step (39.8 % pipe active).  Here
 //
 //   * a cluster of two CTAs (two SMs) works on FOUR 128-sample tiles: tile set X = {tile 0 of CTA 0, tile 0 of
 //     CTA 1}, tile set Y = {tile 1 of CTA 0, tile 1 of CTA 1}.  One M = 256 MMA covers a tile set: each SM's tensor
@@ -36,20 +41,13 @@
 
 namespace hn {
 
-// Timeline of one pass of cluster 0 (measurement aid, HN_TC_ABLATE & 8): clock64 of the leader SM at
-//   [role 0/1 = issuer X/Y][layer][0] operand ready (after the a_ready wait), [1] last MMA + commits issued;
-//   [role 2/3 = epilogue thread of tile set X/Y (warp 2 / 10, lane 0)][layer][0] accumulator complete observed,
-//   [1] operand handed over (arrive done)
-__device__ long long g_tc2_trace[4][32][4];   // issuers: [2] cycles waiting for weights, [3] cycles issuing MMAs + commits
-constexpr int kTraceQuad = 6;      // which pass of cluster 0 is recorded
-
 // kStore: training (activation / mask images are written); kSt: image store mode of store_blocks (1 or 4)
 template <bool kStore, int kSt>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
                  const float* __restrict__ x_skel, const float* __restrict__ hann_w, int ignore_non_rigid,
                  float* __restrict__ raw, float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs,
-                 const __grid_constant__ ImageMaps maps, int ablate, int n_stages) {
+                 const __grid_constant__ ImageMaps maps, int n_stages) {
   using namespace s2;
   const uint32_t stage_bytes = kRingBytes2 / (uint32_t)n_stages;
   // n_dev (nullable): the number of samples actually present, read from device memory (empty-space skipping
@@ -153,16 +151,12 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
       const uint32_t a_inc = (2u * kLboA) >> 4;                                      // one K step = two core matrices
       uint32_t stage = 0, phase = 0, a_phase = 0, full_ok = 0;
       // tile set X leads Y by one chunk (measured: +3.5 %; 2 / 3 / 4 chunks: +1.6 / -1.2 / +1.9 %: the 4-stage ring
-      // then stalls X on refills).  HN_TC_ABLATE=4 switches the lead off, bits 4-6 set other leads (measurement aid)
-      const uint32_t lead_chunks = (ablate & 4) ? ((uint32_t)ablate >> 4) & 7u : 1u;
-      const bool lead = lead_chunks != 0;
+      // then stalls X on refills)
+      constexpr uint32_t lead_chunks = 1u;
+      constexpr bool lead = true;
       uint32_t in_layer = 0;
       uint32_t n_layers_issued = 0;
-      int pass = 0, tr_layer = 0;
-      long long tr_wait = 0, tr_issue = 0;
-      for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters, ++pass) {
-        const bool trace = (ablate & 8) && cluster_id == 0 && pass == kTraceQuad && lane == 0;
-        tr_layer = 0;
+      for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters) {
         for (uint32_t c = first_chunk; c < n_chunks; ++c) {
           const uint2 e = itab.e[c];
           const uint32_t n = e.y & 0xFFFFu, ksteps = (e.y >> 16) & 0xFFu, flags = e.y >> 24;
@@ -180,12 +174,9 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
             if (lead && t == 0u && n_layers_issued > 0) mbar_wait(s_lead + 8, a_phase ^ 1u, 7);
             ++n_layers_issued;
             a_phase ^= 1;
-            if (trace) g_tc2_trace[t][tr_layer][0] = clock64();
           }
-          const long long tw0 = trace ? clock64() : 0;
           if (!full_ok) mbar_wait(s_full + stage * 8, phase, 3);
           tc_fence_after();
-          const long long tw1 = trace ? clock64() : 0;
           // probe the NEXT chunk's weights now: the round trip overlaps the MMA issue below
           {
             const uint32_t ns = stage + 1 == (uint32_t)n_stages ? 0u : stage + 1;
@@ -207,18 +198,6 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
             if (lead && t == 0u && (in_layer == lead_chunks || ((flags & 2u) && in_layer < lead_chunks))) mbar_arrive(s_lead);
           }
           __syncwarp();
-          if (trace) {
-            const long long tw2 = clock64();
-            tr_wait += tw1 - tw0;
-            tr_issue += tw2 - tw1;
-            if (flags & 2u) {
-              g_tc2_trace[t][tr_layer][1] = tw2;
-              g_tc2_trace[t][tr_layer][2] = tr_wait;
-              g_tc2_trace[t][tr_layer][3] = tr_issue;
-              tr_wait = tr_issue = 0;
-            }
-          }
-          if (flags & 2u) ++tr_layer;
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -255,7 +234,6 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
     const int nr_freqs = (int)hdr->nr_freqs, cn_freqs = (int)hdr->cn_freqs;
     const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
 
-    int pass = 0;
     float xn[3] = {0.f, 0.f, 0.f};                // positions of the coming pass
     {
       const int64_t sample0 = (cluster_id * 4 + tile * 2 + (int64_t)rank) * kTileM + row;
@@ -263,8 +241,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
         xn[0] = __ldg(x_skel + sample0 * 3 + 0); xn[1] = __ldg(x_skel + sample0 * 3 + 1); xn[2] = __ldg(x_skel + sample0 * 3 + 2);
       }
     }
-    for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters, ++pass) {
-      const bool trace = (ablate & 8) && blockIdx.x == 0 && pass == kTraceQuad && lane == 0 && half == 0 && quarter == 2;
+    for (int64_t quad = cluster_id; quad < n_quads; quad += n_clusters) {
       // tile set X = tiles 4q, 4q+1 (CTA 0, CTA 1); tile set Y = tiles 4q+2, 4q+3
       const int64_t tile_idx = quad * 4 + tile * 2 + (int64_t)rank;
       const int64_t sample = tile_idx * kTileM + row;
@@ -303,18 +280,11 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
         }
         // training: the image copies of the block this layer overwrites have left shared memory - checked (and, with
         // tensor-map stores, agreed among the four warps) while the layer's MMAs run, not after them
-        if (kStore && !is_out && !(ablate & 1)) block_reusable(st_mode, st_bar);
+        if (kStore && !is_out) block_reusable(st_mode, st_bar);
         mbar_wait(bar_acc, acc_phase, 4);
         acc_phase ^= 1;
         tc_fence_after();
-        if (trace) g_tc2_trace[2 + tile][layer][0] = clock64();
-        if (!is_out && (ablate & 1)) {
-          // measurement aid (HN_TC_ABLATE=1): barrier handshake only, accumulator never read
-          tc_fence_before();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(bar_ready);
-        } else if (!is_out) {
+        if (!is_out) {
           const int n_full = (int)hdr->layer_n[layer];
           const int n_half = n_full >> 1;                          // columns owned by this thread
           const int c_begin = half * n_half;
@@ -364,7 +334,6 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(bar_ready);
-          if (trace) g_tc2_trace[2 + tile][layer][1] = clock64();
           if (store)
             store_blocks(st_mode, &maps.m[is_nr ? 0 : 1], 2 * (is_nr ? layer : layer - nr_layers), st_bar,
                          is_nr ? bufs.h[0][layer] : bufs.h[1][layer - nr_layers], tile_idx, n_full, a_h, quarter, lane,
@@ -410,7 +379,7 @@ field_tc2_kernel(const __grid_constant__ IssueTab itab, const uint8_t* __restric
 // a partner, so this can be below sms / 2).  Returns <0 / cudaError_t like every entry point.
 int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
                      const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
-                     const TrainBufs* bufs, int sms, int ablate, cudaStream_t st) {
+                     const TrainBufs* bufs, int sms, cudaStream_t st) {
   using namespace s2;
   static int max_clusters_cached = 0;
   if (max_clusters_cached == 0) {
@@ -449,27 +418,20 @@ int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_sample
   if (bufs && bufs->leader_stores == 4) {
     HN_TRY(make_image_maps(plan, *bufs, &maps));
     field_tc2_kernel<true, 4><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
-                                                                  ignore_non_rigid, raw, xyz, offsets, *bufs, maps, ablate,
+                                                                  ignore_non_rigid, raw, xyz, offsets, *bufs, maps,
                                                                   tc2_stages());
   } else if (bufs) {
     field_tc2_kernel<true, 1><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
-                                                                  ignore_non_rigid, raw, xyz, offsets, *bufs, maps, ablate,
+                                                                  ignore_non_rigid, raw, xyz, offsets, *bufs, maps,
                                                                   tc2_stages());
   } else {
     TrainBufs none;
     memset(&none, 0, sizeof(none));
     field_tc2_kernel<false, 1><<<grid, kThreads, kSmemTotal2, st>>>(itab, packed, n_samples, n_samples_dev, x_skel, hann_w,
-                                                                   ignore_non_rigid, raw, xyz, offsets, none, maps, ablate,
+                                                                   ignore_non_rigid, raw, xyz, offsets, none, maps,
                                                                    tc2_stages());
   }
   return launched("hn_field_fwd/tcgen05 2sm");
 }
 
 }  // namespace hn
-
-/* measurement aid: copies the timeline of one pass of cluster 0 (HN_TC_ABLATE & 8): 4 x 32 x 2 clock values */
-extern "C" int hn_debug_tc2_trace(long long* out_host) {
-  using namespace hn;
-  if (!out_host) return fail_arg("hn_debug_tc2_trace: null");
-  return check_cuda(cudaMemcpyFromSymbol(out_host, g_tc2_trace, sizeof(long long) * 4 * 32 * 4), "hn_debug_tc2_trace/read");
-}

@@ -1,0 +1,155 @@
+// Canonical field, tensor-core path (HN_PRECISION_BF16): weight packing and the C-ABI entry points of the forward.
+//
+//   hn_field_pack_bf16 / hn_field_repack_bf16   fp32 nn.Linear weights -> the bf16 UMMA shared-memory images the
+//                                               tcgen05 kernels stream (layout: DESIGN.md section 3)
+//   hn_field_fwd                                fp32 SIMT path (field_fp32.cu) or the cta_group::2 kernel (mlp_tc_2sm.cu)
+//
+// Reference semantics: embedders/hannw_fourier.py:38-49, embedders/fourier.py:9-38,
+// non_rigid_motion_mlps/mlp_offset.py:74-114, canonical_mlps/mlp_rgb_sigma.py:132-206.
+#include <cstdlib>
+
+#include "mlp_tc_plan.cuh"
+
+namespace hn {
+
+
+// ------------------------------------------------------------------------------------------
+// Weight packing
+// ------------------------------------------------------------------------------------------
+// one thread per 16-byte core-matrix row: image[(k/8) * (N*16) + n*16 .. +16] = W[n][k0+k .. +8]
+__global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs, const float* __restrict__ cond,
+                                    uint8_t* __restrict__ image) {
+  const int j = blockIdx.y;
+  if (j >= n_jobs) return;
+  const PackJob job = jobs[j];
+  const int units = job.n * (job.kc / 8);
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+    const int kg = u / job.n, n = u - kg * job.n;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kg * 8 + i;
+      float v = 0.0f;
+      if (n < job.valid_n) {
+        if (job.src && k < job.valid_k)
+          v = job.transpose ? job.src[(int64_t)(job.src_row0 + k) * job.src_ld + job.src_col0 + n]
+                            : job.src[(int64_t)n * job.src_ld + job.src_col0 + k];
+        if (k == job.bias_row) {
+          v = job.bias ? job.bias[n] : 0.0f;
+          if (job.fold_w && cond)
+            for (int c = 0; c < job.fold_k; ++c) v += job.fold_w[(int64_t)n * job.fold_ld + c] * cond[c];
+        }
+      }
+      f[i] = v;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    size_t dst = (size_t)kg * job.n * 16 + (size_t)n * 16;
+    if (job.split) {
+      const int nh = job.n >> 1, r = n >= nh ? 1 : 0;
+      dst = (size_t)r * (job.kc / 8) * nh * 16 + (size_t)kg * nh * 16 + (size_t)(n - r * nh) * 16;
+    }
+    *reinterpret_cast<uint4*>(image + job.w_off + dst) = o;
+  }
+}
+
+// mlp_tc_2sm.cu
+int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
+                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                     const TrainBufs* bufs, int sms, cudaStream_t st);
+
+int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples) {
+  TcPlan plan;
+  if (make_tc_plan(p, plan) != 0) return -1;
+  return carve_train_bufs(plan, n_samples, nullptr, nullptr) + 256;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" {
+
+int hn_has_tcgen05(void) { return 1; }
+
+int64_t hn_field_packed_bytes(const hn_field_params* p) {
+  TcPlan plan;
+  if (make_tc_plan(p, plan) != 0) return -1;
+  return (int64_t)plan.hdr.total_bytes;
+}
+
+int hn_field_pack_bf16(const hn_field_params* p, const float* cond, void* packed, void* stream) {
+  TcPlan plan;
+  HN_TRY(make_tc_plan(p, plan));
+  if (!packed) return fail_arg("hn_field_pack_bf16: null destination");
+  if (p->cond_dim > 0 && !cond) return fail_arg("hn_field_pack_bf16: cond missing");
+  for (int l = 0; l < p->nr_layers; ++l)
+    if (!p->nr_w[l] || !p->nr_b[l]) return fail_arg("hn_field_pack_bf16: null non-rigid layer %d", l);
+  for (int l = 0; l < p->cn_layers; ++l)
+    if (!p->cn_w[l] || !p->cn_b[l]) return fail_arg("hn_field_pack_bf16: null canonical layer %d", l);
+  cudaStream_t st = as_stream(stream);
+  uint8_t* dst = static_cast<uint8_t*>(packed);
+  // header, chunk table and job table are staged from pageable host memory: the copies are complete
+  // (staged) when cudaMemcpyAsync returns, so the vectors may die with this frame
+  HN_TRY(check_cuda(cudaMemcpyAsync(dst, &plan.hdr, sizeof(TcHeader), cudaMemcpyHostToDevice, st), "pack/header"));
+  HN_TRY(check_cuda(cudaMemcpyAsync(dst + plan.hdr.table_off, plan.chunks.data(),
+                                    plan.chunks.size() * sizeof(TcChunk), cudaMemcpyHostToDevice, st), "pack/table"));
+  HN_TRY(check_cuda(cudaMemcpyAsync(dst + plan.hdr.bwd_table_off, plan.bwd_chunks.data(),
+                                    plan.bwd_chunks.size() * sizeof(TcChunk), cudaMemcpyHostToDevice, st), "pack/bwd table"));
+  HN_TRY(check_cuda(cudaMemcpyAsync(dst + plan.jobs_off, plan.jobs.data(), plan.jobs.size() * sizeof(PackJob),
+                                    cudaMemcpyHostToDevice, st), "pack/jobs"));
+  dim3 grid(8, (unsigned)plan.jobs.size());
+  pack_weights_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const PackJob*>(dst + plan.jobs_off),
+                                            (int)plan.jobs.size(), cond, dst + plan.hdr.image_off);
+  return launched("hn_field_pack_bf16");
+}
+
+int hn_field_repack_bf16(const hn_field_params* p, const float* cond, void* packed, void* stream) {
+  TcPlan plan;
+  HN_TRY(make_tc_plan(p, plan));
+  if (!packed) return fail_arg("hn_field_repack_bf16: null image");
+  if (p->cond_dim > 0 && !cond) return fail_arg("hn_field_repack_bf16: cond missing");
+  uint8_t* dst = static_cast<uint8_t*>(packed);
+  dim3 grid(8, (unsigned)plan.jobs.size());
+  pack_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const PackJob*>(dst + plan.jobs_off),
+                                                           (int)plan.jobs.size(), cond, dst + plan.hdr.image_off);
+  return launched("hn_field_repack_bf16");
+}
+
+int hn_field_fwd_fp32(const hn_field_params* p, int64_t n_samples, const float* x_skel, const float* cond,
+                      const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                      void* workspace, int64_t workspace_bytes, int save_for_backward, void* stream);
+
+int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_skel, const float* cond,
+                 const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                 void* workspace, int64_t workspace_bytes, int save_for_backward, int precision,
+                 const void* packed, const int64_t* n_samples_dev, void* stream) {
+  if (precision == HN_PRECISION_FP32 && n_samples_dev)
+    return fail_arg("hn_field_fwd: a device-side sample count needs HN_PRECISION_BF16");
+  if (precision == HN_PRECISION_FP32)
+    return hn_field_fwd_fp32(p, n_samples, x_skel, cond, hann_w, ignore_non_rigid, raw, xyz, offsets, workspace,
+                             workspace_bytes, save_for_backward, stream);
+  if (precision != HN_PRECISION_BF16) return fail_arg("hn_field_fwd: unknown precision %d", precision);
+  if (!packed) return fail_arg("hn_field_fwd: bf16 path needs the image from hn_field_pack_bf16");
+  if (n_samples == 0) return 0;
+  if (n_samples < 0 || !x_skel || !raw || !xyz || !offsets) return fail_arg("hn_field_fwd: null pointer");
+  if (!ignore_non_rigid && !hann_w) return fail_arg("hn_field_fwd: hann_w missing");
+  TcPlan plan;
+  HN_TRY(make_tc_plan(p, plan));
+  int dev = 0, sms = 0;
+  HN_TRY(check_cuda(cudaGetDevice(&dev), "hn_field_fwd/device"));
+  HN_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "hn_field_fwd/attr"));
+  // the cta_group::2 kernel of mlp_tc_2sm.cu: CTA pairs share every weight chunk
+  if (sms < 2) return fail_arg("hn_field_fwd: the tcgen05 forward kernel needs a device with thread-block clusters");
+  TrainBufs bufs;
+  if (save_for_backward) {
+    const int64_t need = carve_train_bufs(plan, n_samples, static_cast<uint8_t*>(workspace), &bufs);
+    if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
+    if (!use_relu_bits()) memset(bufs.bits, 0, sizeof(bufs.bits));
+  }
+  return launch_field_tc2(plan, static_cast<const uint8_t*>(packed), n_samples, n_samples_dev, x_skel, hann_w,
+                          ignore_non_rigid ? 1 : 0, raw, xyz, offsets, save_for_backward ? &bufs : nullptr, sms,
+                          as_stream(stream));
+}
+
+}  // extern "C"

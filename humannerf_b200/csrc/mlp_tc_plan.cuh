@@ -123,21 +123,6 @@ struct PackJob {            // one per chunk, consumed by pack_weights_kernel
 
 static inline int round16(int v) { return (v + 15) & ~15; }
 
-// Forward kernel selection, read once per process (the forward part of the weight image depends on it):
-//   default            mlp_tc_2sm.cu  - CTA pairs, tcgen05.mma.cta_group::2, each CTA holds half of every weight chunk
-//   HN_TC_KERNEL=pair  mlp_tc.cu      - one CTA per SM, cta_group::1, two tiles share a 4 x 16 KB weight ring
-//   HN_TC_KERNEL=cluster mlp_tc_cl.cu - experimental multicast kernel (one tile per CTA)
-static inline int tc_kernel_mode() {
-  static const int v = [] {
-    const char* e = getenv("HN_TC_KERNEL");
-    if (e != nullptr && e[0] == 'c') return 2;
-    if (e != nullptr && e[0] == 'p') return 1;
-    return 0;
-  }();
-  return v;
-}
-static inline bool use_cluster_kernel() { return tc_kernel_mode() == 2; }
-static inline bool use_2sm_kernel() { return tc_kernel_mode() == 0; }
 // Ring geometry of the cta_group::2 kernel: 64 KB per CTA as 4 stages x 16 KB (default: chunks of up to 32 KB per
 // pair = 4 MMAs at N = 256, so the ~500 clk an issuer spends per chunk stay below the chunk's tensor-pipe time) or,
 // with HN_TC_2SM_STAGES=8, 8 stages x 8 KB (the chunk table of the tile-pair kernel).
@@ -171,7 +156,7 @@ static inline int use_leader_stores(bool backward) {
 }
 // largest weight chunk (bytes, both halves) for the selected kernel family (forward and backward-data chain)
 static inline uint32_t fwd_chunk_bytes() {
-  return use_2sm_kernel() ? 2u * (65536u / (uint32_t)tc2_stages()) : kStageBytes;
+  return 2u * (65536u / (uint32_t)tc2_stages());
 }
 
 struct TcPlan {
@@ -214,9 +199,6 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
     const uint32_t chunk_cap = fwd_chunk_bytes();      // forward and backward tables share the kernel family
     int kc_max = (int)(chunk_cap / (uint32_t)(n * 2)) / 16 * 16;
     if (kc_max > 240) kc_max = 240;                       // ksteps is a uint8
-    // for the experimental cluster kernel (HN_TC_KERNEL=cluster, mlp_tc_cl.cu) forward chunks never span
-    // more than one 32-column block of the A operand: it hands the operand over block by block
-    if (&table == &plan.chunks && kc_max > 32 && use_cluster_kernel()) kc_max = 32;
     for (int k0 = 0; k0 < k_pad; k0 += kc_max) {
       const int kc = std::min(kc_max, k_pad - k0);
       TcChunk c;
@@ -232,7 +214,7 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
       j.src = W; j.src_ld = ldw; j.valid_n = valid_n; j.n = n; j.kc = kc; j.w_off = w_off;
       j.valid_k = std::max(0, valid_k - k0);
       j.transpose = transpose ? 1 : 0;
-      j.split = use_2sm_kernel() ? 1 : 0;
+      j.split = 1;                                        // two half images, one per CTA of the pair
       if (transpose) { j.src_col0 = col0; j.src_row0 = row0 + k0; }
       else { j.src_col0 = col0 + k0; j.src_row0 = 0; }
       j.bias_row = -1;

@@ -37,14 +37,6 @@ const char* hn_last_error(void);
 int64_t hn_launch_count(void);
 /* 1 if the tcgen05/TMEM fused-MLP kernel was compiled in (sm_100a build). */
 int hn_has_tcgen05(void);
-/* Measurement aid: with the environment variable HN_TC_ABLATE & 8 set, block 0 of the tcgen05 forward
- * kernel accumulates cycle counters per role; this copies the 32 counters to the host and clears them. */
-int hn_debug_tc_prof(unsigned long long* out_host);
-/* same for the cluster kernel (16 counters) */
-int hn_debug_tcc_prof(unsigned long long* out_host);
-/* Measurement aid (HN_TC_ABLATE & 8): timeline of one pass of cluster 0 of the cta_group::2 forward kernel,
- * 4 roles x 32 layers x 2 clock values (layout in csrc/mlp_tc_2sm.cu). */
-int hn_debug_tc2_trace(long long* out_host);
 
 /* ------------------------------------------------------------------------------------------
  * a1  core/utils/camera_util.py:132-159  get_rays_from_KRT

@@ -42,39 +42,3 @@ with torch.no_grad():
 print(f'frame {ev0.elapsed_time(ev1) / args.reps:.2f} ms, culled fraction {net.last_cull_fraction:.3f}, max |rgb - dense| '
       f'{float((out["rgb"] - ref["rgb"]).abs().max()):.2e}, max |alpha - dense| {float((out["alpha"] - ref["alpha"]).abs().max()):.2e}')
 print({k: round(v[0] / args.reps, 3) for k, v in t.items()}, 'TFLOP/s', round(1184768.0 * P / (t['field_fwd_bf16'][0] / args.reps * 1e-3) / 1e12, 1))
-
-if int(os.environ.get('HN_TC_ABLATE', '0')) & 8 and not os.environ.get('HN_TC_KERNEL'):
-    import ctypes
-    from humannerf_b200 import _lib
-    lib = _lib.load()
-    buf = (ctypes.c_longlong * 512)()
-    lib.hn_debug_tc2_trace.restype = ctypes.c_int
-    _lib.check(lib.hn_debug_tc2_trace(buf), 'trace')
-    v = np.array(list(buf), dtype=np.int64).reshape(4, 32, 4)
-    t0 = v[:, :, :2][v[:, :, :2] > 0].min()
-    print('timeline of one pass of cluster 0 (clk since the first event); per layer: issuer X [ready, issued]  issuer Y [ready, issued]  '
-          'epi X [acc seen, handed over]  epi Y [acc seen, handed over]')
-    for l in range(15):
-        print(f'  layer {l:2d}: ' + '   '.join(f'[{(v[r, l, 0] - t0) if v[r, l, 0] else -1:7d} {(v[r, l, 1] - t0) if v[r, l, 1] else -1:7d}]' for r in range(4)) + f'   X wait-w/issue {v[0, l, 2]:5d} {v[0, l, 3]:5d}  Y {v[1, l, 2]:5d} {v[1, l, 3]:5d}')
-    sys.exit(0)
-if int(os.environ.get('HN_TC_ABLATE', '0')) & 8:
-    import ctypes
-    from humannerf_b200 import _lib
-    buf = (ctypes.c_ulonglong * 32)()
-    _lib.check(_lib.load().hn_debug_tc_prof(buf), 'prof')
-    v = [int(x) for x in buf]
-    names = {0: 'producer total', 1: 'producer wait-empty', 4: 'issuer0 total', 5: 'issuer0 wait a_ready', 6: 'issuer0 wait full',
-             7: 'issuer0 issue', 10: 'issuer1 total', 11: 'issuer1 wait a_ready', 12: 'issuer1 wait full', 13: 'issuer1 issue',
-             16: 'epi total', 17: 'epi wait acc', 18: 'epi encoding', 19: 'epi hidden work'}
-    if sum(v):
-        for k, n in names.items():
-            print(f'  {n:24s} {v[k] / 1e6:10.2f} Mcyc')
-    buf2 = (ctypes.c_ulonglong * 16)()
-    _lib.check(_lib.load().hn_debug_tcc_prof(buf2), 'prof')
-    v = [int(x) for x in buf2]
-    names = {0: 'producer total', 1: 'producer wait-empty', 4: 'issuer total', 5: 'issuer wait block/pe', 6: 'issuer wait full',
-             7: 'issuer issue', 8: 'epi total', 9: 'epi wait acc', 11: 'epi hidden blocks'}
-    if sum(v):
-        print(' cluster kernel:')
-        for k, n in names.items():
-            print(f'  {n:24s} {v[k] / 1e6:10.2f} Mcyc')

@@ -2,7 +2,7 @@
 
 Same graph as `oracle.humannerf_oracle.non_rigid_mlp` / `canonical_mlp` (reference
 `mlp_offset.py:74-114`, `mlp_rgb_sigma.py:132-206`) with the rounding points of
-`humannerf_b200/csrc/mlp_tc.cu` / `mlp_tc_bwd.cu`:
+`humannerf_b200/csrc/mlp_tc_2sm.cu` / `mlp_tc_bwd_2sm.cu`:
 
 * weights, biases (the first non-rigid bias with the condition code folded in) and encodings are
   rounded to bf16, products accumulate in fp32;

@@ -399,7 +399,7 @@ def test_relu_mask_images_match_activation_read(tmp_path, P, ignore):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, 'tests'))
     import relu_bits_ab as ab
-    assert os.environ.get('HN_TC_RELU_BITS', '1') != '0' and os.environ.get('HN_TC_KERNEL', '') in ('', '2sm')
+    assert os.environ.get('HN_TC_RELU_BITS', '1') != '0'
     got = ab.field_grads(P, ignore)
     out = str(tmp_path / 'read_h.npz')
     # ... and with the image stores as 256-byte bulk copies instead of 2 KB tensor-map copies (store_blocks modes 1 / 4)
@@ -420,23 +420,19 @@ def test_relu_mask_images_match_activation_read(tmp_path, P, ignore):
     print(f'[parity] ReLU mask images vs activation read [P={P},ignore={ignore}]: worst rel L2 over {len(want.files)} tensors {worst:.2e}')
 
 
-@pytest.mark.parametrize('variant', ['pair', 'cluster', '2sm-8-stages', 'read-activations'])
+@pytest.mark.parametrize('variant', ['2sm-8-stages', 'read-activations'])
 def test_other_forward_kernels_parity(variant):
-    """The default tcgen05 forward kernel is the cta_group::2 kernel of csrc/mlp_tc_2sm.cu with a 4 x 16 KB ring.
-    The other forward kernels must pass the same forward parity and training tests: HN_TC_KERNEL=pair (csrc/mlp_tc.cu,
-    one CTA per SM, cta_group::1), HN_TC_KERNEL=cluster (csrc/mlp_tc_cl.cu, experimental: TMA multicast of the
-    weight stream across a CTA pair, double-buffered TMEM accumulators, block-granular operand hand-over) and the
-    cta_group::2 kernel with an 8 x 8 KB ring (HN_TC_2SM_STAGES=8).  The choice is read once per process (the
-    forward part of the weight image depends on it), hence the subprocess."""
+    """The tcgen05 forward kernel is the cta_group::2 kernel of csrc/mlp_tc_2sm.cu with a 4 x 16 KB ring.  Its two
+    build-time-equivalent variants must pass the same forward parity and training tests: an 8 x 8 KB ring
+    (HN_TC_2SM_STAGES=8) and the backward chain masking with the stored activations instead of the 1-bit images
+    (HN_TC_RELU_BITS=0).  The choice is read once per process (the weight image depends on it), hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
     if variant == '2sm-8-stages':
         env['HN_TC_2SM_STAGES'] = '8'
-    elif variant == 'read-activations':
-        env['HN_TC_RELU_BITS'] = '0'      # backward chain masks with the stored activations instead of the 1-bit images
     else:
-        env['HN_TC_KERNEL'] = variant
+        env['HN_TC_RELU_BITS'] = '0'      # backward chain masks with the stored activations instead of the 1-bit images
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', '-k',
                         'field_bf16_forward or network_eval_bf16 or field_bf16_backward',
                         os.path.join(root, 'tests')], env=env, cwd=root, capture_output=True, text=True, timeout=900)
