@@ -300,11 +300,11 @@ int hn_field_fwd_fp32(const hn_field_params* p, int64_t n_samples, const float* 
                       void* workspace, int64_t workspace_bytes, int save_for_backward, void* stream) {
   FieldPlan fp;
   HN_TRY(make_plan(p, fp));
+  if (n_samples == 0) return 0;        // an empty chunk (all samples culled) has empty tensors: nothing to check or do
   if (n_samples < 0 || !x_skel || !raw || !xyz || !offsets || !workspace)
     return fail_arg("hn_field_fwd: null pointer or negative size");
   if (!ignore_non_rigid && ((p->cond_dim > 0 && !cond) || (p->nr_freqs > 0 && !hann_w)))
     return fail_arg("hn_field_fwd: cond / hann_w missing");
-  if (n_samples == 0) return 0;
   const bool save = save_for_backward != 0;
   const int64_t rows = chunk_samples(n_samples, save);
   if (workspace_bytes < fp.floats_per_sample * rows * (int64_t)sizeof(float))
@@ -385,9 +385,9 @@ int hn_field_bwd(const hn_field_params* p, const hn_field_grads* g, int64_t n_sa
                  int64_t workspace_bytes, void* scratch, int64_t scratch_bytes, void* stream) {
   FieldPlan fp;
   HN_TRY(make_plan(p, fp));
+  if (n_samples == 0) return 0;
   if (!g || n_samples < 0 || !x_skel || !d_raw || !d_x_skel || !workspace || !scratch)
     return fail_arg("hn_field_bwd: null pointer or negative size");
-  if (n_samples == 0) return 0;
   const int64_t n = n_samples, rows = n_samples;
   if (workspace_bytes < fp.floats_per_sample * rows * (int64_t)sizeof(float))
     return fail_arg("hn_field_bwd: workspace is not a save_for_backward workspace of this size");

@@ -135,6 +135,14 @@ class Network(nn.Module):
                 mlp_depth=cfg.pose_decoder.mlp_depth)
 
         nr, cn = self.non_rigid_mlp.module, self.cnl_mlp.module
+        # the fused field kernels plan exactly one skip connection per MLP (what every reference config uses);
+        # more would silently read the wider Linears with the wrong K
+        for name, mod, cats in (('non_rigid_motion_mlp', nr, getattr(nr, 'layers_to_cat_inputs', [])),
+                                ('canonical_mlp', cn, getattr(cn, 'layers_to_cat_input', []))):
+            if len(cats) > 1:
+                raise NotImplementedError(
+                    f'humannerf_b200.Network: `{name}.skips` with {len(cats)} skip connections is not supported by '
+                    f'the fused field kernels (one skip per MLP)')
         self._spec = ops.FieldSpec(
             nr_layers=len(nr.linear_layers()), nr_width=nr_cfg.mlp_width, nr_skip=nr.skip_layer_index(),
             nr_freqs=nr_cfg.multires, cond_dim=nr_cfg.condition_code_size,

@@ -16,6 +16,7 @@ pose-decoder graphs, which gives the same parameter gradients as cut A up to fp3
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Sequence, Tuple
 
 import torch
@@ -96,6 +97,12 @@ class CutBReducer:
             loss.backward(inputs=red.leaf_inputs())   # -> grads of MLP params + boundary tensors
         red.allreduce()                        # one bucket
         red.finish_backward()                  # local backward through decoder / FK / pose decoder
+
+    Precondition: every rank renders rays of the SAME frame in a step (same `dst_posevec`, priors, parameters), as
+    SURVEY 8e's split of one step over ranks does.  Summing boundary gradients and back-propagating the sum through
+    this rank's own front end is only the true gradient then.  `check_same_frame` asserts it (one tiny all-reduce;
+    enabled by HN_CHECK_SAME_FRAME=1 or the `check` argument) - with per-rank frames use an all-reduce of the
+    parameter gradients instead (cut A).
     """
 
     MLP_PREFIXES = ('non_rigid_mlp.', 'cnl_mlp.')
@@ -110,12 +117,26 @@ class CutBReducer:
         motion_scale_Rs, motion_Ts) whose gradients are exchanged instead of their producers'."""
         self.boundary = dict(tensors)
 
+    def check_same_frame(self, group=None) -> None:
+        """Raise unless the boundary tensors (functions of the frame and the replicated parameters only) are
+        identical on every rank: max over ranks of a checksum equals its min."""
+        if not self.boundary or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        sums = torch.stack([t.detach().double().sum() for t in self.boundary.values()])
+        pair = torch.stack([sums, -sums])
+        dist.all_reduce(pair, op=dist.ReduceOp.MAX, group=group)
+        if not torch.equal(pair[0], -pair[1]):
+            raise RuntimeError('CutBReducer: ranks hold different frames / front-end outputs in this step; the cut-B '
+                               'gradient exchange needs the same frame on every rank (use cut A otherwise)')
+
     def leaf_inputs(self) -> List[torch.Tensor]:
         return self.mlp_params + list(self.boundary.values())
 
     def exchange_and_finish(self, loss: torch.Tensor, group=None) -> int:
         """Backward to the boundary, one bucketed all-reduce, then the replicated tail.
         Returns the number of floats exchanged."""
+        if os.environ.get('HN_CHECK_SAME_FRAME', '0') == '1' and not torch.cuda.is_current_stream_capturing():
+            self.check_same_frame(group)
         leaves = self.leaf_inputs()
         grads = torch.autograd.grad(loss, leaves, retain_graph=True, allow_unused=True)
         grads = [torch.zeros_like(t) if g is None else g.contiguous() for g, t in zip(grads, leaves)]

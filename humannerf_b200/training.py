@@ -138,6 +138,7 @@ class FusedAdam(torch.optim.Optimizer):
         for p in ps:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4                # keep every view 16-byte aligned
+        self._offs = offs
         self._flat_m = torch.zeros(total, device=dev)
         self._flat_v = torch.zeros(total, device=dev)
         self.step_dev = torch.zeros(n_t, device=dev)             # per-tensor step counts (floats)
@@ -170,6 +171,33 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _lrs(self):
         return [float(g['lr']) for g in self.param_groups for _ in g['params']]
+
+    def _adopt_state(self) -> None:
+        """Copy whatever `self.state` holds (e.g. tensors a checkpoint brought in) into the flat moment buffers and the
+        device step counts the kernel reads, and point `state[p]` back at views of them."""
+        with torch.no_grad():
+            for i, p in enumerate(self._ps):
+                o, n = self._offs[i], p.numel()
+                views = {'step': self.step_dev[i:i + 1],
+                         'exp_avg': torch.as_strided(self._flat_m[o:o + n], p.shape, p.stride()),
+                         'exp_avg_sq': torch.as_strided(self._flat_v[o:o + n], p.shape, p.stride())}
+                st = self.state.get(p, {})
+                for k, view in views.items():
+                    src = st.get(k)
+                    if src is None:
+                        view.zero_()
+                    elif not (torch.is_tensor(src) and src.data_ptr() == view.data_ptr()):
+                        src = torch.as_tensor(src, dtype=torch.float32, device=view.device)
+                        view.copy_(src.reshape(view.shape) if src.numel() == view.numel() else src)
+                self.state[p] = views
+        self._lr_cache = None                  # param_groups came from the checkpoint: re-upload the learning rates
+
+    def load_state_dict(self, state_dict) -> None:
+        """`torch.optim.Optimizer.load_state_dict` replaces `self.state` with the checkpoint's own tensors (the
+        reference trainer resumes this way, trainer.py:377); the kernel reads the flat buffers, so the loaded
+        moments and step counts are copied into them.  Accepts checkpoints of `torch.optim.Adam` too."""
+        super().load_state_dict(state_dict)
+        self._adopt_state()
 
     def _sync_lr(self):
         lrs = self._lrs()
@@ -297,7 +325,12 @@ class GraphedTrainStep:
         nf = int(cfg.non_rigid_motion_mlp.multires)
         self._nf = nf
         self.sched = torch.zeros(nf + 2, device=dev)                  # [hann (nf) | cond gate | lr scale]
-        self._sched_host = torch.zeros(nf + 2).pin_memory()
+        # pinned staging for the schedule: the host runs ahead of the GPU (a replay is one launch), so a single
+        # buffer could be overwritten for step k+1 before the copy of step k has executed.  A small ring, each
+        # slot guarded by the event recorded after its copy.
+        self._sched_ring = [(torch.zeros(nf + 2).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+        self._sched_slot = 0
+        self.loaded = torch.cuda.Event()
         opt.lr_scale = self.sched[nf + 1:nf + 2]
         self._base_lrs = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -310,11 +343,14 @@ class GraphedTrainStep:
         from humannerf_b200.embedders.hannw_fourier import hann_window_weights
         cfg = get_cfg()
         nr = cfg.non_rigid_motion_mlp
-        h = self._sched_host
+        h, ev = self._sched_ring[self._sched_slot]
+        self._sched_slot = (self._sched_slot + 1) % len(self._sched_ring)
+        ev.synchronize()                       # the copy that last used this slot has executed (no-op if never recorded)
         h[:self._nf] = hann_window_weights(iter_step, self._nf, nr.kick_in_iter, nr.full_band_iter)
         h[self._nf] = 0.0 if iter_step < nr.kick_in_iter else 1.0
         h[self._nf + 1] = 0.1 ** (iter_step / (cfg.train.lrate_decay * 1000))      # exp_decay.py:7-16
         self.sched.copy_(h, non_blocking=True)
+        ev.record()
         pose_on = (not cfg.pose_decoder_off) and iter_step >= cfg.pose_decoder.get('kick_in_iter', 0)
         if self._iter_cfg is None:
             self._iter_cfg = pose_on
@@ -323,7 +359,9 @@ class GraphedTrainStep:
             self._iter_cfg = pose_on
 
     def load(self, batch: Dict[str, torch.Tensor]) -> None:
-        """Copy a padded batch (host pinned or device tensors) into the static input buffers."""
+        """Copy a padded batch (host pinned or device tensors) into the static input buffers.  The copies are
+        asynchronous: a caller that REUSES pinned host buffers must not overwrite them before `self.loaded` (the
+        event recorded after the copies) has completed - `loaded.synchronize()`; fresh buffers per step need nothing."""
         if batch['near'].shape[0] != self.cap:
             raise RuntimeError(f'GraphedTrainStep: batch has {batch["near"].shape[0]} rays, expected the padded '
                                f'{self.cap} (data.make_train_batch(pad_rays=True))')
@@ -332,6 +370,7 @@ class GraphedTrainStep:
         self.far.copy_(batch['far'], non_blocking=True)
         self.index.copy_(batch['scatter_index'], non_blocking=True)
         self.targets.copy_(batch['target_patches'], non_blocking=True)
+        self.loaded.record()
 
     # -- the step -----------------------------------------------------------------------
     def _body(self, iter_step: int) -> torch.Tensor:

@@ -298,6 +298,52 @@ def test_fused_adam_matches_torch_adam(ops):
         err = float((p - q).abs().max())
         print(f'[parity] fused adam tensor {i} {tuple(p.shape)}: max abs err {err:.3e}')
         assert torch.allclose(q, p, rtol=1e-5, atol=2e-6), (i, err)
+
+
+@pytest.mark.parametrize('source', ['fused', 'torch'])
+def test_fused_adam_resume_from_state_dict(ops, source):
+    """Checkpoint resume (reference trainer.py:362-377: `optimizer.state_dict()` saved, `load_state_dict` on resume).
+    After 3 steps the optimizer state is saved - from a FusedAdam or from a torch.optim.Adam (a reference checkpoint) -
+    and loaded into a FRESH FusedAdam; 3 more steps must land where an uninterrupted torch.optim.Adam lands.  A resume
+    that dropped the moments / step counts would restart the bias correction at t = 1 and move every parameter by
+    ~lr * sign(g): caught at 2e-6 + 1e-5 |ref|."""
+    import copy, io
+    from humannerf_b200.training import FusedAdam
+    g = torch.Generator().manual_seed(11)
+    shapes = [(7,), (300, 41), (8192 + 5,), (64, 64)]
+    lrs = [1e-3, 5e-4, 5e-5, 2e-3]
+    p0 = [torch.randn(*s, generator=g) for s in shapes]
+    grads = [[torch.randn(*s, generator=g) for s in shapes] for _ in range(6)]
+    mk = lambda ps: [{'params': [p], 'lr': lr, 'name': f't{i}'} for i, (p, lr) in enumerate(zip(ps, lrs))]
+    ref_p = [p.clone().to(DEV).requires_grad_() for p in p0]
+    ref = torch.optim.Adam(mk(ref_p), betas=(0.9, 0.999))
+    a_p = [p.clone().to(DEV).requires_grad_() for p in p0]
+    first = FusedAdam(mk(a_p), betas=(0.9, 0.999)) if source == 'fused' else torch.optim.Adam(mk(a_p), betas=(0.9, 0.999))
+    for step in range(3):
+        for p, q, gr in zip(ref_p, a_p, grads[step]):
+            p.grad, q.grad = gr.to(DEV), gr.to(DEV)
+        ref.step()
+        first.step()
+    # through a byte stream, like torch.save / torch.load of the reference's checkpoints
+    buf = io.BytesIO()
+    torch.save({'opt': first.state_dict(), 'params': [p.detach() for p in a_p]}, buf)
+    buf.seek(0)
+    ckpt = torch.load(buf, map_location='cpu')
+    b_p = [p.clone().to(DEV).requires_grad_() for p in ckpt['params']]
+    resumed = FusedAdam(mk(b_p), betas=(0.9, 0.999))
+    resumed.load_state_dict(ckpt['opt'])
+    assert float(resumed.step_dev.min()) == 3.0 and float(resumed._flat_m.abs().max()) > 0
+    assert all(resumed.state[p]['exp_avg'].data_ptr() >= resumed._flat_m.data_ptr() for p in b_p)
+    for step in range(3, 6):
+        for p, q, gr in zip(ref_p, b_p, grads[step]):
+            p.grad, q.grad = gr.to(DEV), gr.to(DEV)
+        ref.step()
+        resumed.step()
+    torch.cuda.synchronize()
+    for i, (p, q) in enumerate(zip(ref_p, b_p)):
+        err = float((p - q).abs().max())
+        print(f'[parity] fused adam resumed from a {source} checkpoint, tensor {i}: max abs err {err:.3e}')
+        assert torch.allclose(q, p, rtol=1e-5, atol=2e-6), (i, err)
         assert float(our.state[q]['step']) == float(ref.state[p]['step'])
         assert torch.allclose(our.state[q]['exp_avg'], ref.state[p]['exp_avg'], rtol=1e-4, atol=1e-7)
         assert torch.allclose(our.state[q]['exp_avg_sq'], ref.state[p]['exp_avg_sq'], rtol=1e-4, atol=1e-9)
