@@ -1,6 +1,8 @@
-// LPIPS "head" of one trunk stage, fused (a16: trainer.py:97-113 get_img_rebuild_loss -> third_parties/lpips/lpips.py:
-// normalize_tensor (:10-12), squared difference, 1x1 non-negative `lin` layer, spatial_average (:14-15)):
-//   out[i] += (1 / HW) * sum_p sum_c lin[c] * ( fx[i,c,p] / (||fx[i,:,p]|| + eps) - fy[i,c,p] / (||fy[i,:,p]|| + eps) )^2
+// LPIPS "head" of one trunk stage, fused (a16: trainer.py:97-113 get_img_rebuild_loss -> third_parties/lpips/lpips.py
+// :78-92: normalize_tensor (third_parties/lpips/__init__.py:40-42 - this fork's variant with eps INSIDE and outside
+// the root: f / (sqrt(sum_c f^2 + eps) + eps), eps = 1e-10), squared difference, 1x1 non-negative `lin` layer,
+// spatial_average (lpips.py:14-15)):
+//   out[i] += (1 / HW) * sum_p sum_c lin[c] * ( fx[i,c,p] / nx - fy[i,c,p] / ny )^2,   nx = sqrt(||fx[i,:,p]||^2 + eps) + eps
 // for n image pairs whose features are the two halves of ONE (2n, C, H, W) tensor (prediction rows first), any
 // dense strides (cuDNN hands back NHWC).  One warp per (pair, position): lanes stride over the channels, two
 // passes over C (norms, then the weighted squared difference), warp-shuffle reductions, one atomicAdd per warp.
@@ -25,7 +27,7 @@ lpips_head_fwd_kernel(int n, int C, int HW, const float* __restrict__ f, int64_t
     sx += a * a; sy += b * b;
   }
   sx = warp_sum(sx); sy = warp_sum(sy);
-  const float ix = 1.0f / (sqrtf(sx) + kLpipsEps), iy = 1.0f / (sqrtf(sy) + kLpipsEps);
+  const float ix = 1.0f / (sqrtf(sx + kLpipsEps) + kLpipsEps), iy = 1.0f / (sqrtf(sy + kLpipsEps) + kLpipsEps);
   float acc = 0.f;
   for (int c = lane; c < C; c += 32) {
     const float d = fx[(int64_t)c * s_c] * ix - fy[(int64_t)c * s_c] * iy;
@@ -36,9 +38,9 @@ lpips_head_fwd_kernel(int n, int C, int HW, const float* __restrict__ f, int64_t
 }
 
 // df = g[i] / HW * d(out[i]) / df for both halves:
-//   d_c = fx_c / nx - fy_c / ny,  A = sum_k 2 lin_k d_k fx_k,  B = sum_k 2 lin_k d_k fy_k   (nx = ||fx|| + eps)
-//   dfx_c = g ( 2 lin_c d_c / nx - fx_c A / (nx^2 ||fx||) ),  dfy_c = g ( -2 lin_c d_c / ny + fy_c B / (ny^2 ||fy||) )
-// (the second terms vanish with the feature vector: where torch's sqrt'(0) yields NaN this yields 0)
+//   d_c = fx_c / nx - fy_c / ny,  A = sum_k 2 lin_k d_k fx_k,  B = sum_k 2 lin_k d_k fy_k,  rx = sqrt(||fx||^2 + eps), nx = rx + eps
+//   dfx_c = g ( 2 lin_c d_c / nx - fx_c A / (nx^2 rx) ),  dfy_c = g ( -2 lin_c d_c / ny + fy_c B / (ny^2 ry) )
+// (rx >= 1e-5: an all-zero feature vector - common after a ReLU - has the finite slope 1 / nx, as in the reference)
 __global__ void __launch_bounds__(256)
 lpips_head_bwd_kernel(int n, int C, int HW, const float* __restrict__ f, int64_t s_n, int64_t s_c, int64_t s_p,
                       const float* __restrict__ lin, const float* __restrict__ g_out, float* __restrict__ df) {
@@ -52,7 +54,7 @@ lpips_head_bwd_kernel(int n, int C, int HW, const float* __restrict__ f, int64_t
     sx += a * a; sy += b * b;
   }
   sx = warp_sum(sx); sy = warp_sum(sy);
-  const float rx = sqrtf(sx), ry = sqrtf(sy);
+  const float rx = sqrtf(sx + kLpipsEps), ry = sqrtf(sy + kLpipsEps);
   const float ix = 1.0f / (rx + kLpipsEps), iy = 1.0f / (ry + kLpipsEps);
   float A = 0.f, B = 0.f;
   for (int c = lane; c < C; c += 32) {
@@ -62,7 +64,7 @@ lpips_head_bwd_kernel(int n, int C, int HW, const float* __restrict__ f, int64_t
   }
   A = warp_sum(A); B = warp_sum(B);
   const float g = __ldg(g_out + i) / (float)HW;
-  const float kx = rx > 0.f ? A * ix * ix / rx : 0.f, ky = ry > 0.f ? B * iy * iy / ry : 0.f;
+  const float kx = A * ix * ix / rx, ky = B * iy * iy / ry;
   for (int c = lane; c < C; c += 32) {
     const float a = f[ox + (int64_t)c * s_c], b = f[oy + (int64_t)c * s_c];
     const float t = 2.0f * __ldg(lin + c) * (a * ix - b * iy);

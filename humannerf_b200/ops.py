@@ -628,7 +628,7 @@ def ptr_any(t: torch.Tensor) -> int:
 
 
 def lpips_head(feat: torch.Tensor, lin: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """LPIPS head of one trunk stage (third_parties/lpips/lpips.py:10-15, 78-92): `feat` (2n, C, H, W) holds the
+    """LPIPS head of one trunk stage (third_parties/lpips/__init__.py:40-42, lpips.py:14-15, 78-92): `feat` (2n, C, H, W) holds the
     features of n predictions followed by their n targets; returns `out` (n,) + the stage's spatially averaged,
     `lin`-weighted squared difference of the unit-normalised features (`out` None: starts from zero)."""
     return _LpipsHead.apply(feat.float(), _f32c(lin).reshape(-1), out)

@@ -7,12 +7,21 @@ each rank runs the whole per-ray path on its slice, and
 * training needs an all_gather of the rendered rgb (so every rank evaluates the identical
   patch loss) and ONE bucketed all-reduce of the gradients per step.
 
+Two ways to split a training step (bench.py --scaling):
+  strong  ONE step's rays (<= n_patches * patch^2) are split contiguously over the ranks: forward on the
+          local slice, all_gather of the rendered rgb (GatherRowsWithGrad: 12 B / ray), the identical patch loss on
+          every rank, backward into the local rows only, gradients SUMMED over ranks;
+  weak    every rank renders its own patches of the same frame; loss / world, gradients summed = the mean.
+
 The all-reduce is cut at the replicated-input boundary ("cut B"): the summed tensors are the MLP
 parameter gradients (595 207 floats), d(motion-weight volume) (819 200 floats) and
 d(motion_scale_Rs, motion_Ts) (288 floats) - 5.7 MB instead of the 257.7 MB of all 64.4 M
 parameter gradients ("cut A", 63.6 M of which belong to the volume decoder).  Every rank then
 back-propagates the summed volume / pose gradients through its identical decoder, FK and
 pose-decoder graphs, which gives the same parameter gradients as cut A up to fp32 summation order.
+The exchange is two buckets: the boundary gradients (3.3 MB) are on the critical path of the replicated tail; the
+MLP parameter gradients (2.4 MB) are only consumed by the optimizer, so their all-reduce is issued asynchronously and
+waited for after the tail's backward - it runs under the decoder backward.
 """
 from __future__ import annotations
 
@@ -40,6 +49,19 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
         return local
     world = dist.get_world_size(group)
     sizes = shard_sizes(n_total, world)
+    if local.is_cuda and dist.get_backend(group) == 'gloo':
+        # gloo moves CUDA tensors only through all_reduce / broadcast (single-GPU test rigs): every rank adds its
+        # rows into a zero buffer - same result as the gather
+        out = local.new_zeros((n_total,) + tuple(local.shape[1:]))
+        a = sum(sizes[:dist.get_rank(group)])
+        out[a:a + local.shape[0]] = local
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+    if min(sizes) == max(sizes):
+        # equal slices: one collective straight into the result, no padding and no concatenation
+        out = local.new_empty((n_total,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = max(sizes)
     buf = local.new_zeros((pad,) + tuple(local.shape[1:]))
     buf[:local.shape[0]] = local
@@ -78,14 +100,55 @@ def unflatten_bucket(flat: torch.Tensor, like: Sequence[torch.Tensor]) -> List[t
     return out
 
 
-def allreduce_bucket(tensors: Sequence[torch.Tensor], group=None) -> None:
-    """Sum `tensors` over ranks with one flat all-reduce (in place)."""
+def allreduce_bucket(tensors: Sequence[torch.Tensor], group=None, async_op: bool = False):
+    """Sum `tensors` over ranks with one flat all-reduce (in place).  With `async_op` the collective is only
+    enqueued; the returned callable waits for it (on the current stream) and copies the sums back."""
     if not tensors or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return
+        return (lambda: None) if async_op else None
     flat = flatten_bucket(tensors)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    for t, v in zip(tensors, unflatten_bucket(flat, tensors)):
-        t.copy_(v)
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    def finish():
+        if work is not None:
+            work.wait()
+        for t, v in zip(tensors, unflatten_bucket(flat, tensors)):
+            t.copy_(v)
+    if async_op:
+        return finish
+    finish()
+    return None
+
+
+def broadcast_parameters(network: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Overwrite every rank's parameters with rank `src`'s.  Replicas that apply the same summed gradients stay
+    identical only as long as every replicated kernel is deterministic; call this at start-up (after loading a
+    checkpoint) and every few thousand steps to cancel any drift."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for p in network.parameters():
+            if p.is_contiguous():
+                dist.broadcast(p, src=src, group=group)
+            else:                                       # channels_last_3d decoder weights: broadcast the storage order
+                flat = torch.as_strided(p, (p.numel(),), (1,)) if p.dim() == 5 and \
+                    p.is_contiguous(memory_format=torch.channels_last_3d) else p.contiguous().view(-1)
+                dist.broadcast(flat, src=src, group=group)
+                if flat.data_ptr() != p.data_ptr():
+                    p.copy_(flat.view_as(p))
+
+
+def max_parameter_divergence(network: torch.nn.Module, group=None) -> float:
+    """max over parameters and ranks of |p_rank - p_rank0| (0.0 = the replicas are bit-identical)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0.0
+    worst = torch.zeros(1, device=next(network.parameters()).device)
+    with torch.no_grad():
+        for p in network.parameters():
+            ref = p.detach().clone()
+            dist.broadcast(ref, src=0, group=group)
+            worst = torch.maximum(worst, (p.detach() - ref).abs().max().reshape(1))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+    return float(worst)
 
 
 class CutBReducer:
@@ -101,7 +164,7 @@ class CutBReducer:
     Precondition: every rank renders rays of the SAME frame in a step (same `dst_posevec`, priors, parameters), as
     SURVEY 8e's split of one step over ranks does.  Summing boundary gradients and back-propagating the sum through
     this rank's own front end is only the true gradient then.  `check_same_frame` asserts it (one tiny all-reduce;
-    enabled by HN_CHECK_SAME_FRAME=1 or the `check` argument) - with per-rank frames use an all-reduce of the
+    run before every eager exchange with HN_CHECK_SAME_FRAME=1) - with per-rank frames use an all-reduce of the
     parameter gradients instead (cut A).
     """
 
@@ -132,24 +195,30 @@ class CutBReducer:
     def leaf_inputs(self) -> List[torch.Tensor]:
         return self.mlp_params + list(self.boundary.values())
 
-    def exchange_and_finish(self, loss: torch.Tensor, group=None) -> int:
-        """Backward to the boundary, one bucketed all-reduce, then the replicated tail.
+    def exchange_and_finish(self, loss: torch.Tensor, group=None, overlap: bool = True) -> int:
+        """Backward to the boundary, the two bucketed all-reduces, then the replicated tail.
         Returns the number of floats exchanged."""
         if os.environ.get('HN_CHECK_SAME_FRAME', '0') == '1' and not torch.cuda.is_current_stream_capturing():
             self.check_same_frame(group)
         leaves = self.leaf_inputs()
         grads = torch.autograd.grad(loss, leaves, retain_graph=True, allow_unused=True)
         grads = [torch.zeros_like(t) if g is None else g.contiguous() for g, t in zip(grads, leaves)]
-        allreduce_bucket(grads, group=group)
         n_mlp = len(self.mlp_params)
+        b_tensors = list(self.boundary.values())
+        b_grads = grads[n_mlp:]
+        # critical path first: the boundary gradients feed the replicated backward below.  The MLP bucket is
+        # issued behind it on the communicator's stream and only joined before the parameters' .grad is set, so
+        # it overlaps the decoder / FK / pose-decoder backward.
+        allreduce_bucket(b_grads, group=group)
+        finish_mlp = allreduce_bucket(grads[:n_mlp], group=group, async_op=overlap)
+        live = [(t, g) for t, g in zip(b_tensors, b_grads) if t.requires_grad]
+        if live:
+            torch.autograd.backward([t for t, _ in live], [g for _, g in live])
+        if finish_mlp is not None:
+            finish_mlp()
         for p, g in zip(self.mlp_params, grads[:n_mlp]):
             if p.grad is None:
                 p.grad = g
             else:
                 p.grad.add_(g)          # in place: keeps the flat-buffer views of training.FusedAdam
-        b_tensors = list(self.boundary.values())
-        b_grads = grads[n_mlp:]
-        live = [(t, g) for t, g in zip(b_tensors, b_grads) if t.requires_grad]
-        if live:
-            torch.autograd.backward([t for t, _ in live], [g for _, g in live])
         return int(sum(g.numel() for g in grads))

@@ -3,9 +3,10 @@
 `core/train/optimizers/human_nerf/optimizer.py:12-43`).
 
 Patch assembly uses the CUDA row scatter (ops.scatter_rows); the perceptual term is the LPIPS(VGG16)
-architecture on cuDNN.  The reference's LPIPS needs ImageNet VGG16 weights that cannot be
-downloaded offline, so `PerceptualLoss` is seeded-random-initialised:
-the LPIPS term is therefore "parity unpinned against real weights"; the MSE term is exact."""
+architecture on cuDNN with one fused head kernel per stage.  The reference's LPIPS needs ImageNet VGG16 weights
+that cannot be downloaded offline, so `PerceptualLoss(seed)` is the reference's own
+`LPIPS(net='vgg', pnet_rand=True)` under that seed - pinned against the reference module by
+tests/golden/train_step_cfg2.npz; parity against the ImageNet weights stays unpinned."""
 from __future__ import annotations
 
 from typing import Dict, Optional
@@ -34,7 +35,15 @@ def unpack_imgs(rgbs: torch.Tensor, patch_masks: torch.Tensor, bgcolor01: torch.
 
 class PerceptualLoss(nn.Module):
     """LPIPS v0.1 with a VGG16 trunk (third_parties/lpips/lpips.py:23-129): scale -> five VGG16 stages
-    -> unit-normalise channels -> squared difference -> 1x1 non-negative 'lin' -> spatial mean -> sum."""
+    -> unit-normalise channels (third_parties/lpips/__init__.py:40-42) -> squared difference -> 1x1 non-negative
+    'lin' -> spatial mean -> sum.
+
+    Weights.  The reference builds `LPIPS(net='vgg')` (trainer.py:70), whose trunk is torchvision's ImageNet VGG16 -
+    a download, unavailable offline.  `PerceptualLoss(seed)` builds the SAME trunk the reference builds with
+    `LPIPS(net='vgg', pnet_rand=True)` under `torch.manual_seed(seed)` (torchvision's constructor consumes the
+    generator identically: pinned bit for bit by tests/golden/train_step_cfg2.npz), and `load_reference_weights`
+    takes real weights when they exist: the trunk from a torchvision VGG16 state_dict and the five 1x1 `lin`
+    layers from the reference's vendored `third_parties/lpips/weights/v0.1/vgg.pth`."""
 
     def __init__(self, seed: int = 0):
         super().__init__()
@@ -56,6 +65,34 @@ class PerceptualLoss(nn.Module):
         self.stages.to(memory_format=torch.channels_last)
         self.eval()
 
+    def load_reference_weights(self, lins=None, trunk=None) -> 'PerceptualLoss':
+        """`lins`: the reference LPIPS module's state_dict (or its vgg.pth: keys `lin{k}.model.1.weight`), or a list of
+        five arrays; `trunk`: a torchvision VGG16 `features` state_dict (keys `{i}.weight` / `{i}.bias`) or the
+        reference LPIPS state_dict (keys `net.slice{s}.{i}.*`)."""
+        with torch.no_grad():
+            if lins is not None:
+                if isinstance(lins, dict):
+                    lins = [lins[f'lin{k}.model.1.weight'] for k in range(5)]
+                for l, w in zip(self.lins, lins):
+                    l.weight.copy_(torch.as_tensor(w, dtype=torch.float32).reshape(l.weight.shape))
+            if trunk is not None:
+                flat = {}
+                for k, v in trunk.items():
+                    parts = k.split('.')
+                    if parts[0] == 'net' and parts[1].startswith('slice'):
+                        flat[f'{parts[2]}.{parts[3]}'] = v
+                    elif parts[0] == 'features':
+                        flat[f'{parts[1]}.{parts[2]}'] = v
+                    elif len(parts) == 2 and parts[0].isdigit():
+                        flat[k] = v
+                cuts = (0, 4, 9, 16, 23, 30)
+                for stage, a in zip(self.stages, cuts[:-1]):
+                    for j, m in enumerate(stage):
+                        if isinstance(m, nn.Conv2d):
+                            m.weight.copy_(flat[f'{a + j}.weight'])
+                            m.bias.copy_(flat[f'{a + j}.bias'])
+        return self
+
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         # prediction and target go through the trunk as ONE batch (half the launches of two passes; every op
         # of the trunk is per image, so the values are those of lpips.py:78-92)
@@ -71,7 +108,7 @@ class PerceptualLoss(nn.Module):
             return acc.view(n, 1, 1, 1)
         for stage, lin in zip(self.stages, self.lins):       # CPU tensors: host-logic tests and the oracle arm
             f = stage(f)
-            nf = f / (torch.sqrt(torch.sum(f ** 2, dim=1, keepdim=True)) + 1e-10)
+            nf = f / (torch.sqrt(torch.sum(f ** 2, dim=1, keepdim=True) + 1e-10) + 1e-10)
             total = total + lin((nf[:n] - nf[n:]) ** 2).mean([2, 3], keepdim=True)
         return total
 
@@ -306,7 +343,10 @@ class GraphedTrainStep:
 
     def __init__(self, net: nn.Module, crit: nn.Module, opt: 'FusedAdam', frame_kw: Dict[str, torch.Tensor],
                  bgcolor01: torch.Tensor, n_patches: int, patch_size: int, reducer=None, world: int = 1,
-                 rays_dtype: torch.dtype = torch.float64):
+                 rays_dtype: torch.dtype = torch.float64, scaling: str = 'weak', rank: int = 0):
+        """`scaling` (world > 1): 'weak' - every rank steps on its OWN batch, gradients averaged; 'strong' - every
+        rank loads the SAME batch and renders the contiguous slice `shard_bounds(cap, rank, world)` of its rays
+        (SURVEY 8e cfg3), the rgb rows are all-gathered, every rank evaluates the identical loss, gradients summed."""
         if not isinstance(opt, FusedAdam):
             raise RuntimeError('GraphedTrainStep needs the FusedAdam optimizer (device-side schedule)')
         cfg = get_cfg()
@@ -314,7 +354,9 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep: set cfg.b200.jitter_rng = 'device' (the reference draws the "
                                "stratified jitter on the CPU generator, which cannot be captured in a CUDA graph)")
         self.net, self.crit, self.opt, self.frame_kw, self.bg01 = net, crit, opt, frame_kw, bgcolor01
-        self.reducer, self.world = reducer, world
+        self.reducer, self.world, self.rank, self.scaling = reducer, world, rank, scaling
+        if scaling not in ('weak', 'strong'):
+            raise ValueError(f'GraphedTrainStep: scaling = {scaling!r}')
         dev = bgcolor01.device
         self.cap = n_patches * patch_size * patch_size
         self.rays = torch.zeros(3, self.cap, 3, dtype=rays_dtype, device=dev)
@@ -375,11 +417,19 @@ class GraphedTrainStep:
     # -- the step -----------------------------------------------------------------------
     def _body(self, iter_step: int) -> torch.Tensor:
         self.opt.zero_grad(set_to_none=True)
-        out = self.net(rays=self.rays, near=self.near, far=self.far, iter_val=iter_step,
-                       b200_hann_w=self.sched[:self._nf], b200_cond_gate=self.sched[self._nf:self._nf + 1],
-                       **self.frame_kw)
-        losses = self.crit(out['rgb'], None, self.bg01, self.targets, index=self.index)
-        loss = losses['total'] / self.world
+        sched = dict(b200_hann_w=self.sched[:self._nf], b200_cond_gate=self.sched[self._nf:self._nf + 1])
+        if self.world > 1 and self.scaling == 'strong':
+            from humannerf_b200.parallel import GatherRowsWithGrad, shard_bounds
+            a, b = shard_bounds(self.cap, self.rank, self.world)
+            out = self.net(rays=self.rays[:, a:b], near=self.near[a:b], far=self.far[a:b], iter_val=iter_step,
+                           **sched, **self.frame_kw)
+            rgb = GatherRowsWithGrad.apply(out['rgb'], self.cap)
+            losses = self.crit(rgb, None, self.bg01, self.targets, index=self.index)
+            loss = losses['total']                  # each rank back-propagates into its own rows only: the SUM is the gradient
+        else:
+            out = self.net(rays=self.rays, near=self.near, far=self.far, iter_val=iter_step, **sched, **self.frame_kw)
+            losses = self.crit(out['rgb'], None, self.bg01, self.targets, index=self.index)
+            loss = losses['total'] / self.world
         if self.world > 1 and self.reducer is not None:
             self.reducer.set_boundary(**self.net.boundary_tensors)
             self.reducer.exchange_and_finish(loss)

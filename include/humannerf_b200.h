@@ -232,9 +232,9 @@ int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* 
                    float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * a16  trainer.py:97-113 get_img_rebuild_loss -> third_parties/lpips/lpips.py:10-15, 78-92
+ * a16  trainer.py:97-113 get_img_rebuild_loss -> third_parties/lpips/__init__.py:40-42, lpips.py:14-15, 78-92
  * The LPIPS head of one trunk stage, fused: unit-normalise the channel vector of every position
- * (x / (||x|| + 1e-10)), squared difference of prediction and target, non-negative 1x1 `lin` weights (C),
+ * (x / (sqrt(||x||^2 + 1e-10) + 1e-10), the fork's normalize_tensor), squared difference of prediction and target, non-negative 1x1 `lin` weights (C),
  * spatial mean.  feat: (2 * n_pairs, C, positions) features of one trunk stage with element strides
  * (stride_n, stride_c, stride_p) - prediction images first, then their targets.
  *   out[i] += lpips_stage(feat[i], feat[n_pairs + i])           (accumulates: one call per stage)

@@ -489,7 +489,8 @@ def test_other_forward_kernels_parity(variant):
 @pytest.mark.parametrize('shape,channels_last', [((12, 64, 32, 32), False), ((12, 512, 2, 2), True), ((4, 100, 5, 3), True)])
 def test_lpips_head_matches_torch(ops, shape, channels_last):
     """hn_lpips_head_fwd / _bwd (one kernel per trunk stage) against the reference's expression
-    (third_parties/lpips/lpips.py:10-15, 78-92: normalize_tensor, squared difference, 1x1 lin, spatial_average) and its
+    (third_parties/lpips/__init__.py:40-42 normalize_tensor = f / (sqrt(sum f^2 + 1e-10) + 1e-10), lpips.py:78-92 squared
+    difference, 1x1 lin, spatial_average :14-15) and its
     autograd, for NCHW and NHWC feature strides, accumulating into a previous stage's result."""
     gen = torch.Generator().manual_seed(sum(shape))
     f0 = torch.relu(torch.randn(*shape, generator=gen)).to(DEV)
@@ -503,7 +504,7 @@ def test_lpips_head_matches_torch(ops, shape, channels_last):
     got = ops.lpips_head(fa, lin, pa)
     (got * gout).sum().backward()
     fb, pb = f0.clone().double().requires_grad_(), prev0.clone().double().requires_grad_()
-    nf = fb / (torch.sqrt(torch.sum(fb ** 2, dim=1, keepdim=True)) + 1e-10)
+    nf = fb / (torch.sqrt(torch.sum(fb ** 2, dim=1, keepdim=True) + 1e-10) + 1e-10)
     want = pb + torch.nn.functional.conv2d((nf[:n] - nf[n:]) ** 2, lin.double()).mean([2, 3]).view(n)
     (want * gout.double()).sum().backward()
     assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-7

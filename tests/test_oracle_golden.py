@@ -219,3 +219,36 @@ def test_analytic_known_answers():
     mRs, mTs = orc.motion_bases(Rs0, T(fr['dst_Ts']), T(fr['cnl_gtfms']))
     np.testing.assert_allclose(mRs.numpy(), np.tile(np.eye(3), (24, 1, 1)), atol=1e-6)
     np.testing.assert_allclose(mTs.numpy(), 0.0, atol=1e-6)
+
+
+def test_train_step_cfg2_p20_oracle_and_lpips_against_reference():
+    """The oracle (and `training.PerceptualLoss` on CPU tensors) against one full TRAIN STEP of the unmodified
+    reference at cfg2's single_gpu.yaml size (6 x 20 x 20 patches = 2400 rays x 128 samples, iter 30000, perturb 1):
+    forward outputs, the loss through the reference's Trainer.get_loss with LPIPS(net='vgg', pnet_rand=True), and
+    the gradients of all 55 tensors.  Stated tolerances: outputs 1e-5 + 1e-5 |ref|, loss terms 1e-5 relative, gradients 2e-3
+    relative L2 (pose decoder 1e-2, see test_network_forward_eval_and_train_with_grads)."""
+    import step_fixture as sf
+    st = sf.load_step('p20')
+    fr = {k: T(v) for k, v in st['frame'].items()}
+    fr['bgcolor'] = T(st['bgcolor'])
+    sd = {k: v.clone().requires_grad_(True)
+          for k, v in syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True).items()}
+    out = orc.network_forward(sd, T(st['rays']), T(st['near']), T(st['far']), fr, torch.full((1,), st['iter']),
+                              t_rand=st['t_rand'])
+    for k in ('rgb', 'alpha', 'depth'):
+        err = float(((out[k].detach() - T(st[k])).abs() - 1e-5 * T(st[k]).abs()).max())
+        assert err < 1e-5, (k, err)
+    lp = sf.make_perceptual(st)
+    img = orc.unpack_patches(out['rgb'], T(st['patch_masks']), T(st['bgcolor']) / 255.0, st['div_indices'])
+    tg = T(st['targets'])
+    mse = torch.mean((img - tg) ** 2)
+    lpips = torch.mean(lp(img.permute(0, 3, 1, 2) * 2 - 1, tg.permute(0, 3, 1, 2) * 2 - 1))
+    assert abs(float(mse) * 0.2 - st['loss_mse']) <= 1e-5 * st['loss_mse']
+    assert abs(float(lpips) - st['loss_lpips']) <= 1e-5 * st['loss_lpips'], (float(lpips), st['loss_lpips'])
+    loss = 0.2 * mse + 1.0 * lpips
+    assert abs(float(loss) - st['loss']) <= 1e-5 * st['loss']
+    loss.backward()
+    rows = sf.compare_grads(st, {k: v.grad for k, v in sd.items()}, 2e-3, pose_tol=1e-2, label='oracle p20')
+    worst = max(rows, key=lambda r: r[1])
+    print(f'[parity] oracle vs reference train step p20: loss {float(loss):.6f} vs {st["loss"]:.6f}, '
+          f'worst gradient rel L2 {worst[1]:.2e} ({worst[0]})')
