@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-HN_ABI_VERSION = 4
+HN_ABI_VERSION = 5
 HN_MAX_LAYERS = 16
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
@@ -88,6 +88,8 @@ SIGNATURES = {
     'hn_tile_wgrad': (_int, [C.POINTER(WgradJob), _int, _i64, _p, _p]),
     'hn_scatter_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
     'hn_gather_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
+    'hn_patch_prepare': (_int, [_int, _int] + [_p] * 7),
+    'hn_select_patches': (_int, [_int, _int, _int, _int, C.c_double] + [_p] * 22),
     'hn_lpips_head_fwd': (_int, [_int, _int, _int, _p, _i64, _i64, _i64, _p, _p, _p]),
     'hn_lpips_head_bwd': (_int, [_int, _int, _int, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
 }

@@ -70,3 +70,86 @@ def make_train_batch(rays_o: np.ndarray, rays_d: np.ndarray, near: np.ndarray, f
         'scatter_index': index,
         'n_rays': np.asarray(n, dtype=np.int64),
     }
+
+
+class DevicePatchSampler:
+    """Patch selection on the device (a3 / SURVEY 8f row 2): the frame's compacted rays, masks and image stay
+    resident in HBM; per step the host only draws the reference's two randoms per patch (`draw`) and ONE kernel
+    (`hn_select_patches`, csrc/patches.cu) writes the whole padded batch.  Integer outputs (`select_inds`,
+    `patch_masks`, `div_indices`, `xy_min`) are bit-exact with `sample_patches` / the reference for the same draws.
+
+    ray_mask (H*W) uint8 / bool device tensor (= the reference's `bbox_mask` flattened), subject_mask (H, W) device
+    tensor, rays_o / rays_d (R, 3), near / far (R) or (R, 1): the COMPACTED fp32 ray arrays (`ops.compact_rays`),
+    image (H, W, 3) fp32 on the device."""
+
+    def __init__(self, ray_mask, subject_mask, rays_o, rays_d, near, far, image, H: int, W: int, n_patches: int,
+                 patch_size: int, sample_subject_ratio: float = 0.8):
+        import ctypes as C
+        import torch
+        from humannerf_b200 import _lib
+        self._lib, self._torch = _lib, torch
+        dev = rays_o.device
+        if dev.type != 'cuda':
+            raise RuntimeError('DevicePatchSampler: tensors must live on a CUDA device (no CPU fallback)')
+        self.H, self.W, self.n_patches, self.patch, self.ratio = H, W, int(n_patches), int(patch_size), float(sample_subject_ratio)
+        u8 = lambda t: t.reshape(-1).to(torch.uint8).contiguous()
+        self.ray_mask, self.subject = u8(ray_mask), u8(subject_mask)
+        f32 = lambda t: t.to(torch.float32).contiguous()
+        self.rays_o, self.rays_d = f32(rays_o), f32(rays_d)
+        self.near, self.far = f32(near).reshape(-1), f32(far).reshape(-1)
+        self.image = f32(image).reshape(H, W, 3)
+        n = H * W
+        self.cum = torch.empty(3, n, dtype=torch.int32, device=dev)      # ray / subject / background prefix counts
+        counts = torch.zeros(3, dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hn_patch_prepare(H, W, _lib.ptr(self.ray_mask), _lib.ptr(self.subject), _lib.ptr(self.cum[0]),
+                                            _lib.ptr(self.cum[1]), _lib.ptr(self.cum[2]), _lib.ptr(counts),
+                                            _lib.stream_ptr()), 'patch_prepare')
+        # once per FRAME: the host needs the candidate counts to draw np.random.choice(n) like the reference
+        self.n_rays_frame, self.n_subject, self.n_background = [int(v) for v in counts.tolist()]
+        if self.n_rays_frame != self.rays_o.shape[0]:
+            raise RuntimeError(f'DevicePatchSampler: ray_mask selects {self.n_rays_frame} rays, got {self.rays_o.shape[0]}')
+        self.cap = self.n_patches * self.patch * self.patch
+
+    def draw(self, rng) -> 'np.ndarray':
+        """The reference's host randoms for one step, in its order (train.py:263, :307): per patch `rand(1)` then
+        `choice(n_candidates)`.  Returns a (2, n_patches) float64 array [u; k] (k is exact in float64)."""
+        out = np.empty((2, self.n_patches), dtype=np.float64)
+        for i in range(self.n_patches):
+            u = rng.rand(1)[0]
+            n = self.n_subject if u < self.ratio else self.n_background
+            out[0, i] = u
+            out[1, i] = rng.choice(n, size=[1], replace=False)[0]
+        return out
+
+    def alloc(self):
+        """Output buffers of one step (reusable; `select` overwrites every element)."""
+        torch = self._torch
+        dev, n, P, cap = self.rays_o.device, self.n_patches, self.patch, self.cap
+        return {'rays': torch.empty(3, cap, 3, device=dev), 'near': torch.empty(cap, 1, device=dev),
+                'far': torch.empty(cap, 1, device=dev), 'scatter_index': torch.empty(cap, dtype=torch.int64, device=dev),
+                'target_patches': torch.empty(n, P, P, 3, device=dev),
+                'select_inds': torch.empty(cap, dtype=torch.int32, device=dev),
+                'patch_masks': torch.empty(n, P, P, dtype=torch.uint8, device=dev),
+                'patch_div_indices': torch.empty(n + 1, dtype=torch.int32, device=dev),
+                'xy_min': torch.empty(n, 2, dtype=torch.int32, device=dev),
+                'n_rays': torch.empty(1, dtype=torch.int64, device=dev)}
+
+    def select(self, u, k, out=None):
+        """u (n_patches,) float64 and k (n_patches,) int64 DEVICE tensors -> the padded batch (device tensors).
+        Asynchronous, no host round trip: capturable in a CUDA graph."""
+        torch, _lib = self._torch, self._lib
+        out = self.alloc() if out is None else out
+        lib = _lib.load()
+        ptr = _lib.ptr
+        assert u.dtype == torch.float64 and k.dtype == torch.int64 and u.numel() == self.n_patches == k.numel()
+        with torch.cuda.device(self.rays_o.device):
+            _lib.check(lib.hn_select_patches(
+                self.H, self.W, self.n_patches, self.patch, self.ratio, ptr(self.ray_mask), ptr(self.cum[0]),
+                ptr(self.cum[1]), ptr(self.cum[2]), ptr(u), ptr(k), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near),
+                ptr(self.far), ptr(self.image), ptr(out['select_inds']), ptr(out['patch_masks']),
+                ptr(out['patch_div_indices']), ptr(out['xy_min']), ptr(out['target_patches']), ptr(out['rays']),
+                ptr(out['near']), ptr(out['far']), ptr(out['scatter_index']), ptr(out['n_rays']), _lib.stream_ptr()),
+                'select_patches')
+        return out

@@ -181,14 +181,15 @@ class CutBReducer:
         self.boundary = dict(tensors)
 
     def check_same_frame(self, group=None) -> None:
-        """Raise unless the boundary tensors (functions of the frame and the replicated parameters only) are
-        identical on every rank: max over ranks of a checksum equals its min."""
+        """Raise unless the boundary tensors (functions of the frame and the replicated parameters only) agree on
+        every rank: max and min over ranks of a per-tensor checksum within 1e-5 relative (the cuDNN decoder is not
+        bit-reproducible between processes; a different frame moves the checksums by orders of magnitude more)."""
         if not self.boundary or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
-        sums = torch.stack([t.detach().double().sum() for t in self.boundary.values()])
+        sums = torch.stack([t.detach().double().abs().sum() for t in self.boundary.values()])
         pair = torch.stack([sums, -sums])
         dist.all_reduce(pair, op=dist.ReduceOp.MAX, group=group)
-        if not torch.equal(pair[0], -pair[1]):
+        if bool(((pair[0] + pair[1]) > 1e-5 * pair[0].abs() + 1e-12).any()):
             raise RuntimeError('CutBReducer: ranks hold different frames / front-end outputs in this step; the cut-B '
                                'gradient exchange needs the same frame on every rank (use cut A otherwise)')
 

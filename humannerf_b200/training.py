@@ -322,6 +322,24 @@ def update_lr(optimizer: torch.optim.Optimizer, iter_step: int) -> None:
 # ---------------------------------------------------------------------------------------------
 # the whole train step as one CUDA graph
 # ---------------------------------------------------------------------------------------------
+class _PinnedRing:
+    """Small pinned staging buffers for per-step host values.  The host runs ahead of the GPU (a graph replay is one
+    launch), so one buffer could be overwritten for step k+1 before the copy of step k has executed: a ring, each
+    slot guarded by the event recorded after its last copy."""
+
+    def __init__(self, shape, dtype, slots: int = 4):
+        self.slots = [(torch.zeros(shape, dtype=dtype).pin_memory(), torch.cuda.Event()) for _ in range(slots)]
+        self.i = 0
+
+    def stage(self, fill, dst: torch.Tensor) -> None:
+        h, ev = self.slots[self.i]
+        self.i = (self.i + 1) % len(self.slots)
+        ev.synchronize()                       # no-op unless the GPU is more than `slots` steps behind
+        fill(h)
+        dst.copy_(h, non_blocking=True)
+        ev.record()
+
+
 class GraphedTrainStep:
     """forward + loss + backward (+ gradient all-reduce) + Adam of `trainer.py:194-220` captured once in
     a CUDA graph and replayed per step: an eager step is ~1350 kernel launches and is bound by the
@@ -343,10 +361,12 @@ class GraphedTrainStep:
 
     def __init__(self, net: nn.Module, crit: nn.Module, opt: 'FusedAdam', frame_kw: Dict[str, torch.Tensor],
                  bgcolor01: torch.Tensor, n_patches: int, patch_size: int, reducer=None, world: int = 1,
-                 rays_dtype: torch.dtype = torch.float64, scaling: str = 'weak', rank: int = 0):
+                 rays_dtype: torch.dtype = torch.float64, scaling: str = 'weak', rank: int = 0, sampler=None):
         """`scaling` (world > 1): 'weak' - every rank steps on its OWN batch, gradients averaged; 'strong' - every
         rank loads the SAME batch and renders the contiguous slice `shard_bounds(cap, rank, world)` of its rays
-        (SURVEY 8e cfg3), the rgb rows are all-gathered, every rank evaluates the identical loss, gradients summed."""
+        (SURVEY 8e cfg3), the rgb rows are all-gathered, every rank evaluates the identical loss, gradients summed.
+        `sampler` (data.DevicePatchSampler): patch selection becomes the first kernel of the captured step - the
+        per-step input is then `draws` (the reference's two host randoms per patch, 16 bytes each) instead of a batch."""
         if not isinstance(opt, FusedAdam):
             raise RuntimeError('GraphedTrainStep needs the FusedAdam optimizer (device-side schedule)')
         cfg = get_cfg()
@@ -359,6 +379,14 @@ class GraphedTrainStep:
             raise ValueError(f'GraphedTrainStep: scaling = {scaling!r}')
         dev = bgcolor01.device
         self.cap = n_patches * patch_size * patch_size
+        self.sampler = sampler
+        if sampler is not None:
+            if sampler.cap != self.cap:
+                raise RuntimeError('GraphedTrainStep: the sampler was built for another patch geometry')
+            rays_dtype = torch.float32                              # the sampler gathers the frame's fp32 rays
+            self.draws = torch.zeros(2, n_patches, dtype=torch.float64, device=dev)
+            self._draw_ring = _PinnedRing((2, n_patches), torch.float64)
+            self._sampler_out = sampler.alloc()
         self.rays = torch.zeros(3, self.cap, 3, dtype=rays_dtype, device=dev)
         self.near = torch.zeros(self.cap, 1, device=dev)
         self.far = torch.zeros(self.cap, 1, device=dev)
@@ -367,16 +395,16 @@ class GraphedTrainStep:
         nf = int(cfg.non_rigid_motion_mlp.multires)
         self._nf = nf
         self.sched = torch.zeros(nf + 2, device=dev)                  # [hann (nf) | cond gate | lr scale]
-        # pinned staging for the schedule: the host runs ahead of the GPU (a replay is one launch), so a single
-        # buffer could be overwritten for step k+1 before the copy of step k has executed.  A small ring, each
-        # slot guarded by the event recorded after its copy.
-        self._sched_ring = [(torch.zeros(nf + 2).pin_memory(), torch.cuda.Event()) for _ in range(4)]
-        self._sched_slot = 0
+        self._sched_ring = _PinnedRing((nf + 2,), torch.float32)
         self.loaded = torch.cuda.Event()
+        if sampler is not None:
+            self._sampler_out.update(rays=self.rays, near=self.near, far=self.far, scatter_index=self.index,
+                                     target_patches=self.targets)
         opt.lr_scale = self.sched[nf + 1:nf + 2]
         self._base_lrs = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
+        self.rays_seen = torch.zeros(1, dtype=torch.int64, device=dev)      # real (non-padding) rays of all steps so far
         self.launches_per_step = 0
         self._iter_cfg = None
 
@@ -385,14 +413,11 @@ class GraphedTrainStep:
         from humannerf_b200.embedders.hannw_fourier import hann_window_weights
         cfg = get_cfg()
         nr = cfg.non_rigid_motion_mlp
-        h, ev = self._sched_ring[self._sched_slot]
-        self._sched_slot = (self._sched_slot + 1) % len(self._sched_ring)
-        ev.synchronize()                       # the copy that last used this slot has executed (no-op if never recorded)
-        h[:self._nf] = hann_window_weights(iter_step, self._nf, nr.kick_in_iter, nr.full_band_iter)
-        h[self._nf] = 0.0 if iter_step < nr.kick_in_iter else 1.0
-        h[self._nf + 1] = 0.1 ** (iter_step / (cfg.train.lrate_decay * 1000))      # exp_decay.py:7-16
-        self.sched.copy_(h, non_blocking=True)
-        ev.record()
+        def fill(h):
+            h[:self._nf] = hann_window_weights(iter_step, self._nf, nr.kick_in_iter, nr.full_band_iter)
+            h[self._nf] = 0.0 if iter_step < nr.kick_in_iter else 1.0
+            h[self._nf + 1] = 0.1 ** (iter_step / (cfg.train.lrate_decay * 1000))      # exp_decay.py:7-16
+        self._sched_ring.stage(fill, self.sched)
         pose_on = (not cfg.pose_decoder_off) and iter_step >= cfg.pose_decoder.get('kick_in_iter', 0)
         if self._iter_cfg is None:
             self._iter_cfg = pose_on
@@ -417,6 +442,10 @@ class GraphedTrainStep:
     # -- the step -----------------------------------------------------------------------
     def _body(self, iter_step: int) -> torch.Tensor:
         self.opt.zero_grad(set_to_none=True)
+        if self.sampler is not None:
+            # a3 on the device: this step's patches from the two host randoms per patch, straight into the static buffers
+            self.sampler.select(self.draws[0], self.draws[1].to(torch.int64), out=self._sampler_out)
+        self.rays_seen += self._sampler_out['n_rays'] if self.sampler is not None else (self.index >= 0).sum()
         sched = dict(b200_hann_w=self.sched[:self._nf], b200_cond_gate=self.sched[self._nf:self._nf + 1])
         if self.world > 1 and self.scaling == 'strong':
             from humannerf_b200.parallel import GatherRowsWithGrad, shard_bounds
@@ -468,9 +497,19 @@ class GraphedTrainStep:
             self.opt.step_dev.copy_(snap[2])
         self.graph = graph
 
-    def __call__(self, batch: Optional[Dict[str, torch.Tensor]], iter_step: int) -> torch.Tensor:
+    def __call__(self, batch: Optional[Dict[str, torch.Tensor]], iter_step: int, draws=None) -> torch.Tensor:
+        """`batch`: a padded batch (host pinned or device tensors), or None to reuse the loaded one; with a sampler
+        pass `draws` = `sampler.draw(rng)` instead ((2, n_patches) float64: u and k per patch)."""
         self._set_schedule(int(iter_step))
-        if batch is not None:
+        if draws is not None:
+            if self.sampler is None:
+                raise RuntimeError('GraphedTrainStep: `draws` needs a DevicePatchSampler')
+            if torch.is_tensor(draws) and draws.is_cuda:
+                self.draws.copy_(draws)                                   # already resident in HBM
+            else:
+                src = torch.as_tensor(draws, dtype=torch.float64)
+                self._draw_ring.stage(lambda h: h.copy_(src), self.draws)
+        elif batch is not None:
             self.load(batch)
         if self.graph is None:
             self._capture(int(iter_step))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 4
+#define HN_ABI_VERSION 5
 #define HN_MAX_LAYERS 16
 
 /* ABI version of the loaded library (compare with HN_ABI_VERSION). */
@@ -230,6 +230,31 @@ int hn_scatter_rows(int64_t n_rows, int n_cols, const float* src, const int64_t*
                     float* out, void* stream);
 int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* src_index,
                    float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  core/data/human_nerf/train.py:235-340 get_patch_ray_indices / _get_patch_ray_indices,
+ *     :226-233 select_rays, :450-476 sample_patch_rays - patch selection on the device.
+ * Per frame: hn_patch_prepare turns ray_mask (H*W uint8, = bbox_mask) and subject_mask (H*W uint8) into inclusive
+ * prefix counts of the ray mask, the subject mask and bbox-minus-subject (int32 each, H*W) and counts[3] = their
+ * totals (the host needs counts[1], counts[2] to draw `np.random.choice(n)` like the reference).
+ * Per step: hn_select_patches consumes the reference's two host randoms per patch - u[i] = np.random.rand(1)[0]
+ * (subject if u < subject_ratio, :263) and choice[i] = np.random.choice(n_candidates) (:307) - and writes, for
+ * cap = n_patches * patch_size^2 rows: select_inds (compacted ray id per selected ray, -1 padding),
+ * patch_masks (n_patches, P, P) uint8, div_indices (n_patches + 1), xy_min (n_patches, 2) = (x_min, y_min),
+ * target_patches (n_patches, P, P, 3) cropped from image (H, W, 3), and the gathered batch: out_rays (3, cap, 3) =
+ * [o, d, d] from the frame's compacted fp32 rays_o / rays_d (R, 3), out_near / out_far (cap), scatter_index (cap) =
+ * flat (patch, y, x) of every ray (-1 padding; zero rays, near = far = 0), n_rays (1, optional) = div_indices[-1].
+ * Integer outputs are bit-exact with the reference for the same draws.  n_patches <= 32.
+ */
+int hn_patch_prepare(int H, int W, const uint8_t* ray_mask, const uint8_t* subject_mask, int32_t* ray_cum,
+                     int32_t* subject_cum, int32_t* background_cum, int32_t* counts, void* stream);
+int hn_select_patches(int H, int W, int n_patches, int patch_size, double subject_ratio, const uint8_t* ray_mask,
+                      const int32_t* ray_cum, const int32_t* subject_cum, const int32_t* background_cum,
+                      const double* u, const int64_t* choice, const float* rays_o, const float* rays_d,
+                      const float* near, const float* far, const float* image, int32_t* select_inds,
+                      uint8_t* patch_masks, int32_t* div_indices, int32_t* xy_min, float* target_patches,
+                      float* out_rays, float* out_near, float* out_far, int64_t* scatter_index, int64_t* n_rays,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a16  trainer.py:97-113 get_img_rebuild_loss -> third_parties/lpips/__init__.py:40-42, lpips.py:14-15, 78-92

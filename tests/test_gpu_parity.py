@@ -720,3 +720,98 @@ def test_pose_fk_kernel_against_torch_modules(ops):
     # no refinement: rvec = None
     _, G0 = ops.pose_fk(None, dst_Rs, dst_Ts, SMPL_PARENT)
     assert torch.isfinite(G0).all()
+
+
+# --------------------------------------------------------------------------------------
+# a3: patch selection on the device
+# --------------------------------------------------------------------------------------
+def _sampler_inputs(ray_mask, H, W, seed):
+    gen = torch.Generator().manual_seed(seed)
+    R = int(ray_mask.sum())
+    ro, rd = torch.randn(R, 3, generator=gen), torch.randn(R, 3, generator=gen)
+    near, far = torch.rand(R, generator=gen) + 4.0, torch.rand(R, generator=gen) + 6.0
+    image = torch.rand(H, W, 3, generator=gen)
+    return ro, rd, near, far, image
+
+
+def test_device_patch_selection_bit_exact_against_reference():
+    """hn_patch_prepare + hn_select_patches against the reference's Dataset.get_patch_ray_indices
+    (tests/golden/patches.npz: 6 patches of 16 x 16 on a 64 x 64 frame, the reference's logged host randoms)."""
+    from humannerf_b200.data import DevicePatchSampler
+    g = gold('patches.npz')
+    H, W, P = int(g['H']), int(g['W']), int(g['patch_size'])
+    ray_mask, subject = g['ray_mask'].astype(bool).reshape(-1), g['subject_mask'].astype(bool)
+    ro, rd, near, far, image = _sampler_inputs(ray_mask, H, W, 3)
+    smp = DevicePatchSampler(T(ray_mask.astype(np.uint8), DEV), T(subject.astype(np.uint8), DEV), ro.to(DEV), rd.to(DEV),
+                             near.to(DEV), far.to(DEV), image.to(DEV), H, W, 6, P,
+                             sample_subject_ratio=float(g['sample_subject_ratio']))
+    assert smp.n_rays_frame == int(ray_mask.sum()) and smp.n_subject == int(subject.sum())
+    assert smp.n_background == int((ray_mask.reshape(H, W) & ~subject).sum())
+    # the candidate counts the reference drew from are the ones the device computed
+    for u, n in zip(g['u_subject'], g['choice_n']):
+        assert int(n) == (smp.n_subject if u < smp.ratio else smp.n_background)
+    out = smp.select(T(g['u_subject'].astype(np.float64), DEV), T(g['choice_idx'].astype(np.int64), DEV))
+    torch.cuda.synchronize()
+    n = int(out['n_rays'])
+    assert n == int(g['div_indices'][-1]) == g['select_inds'].shape[0]
+    assert np.array_equal(out['select_inds'][:n].cpu().numpy(), g['select_inds'])
+    assert np.array_equal(out['patch_masks'].cpu().numpy().astype(bool), g['patch_masks'])
+    assert np.array_equal(out['patch_div_indices'].cpu().numpy(), g['div_indices'])
+    assert np.array_equal(out['xy_min'].cpu().numpy(), g['xy_min'])
+    sel = torch.from_numpy(g['select_inds'].astype(np.int64))
+    assert torch.equal(out['rays'][0, :n].cpu(), ro[sel]) and torch.equal(out['rays'][1, :n].cpu(), rd[sel])
+    assert torch.equal(out['rays'][2, :n].cpu(), rd[sel])
+    assert torch.equal(out['near'][:n, 0].cpu(), near[sel]) and torch.equal(out['far'][:n, 0].cpu(), far[sel])
+    assert np.array_equal(out['scatter_index'][:n].cpu().numpy(), np.nonzero(g['patch_masks'].reshape(-1))[0])
+    assert bool((out['scatter_index'][n:] == -1).all()) and float(out['rays'][:, n:].abs().max()) == 0.0
+    for i, (x, y) in enumerate(g['xy_min']):
+        assert torch.equal(out['target_patches'][i].cpu(), image[y:y + P, x:x + P])
+    print(f'[parity] device patch selection: {n} rays in 6 patches, select_inds / masks / div / xy_min bit-exact')
+
+
+@pytest.mark.parametrize('P,H,W', [(32, 512, 512), (20, 512, 512), (16, 37, 53), (16, 16, 16)])
+def test_device_patch_selection_matches_host(P, H, W):
+    """... and against the host implementation (data.sample_patches / make_train_batch, itself pinned to the reference by
+    tests/test_host.py) at the benchmarked geometry and on ragged images, 25 steps of seeded draws each: windows
+    clipped at every border, patches without any ray, the k = 0 and k = n - 1 candidates."""
+    from humannerf_b200.data import DevicePatchSampler, make_train_batch
+    rs = np.random.RandomState(P * 1000 + H)
+    yy, xx = np.mgrid[0:H, 0:W]
+    ray_mask = ((xx - W * 0.45) ** 2 / (0.4 * W) ** 2 + (yy - H * 0.5) ** 2 / (0.47 * H) ** 2 < 1.0)
+    ray_mask |= rs.rand(H, W) < 0.02
+    ray_mask[0, 0] = ray_mask[H - 1, W - 1] = True
+    subject = ((xx - W * 0.5) ** 2 / (0.15 * W) ** 2 + (yy - H * 0.5) ** 2 / (0.35 * H) ** 2 < 1.0)
+    subject[0, 0] = True                      # first candidate in row-major order
+    subject[H - 1, W - 1] = True
+    ro, rd, near, far, image = _sampler_inputs(ray_mask.reshape(-1), H, W, 5)
+    smp = DevicePatchSampler(T(ray_mask.reshape(-1).astype(np.uint8), DEV), T(subject.astype(np.uint8), DEV), ro.to(DEV),
+                             rd.to(DEV), near.to(DEV), far.to(DEV), image.to(DEV), H, W, 6, P)
+    buf = smp.alloc()
+    for step in range(25):
+        rng_a, rng_b = np.random.RandomState(step), np.random.RandomState(step)
+        draws = smp.draw(rng_a)
+        if step == 0:
+            draws[:, 0] = (0.1, 0)                                   # first subject pixel
+            draws[:, 1] = (0.1, smp.n_subject - 1)                   # last subject pixel
+            draws[:, 2] = (0.9, smp.n_background - 1)                # last background pixel
+        out = smp.select(T(draws[0], DEV), T(draws[1].astype(np.int64), DEV), out=buf)
+        if step == 0:
+            continue                                                 # hand-made draws: checked by invariants below
+        b = make_train_batch(ro.numpy(), rd.numpy(), near.numpy(), far.numpy(), ray_mask.reshape(-1), subject,
+                             image.numpy(), H, W, 6, P, rng_b, pad_rays=True)
+        n = int(out['n_rays'])
+        assert n == int(b['n_rays'])
+        assert np.array_equal(out['patch_masks'].cpu().numpy().astype(bool), b['patch_masks'])
+        assert np.array_equal(out['patch_div_indices'].cpu().numpy(), b['patch_div_indices'])
+        assert np.array_equal(out['scatter_index'].cpu().numpy(), b['scatter_index'])
+        assert np.array_equal(out['rays'].cpu().numpy(), b['rays'])
+        assert np.array_equal(out['near'].cpu().numpy(), b['near']) and np.array_equal(out['far'].cpu().numpy(), b['far'])
+        assert np.array_equal(out['target_patches'].cpu().numpy(), b['target_patches'])
+    # invariants of SURVEY 8c (viii) on the hand-made draws of step 0
+    out = smp.select(T(np.array([0.1, 0.1, 0.9, 0.5, 0.5, 0.5]), DEV),
+                     T(np.array([0, smp.n_subject - 1, smp.n_background - 1, 1, 2, 3], dtype=np.int64), DEV), out=buf)
+    xy = out['xy_min'].cpu().numpy()
+    assert (xy >= 0).all() and (xy[:, 0] <= W - P).all() and (xy[:, 1] <= H - P).all()
+    assert tuple(xy[0]) == (0, 0) and tuple(xy[1]) == (W - P, H - P)
+    assert int(out['patch_div_indices'][-1]) == int(out['n_rays']) == int(out['patch_masks'].sum())
+    print(f'[parity] device patch selection vs host, P={P} on {H}x{W}: 24 seeded steps bit-exact')

@@ -298,6 +298,9 @@ def test_fused_adam_matches_torch_adam(ops):
         err = float((p - q).abs().max())
         print(f'[parity] fused adam tensor {i} {tuple(p.shape)}: max abs err {err:.3e}')
         assert torch.allclose(q, p, rtol=1e-5, atol=2e-6), (i, err)
+        assert float(our.state[q]['step']) == float(ref.state[p]['step'])
+        assert torch.allclose(our.state[q]['exp_avg'], ref.state[p]['exp_avg'], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(our.state[q]['exp_avg_sq'], ref.state[p]['exp_avg_sq'], rtol=1e-4, atol=1e-9)
 
 
 @pytest.mark.parametrize('source', ['fused', 'torch'])
@@ -344,9 +347,9 @@ def test_fused_adam_resume_from_state_dict(ops, source):
         err = float((p - q).abs().max())
         print(f'[parity] fused adam resumed from a {source} checkpoint, tensor {i}: max abs err {err:.3e}')
         assert torch.allclose(q, p, rtol=1e-5, atol=2e-6), (i, err)
-        assert float(our.state[q]['step']) == float(ref.state[p]['step'])
-        assert torch.allclose(our.state[q]['exp_avg'], ref.state[p]['exp_avg'], rtol=1e-4, atol=1e-7)
-        assert torch.allclose(our.state[q]['exp_avg_sq'], ref.state[p]['exp_avg_sq'], rtol=1e-4, atol=1e-9)
+        assert float(resumed.state[q]['step']) == float(ref.state[p]['step'])
+        assert torch.allclose(resumed.state[q]['exp_avg'], ref.state[p]['exp_avg'], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(resumed.state[q]['exp_avg_sq'], ref.state[p]['exp_avg_sq'], rtol=1e-4, atol=1e-9)
 
 
 def _train_setup(precision, seed=0):

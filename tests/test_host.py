@@ -174,11 +174,12 @@ def test_bench_reference_arm_runs_on_cpu():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
-                        '--warmup-ref', '0'], capture_output=True, text=True, timeout=900, cwd=root)
+                        '--warmup-ref', '0', '--ref-patch', '16'], capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
     d = json.loads(line)
     assert d['impl'] == 'reference' and d['metric'] == 'train_step_rays_per_sec' and d['value'] > 0
+    assert '16x16' in d['config']['workload'] and d['steps'] == 1          # the line states what actually ran
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
 
