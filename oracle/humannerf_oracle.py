@@ -176,7 +176,7 @@ def motion_bases(dst_Rs: torch.Tensor, dst_Ts: torch.Tensor, cnl_gtfms: torch.Te
     kinematics down the SMPL tree, then canonical_global @ inverse(posed_global)
     per joint.  Returns scale_Rs (24,3,3), Ts (24,3)."""
     n = dst_Rs.shape[0]
-    local = torch.zeros(n, 4, 4, dtype=dst_Rs.dtype)
+    local = torch.zeros(n, 4, 4, dtype=dst_Rs.dtype, device=dst_Rs.device)
     local[:, :3, :3] = dst_Rs
     local[:, :3, 3] = dst_Ts
     local[:, 3, 3] = 1.0
@@ -271,7 +271,7 @@ def hann_weights(iter_val, n_freqs: int, kick_in_iter: float, full_band_iter: fl
     t = torch.clamp(it - float(kick_in_iter), min=0.0)
     span = float(full_band_iter) - float(kick_in_iter)
     alpha = torch.tensor(float(n_freqs)) if span == 0 else n_freqs * t / span
-    k = torch.arange(n_freqs, dtype=torch.float32)
+    k = torch.arange(n_freqs, dtype=torch.float32, device=it.device)
     return (1.0 - torch.cos(math.pi * torch.clamp(alpha - k, 0.0, 1.0))) / 2.0
 
 

@@ -113,8 +113,8 @@ def main():
             losses.append(float(ls))
         mode = 'eager (gloo cannot be captured)'
     div = max_parameter_divergence(net)
-    moved = float(max((p.detach() - q.to(dev)).abs().max() for p, q in
-                      zip(net.state_dict().values(), syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True).values())))
+    sd0 = syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True)
+    moved = float(max((p.detach() - sd0[k].to(dev)).abs().max() for k, p in net.state_dict().items()))
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:

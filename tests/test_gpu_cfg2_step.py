@@ -116,9 +116,14 @@ def test_train_step_bf16_against_reference():
     """The bf16 tensor-core TRAINING path (what bench.py's `value` runs) on the reference's 6 x 32 x 32 step.
     Forward: rgb / alpha within 2e-2 abs of the reference, depth within 2e-2 of the ray's far bound (depth =
     sum_s w_s z_s, so |d depth| <= far * sum |dw|: the 2e-2 bound on the weights is 2e-2 * far in depth units).
-    Loss within 2 % of the reference's.  Gradients: relative L2 against the float64 gradient, per tensor; bounds by
-    group from the measured values (printed) with ~1.5x head-room - at 6144 rays the ReLU-flip noise of bf16
-    activations averages out, so these bounds are far below the 0.6 a 24-ray fixture needed."""
+    Loss within 1e-3 of the reference's (measured 4e-5).  Gradients, per tensor (all 55), against the float64 gradient:
+    relative L2 <= the group bound AND cosine similarity >= the group bound (a zero, random or sign-flipped gradient
+    has cosine <= 0; independent noise of relative size e gives 1 / sqrt(1 + e^2)).  Measured on the B200 (printed):
+    canonical MLP 0.012-0.09 / cos >= 0.996, volume decoder 0.05-0.28, non-rigid MLP 0.30-0.55, pose decoder 0.32.
+    The input-side groups are large because the bf16 forward flips ~2 % of the ReLU masks per layer and d(raw)/d(xyz)
+    of a ReLU MLP behind a 2^9-frequency encoding changes by O(1) in every flipped region: the bf16 gradient is the
+    exact gradient of the bf16 forward function (tests/bf16_emu.py agrees with the kernels to 0.12), not a noisy copy
+    of the fp32 one.  What training makes of it: test_training_trajectory_bf16_graph_tracks_fp32."""
     tag = 'p32'
     st = sf.load_step(tag)
     out, losses, grads = _run_step(st, 'bf16')
@@ -133,27 +138,35 @@ def test_train_step_bf16_against_reference():
     tot = float(losses['total'])
     print(f'[parity] cfg2 {tag} bf16 loss: total {tot:.6f} vs reference {st["loss"]:.6f} (mse {float(losses["mse"]):.6f} vs '
           f'{st["loss_mse"]:.6f}, lpips {float(losses["lpips"]):.6f} vs {st["loss_lpips"]:.6f})')
-    assert abs(tot - st['loss']) <= 2e-2 * st['loss']
+    assert abs(tot - st['loss']) <= 1e-3 * st['loss']
     rows = _grad_table(st, grads, tag)
-    bounds = {'cnl_mlp': 0.10, 'non_rigid_mlp': 0.20, 'mweight_vol_decoder': 0.10, 'pose_decoder': 0.35}
+    bounds = {'cnl_mlp': (0.12, 0.99), 'mweight_vol_decoder': (0.35, 0.93), 'non_rigid_mlp': (0.65, 0.80),
+              'pose_decoder': (0.42, 0.90)}
+    f64 = np.load(F64, allow_pickle=False)
     bad = []
     for n, e_ref, e_f64, r_f64, nrm in rows:
-        lim = bounds[n.split('.')[0]]
-        ok = e_f64 <= lim and nrm <= lim
-        print(f'[parity] cfg2 {tag} bf16 grad {n}: vs float64 {e_f64:.2e} (limit {lim}), vs reference {e_ref:.2e}, '
-              f'norm {nrm:.2e}{"" if ok else "  <-- FAIL"}')
+        lim, cos_min = bounds[n.split('.')[0]]
+        tru = f64[f'{tag}_grad/{n}'].astype(np.float64)
+        full = grads[n].detach().double().reshape(-1).cpu().numpy()
+        ours = full if tru.size == full.size else full[sf.sample_index(n, full.size)]
+        cos = float(ours @ tru / (np.linalg.norm(ours) * np.linalg.norm(tru) + 1e-300))
+        ok = e_f64 <= lim and cos >= cos_min
+        print(f'[parity] cfg2 {tag} bf16 grad {n}: vs float64 rel L2 {e_f64:.2e} (limit {lim}), cosine {cos:.4f} (>= {cos_min}), '
+              f'vs reference {e_ref:.2e}, norm {nrm:.2e}{"" if ok else "  <-- FAIL"}')
         if not ok:
-            bad.append((n, e_f64, nrm))
+            bad.append((n, e_f64, cos))
     assert not bad, bad
 
 
 def test_training_trajectory_bf16_graph_tracks_fp32():
     """200 Adam steps on IDENTICAL batches: the fp32 parity path stepped eagerly against the bf16 tensor-core path
     stepped as one CUDA graph (the bench configuration), same initial weights, same schedule (iterations 20000-20199:
-    inside the hann window, condition code on), perturb = 0 so that neither side draws random numbers.  Both losses must
-    fall, the smoothed curves must stay within 5 % of each other, and the final 64 x 64 renders of the two trained
-    networks must agree to 5e-2 max abs / 35 dB PSNR.  (An optimisation trajectory amplifies rounding: per-step
-    agreement is not expected; the bound is on what training produces.)"""
+    inside the hann window, condition code on), perturb = 0 so that neither side draws random numbers, ten times the
+    reference's learning rates so that 200 steps visibly train.  Checked: (1) training moved - the validation MSE of a
+    64 x 64 render against the target falls by >= 20 % on both paths; (2) the per-step training losses (same batch on
+    both sides) stay within 5 % of each other, mean within 1 %; (3) the final 64 x 64 renders of the two trained
+    networks agree to 5e-2 max abs / 35 dB PSNR, and differ from each other far less than either moved from the initial
+    render.  (An optimisation trajectory amplifies rounding; the bound is on what training produces.)"""
     from humannerf_b200 import ops
     from humannerf_b200.config import make_cfg
     from humannerf_b200.data import make_train_batch
@@ -204,6 +217,7 @@ def test_training_trajectory_bf16_graph_tracks_fp32():
         nets[prec] = n.to(DEV).train()
     # target: the subject's silhouette (initial render) painted with a smooth colour pattern - something to learn
     img0, a0 = render(nets['fp32'], 'fp32', H, W)
+    init64, a64 = render(nets['fp32'], 'fp32', 64, 64)
     yy, xx = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing='ij')
     pattern = torch.stack([0.5 + 0.5 * torch.sin(xx / 9.0), 0.5 + 0.5 * torch.cos(yy / 11.0), 0.3 + 0.0 * xx], -1)
     target = (pattern * a0[..., None]).cpu().numpy().astype(np.float32)
@@ -245,21 +259,24 @@ def test_training_trajectory_bf16_graph_tracks_fp32():
     curves['bf16'] = torch.stack(ls).cpu().numpy()
     step.graph = None
 
-    k = 20
-    smooth = {p: np.convolve(c, np.ones(k) / k, mode='valid') for p, c in curves.items()}
-    rel = np.abs(smooth['bf16'] - smooth['fp32']) / smooth['fp32']
     for p, c in curves.items():
-        print(f'[trajectory] {p}: loss first {k} steps {c[:k].mean():.5f} -> last {k} steps {c[-k:].mean():.5f}; every 25th: '
-              + ' '.join(f'{v:.4f}' for v in c[::25]))
-    for p, c in curves.items():
-        assert c[-k:].mean() < 0.95 * c[:k].mean(), (p, 'loss did not fall')
-    print(f'[trajectory] smoothed (window {k}) loss curves: max rel difference {rel.max():.3e}, mean {rel.mean():.3e}, '
-          f'final {rel[-1]:.3e}; step-0 losses {curves["fp32"][0]:.6f} / {curves["bf16"][0]:.6f}')
-    assert rel.max() <= 5e-2, float(rel.max())
+        print(f'[trajectory] {p}: training loss every 25th step: ' + ' '.join(f'{v:.5f}' for v in c[::25]))
+    rel = np.abs(curves['bf16'] - curves['fp32']) / curves['fp32']
+    print(f'[trajectory] per-step training loss, bf16 graph vs fp32 eager (same batches): max rel difference {rel.max():.3e}, '
+          f'mean {rel.mean():.3e}, last step {rel[-1]:.3e}')
     im32, _ = render(nets['fp32'], 'fp32', 64, 64)
     im16, _ = render(nets['bf16'], 'bf16', 64, 64)
+    yy64, xx64 = torch.meshgrid(torch.arange(64, device=DEV) * 2.0, torch.arange(64, device=DEV) * 2.0, indexing='ij')
+    tgt64 = torch.stack([0.5 + 0.5 * torch.sin(xx64 / 9.0), 0.5 + 0.5 * torch.cos(yy64 / 11.0), 0.3 + 0.0 * xx64], -1) * a64[..., None]
+    val = {'initial': float(torch.mean((init64 - tgt64) ** 2)), 'fp32': float(torch.mean((im32 - tgt64) ** 2)),
+           'bf16': float(torch.mean((im16 - tgt64) ** 2))}
+    moved = float((im32 - init64).abs().max())
     diff = (im32 - im16).abs()
     psnr = float(-10.0 * torch.log10(torch.mean((im32 - im16) ** 2) + 1e-20))
+    print(f'[trajectory] validation MSE of the 64x64 render vs the target: initial {val["initial"]:.5f} -> fp32-trained '
+          f'{val["fp32"]:.5f}, bf16-trained {val["bf16"]:.5f}')
     print(f'[trajectory] final 64x64 renders, bf16-trained vs fp32-trained: max abs diff {float(diff.max()):.3e}, '
-          f'mean {float(diff.mean()):.3e}, PSNR {psnr:.1f} dB')
-    assert float(diff.max()) <= 5e-2 and psnr >= 35.0
+          f'mean {float(diff.mean()):.3e}, PSNR {psnr:.1f} dB; training moved the render by up to {moved:.3f}')
+    assert val['fp32'] < 0.8 * val['initial'] and val['bf16'] < 0.8 * val['initial'], val
+    assert rel.max() <= 5e-2 and rel.mean() <= 1e-2, (float(rel.max()), float(rel.mean()))
+    assert float(diff.max()) <= 5e-2 and psnr >= 35.0 and float(diff.max()) < 0.25 * moved

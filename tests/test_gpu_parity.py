@@ -763,7 +763,8 @@ def test_device_patch_selection_bit_exact_against_reference():
     assert torch.equal(out['rays'][2, :n].cpu(), rd[sel])
     assert torch.equal(out['near'][:n, 0].cpu(), near[sel]) and torch.equal(out['far'][:n, 0].cpu(), far[sel])
     assert np.array_equal(out['scatter_index'][:n].cpu().numpy(), np.nonzero(g['patch_masks'].reshape(-1))[0])
-    assert bool((out['scatter_index'][n:] == -1).all()) and float(out['rays'][:, n:].abs().max()) == 0.0
+    if n < smp.cap:
+        assert bool((out['scatter_index'][n:] == -1).all()) and float(out['rays'][:, n:].abs().max()) == 0.0
     for i, (x, y) in enumerate(g['xy_min']):
         assert torch.equal(out['target_patches'][i].cpu(), image[y:y + P, x:x + P])
     print(f'[parity] device patch selection: {n} rays in 6 patches, select_inds / masks / div / xy_min bit-exact')
