@@ -564,11 +564,14 @@ def main():
     host_s = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    dr = sampler.draw(rng_e2e)
     for i in range(args.steps):
+        loss_val = run_step(dr if graphed is not None else torch.from_numpy(dr).to(dev))
+        # the next step's draws are made while the GPU runs this step (what a DataLoader worker does for the reference);
+        # the read-back below then waits for the step
         t0 = time.perf_counter()
         dr = sampler.draw(rng_e2e)
         host_s += time.perf_counter() - t0
-        loss_val = run_step(dr if graphed is not None else torch.from_numpy(dr).to(dev))
         _ = float(loss_val.item())                                     # device -> host read of the step's result
     e1.record()
     barrier()

@@ -161,8 +161,8 @@ def test_train_step_bf16_against_reference():
 def test_training_trajectory_bf16_graph_tracks_fp32():
     """200 Adam steps on IDENTICAL batches: the fp32 parity path stepped eagerly against the bf16 tensor-core path
     stepped as one CUDA graph (the bench configuration), same initial weights, same schedule (iterations 20000-20199:
-    inside the hann window, condition code on), perturb = 0 so that neither side draws random numbers, ten times the
-    reference's learning rates so that 200 steps visibly train.  Checked: (1) training moved - the validation MSE of a
+    inside the hann window, condition code on), perturb = 0 so that neither side draws random numbers, the reference's
+    learning rates.  Checked: (1) training moved - the validation MSE of a
     64 x 64 render against the target falls by >= 20 % on both paths; (2) the per-step training losses (same batch on
     both sides) stay within 5 % of each other, mean within 1 %; (3) the final 64 x 64 renders of the two trained
     networks agree to 5e-2 max abs / 35 dB PSNR, and differ from each other far less than either moved from the initial
@@ -204,23 +204,21 @@ def test_training_trajectory_bf16_graph_tracks_fp32():
     cfg.perturb = 0.0
     cfg.b200.heavy_outputs = False
     cfg.b200.jitter_rng = 'device'
-    # ten times the reference's learning rates: 200 steps must visibly train (the comparison is about what training
-    # produces, and a trajectory that hardly moves would agree trivially)
-    cfg.train.lr = 10 * cfg.train.lr
-    for key in [k for k in cfg.train.keys() if k.startswith('lr_')]:
-        cfg.train[key] = 10 * cfg.train[key]
     sd0 = syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True)
     nets = {}
     for prec in ('fp32', 'bf16'):
         n = Network()
         n.load_state_dict(sd0, strict=True)
         nets[prec] = n.to(DEV).train()
-    # target: the subject's silhouette (initial render) painted with a smooth colour pattern - something to learn
+    # target: the initial render with a smooth colour tint (same silhouette and density, other colours): something to
+    # learn that does not reward switching the density off (the fixture's density row is scaled x25 and collapses to
+    # alpha = 0 within a few Adam steps if the target is much darker than the render)
+    def tint(h, w, scale):
+        yy, xx = torch.meshgrid(torch.arange(h, device=DEV) * scale, torch.arange(w, device=DEV) * scale, indexing='ij')
+        return torch.stack([1.0 + 0.4 * torch.sin(xx / 9.0), 1.0 + 0.4 * torch.cos(yy / 11.0), 0.7 + 0.0 * xx], -1)
     img0, a0 = render(nets['fp32'], 'fp32', H, W)
     init64, a64 = render(nets['fp32'], 'fp32', 64, 64)
-    yy, xx = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing='ij')
-    pattern = torch.stack([0.5 + 0.5 * torch.sin(xx / 9.0), 0.5 + 0.5 * torch.cos(yy / 11.0), 0.3 + 0.0 * xx], -1)
-    target = (pattern * a0[..., None]).cpu().numpy().astype(np.float32)
+    target = torch.clamp(img0 * tint(H, W, 1.0), 0.0, 1.0).cpu().numpy().astype(np.float32)
     o, d, nr, fa, pix, m = frame_rays(H, W)
     mask_np = m.cpu().numpy().astype(bool)
     subject = (a0 > 0.5).cpu().numpy() & mask_np.reshape(H, W)
@@ -266,8 +264,10 @@ def test_training_trajectory_bf16_graph_tracks_fp32():
           f'mean {rel.mean():.3e}, last step {rel[-1]:.3e}')
     im32, _ = render(nets['fp32'], 'fp32', 64, 64)
     im16, _ = render(nets['bf16'], 'bf16', 64, 64)
-    yy64, xx64 = torch.meshgrid(torch.arange(64, device=DEV) * 2.0, torch.arange(64, device=DEV) * 2.0, indexing='ij')
-    tgt64 = torch.stack([0.5 + 0.5 * torch.sin(xx64 / 9.0), 0.5 + 0.5 * torch.cos(yy64 / 11.0), 0.3 + 0.0 * xx64], -1) * a64[..., None]
+    tgt64 = torch.clamp(init64 * tint(64, 64, 2.0), 0.0, 1.0)
+    _, a32 = render(nets['fp32'], 'fp32', 64, 64)
+    print(f'[trajectory] mean alpha of the 64x64 render: initial {float(a64.mean()):.4f}, after training {float(a32.mean()):.4f}')
+    assert float(a32.mean()) > 0.5 * float(a64.mean()), 'the density collapsed: the comparison would be vacuous'
     val = {'initial': float(torch.mean((init64 - tgt64) ** 2)), 'fp32': float(torch.mean((im32 - tgt64) ** 2)),
            'bf16': float(torch.mean((im16 - tgt64) ** 2))}
     moved = float((im32 - init64).abs().max())
