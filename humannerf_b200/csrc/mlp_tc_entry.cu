@@ -33,11 +33,11 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
       if (n < job.valid_n) {
         if (job.src && k < job.valid_k)
           v = job.transpose ? job.src[(int64_t)(job.src_row0 + k) * job.src_ld + job.src_col0 + n]
-                            : job.src[(int64_t)n * job.src_ld + job.src_col0 + k];
+                            : job.src[(int64_t)(job.src_n0 + n) * job.src_ld + job.src_col0 + k];
         if (k == job.bias_row) {
-          v = job.bias ? job.bias[n] : 0.0f;
+          v = job.bias ? job.bias[job.src_n0 + n] : 0.0f;
           if (job.fold_w && cond)
-            for (int c = 0; c < job.fold_k; ++c) v += job.fold_w[(int64_t)n * job.fold_ld + c] * cond[c];
+            for (int c = 0; c < job.fold_k; ++c) v += job.fold_w[(int64_t)(job.src_n0 + n) * job.fold_ld + c] * cond[c];
         }
       }
       f[i] = v;
@@ -57,6 +57,21 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
 int launch_field_tc2(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
                      const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
                      const TrainBufs* bufs, int sms, cudaStream_t st);
+
+// mlp_tc_ts.cu
+int launch_field_ts(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
+                    const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                    const TrainBufs* bufs, int sms, cudaStream_t st);
+
+// Forward kernel selection, read once per process: the TS kernel (hidden activations in tensor memory, mlp_tc_ts.cu) is the
+// default whenever the MLP widths allow it; HN_TC_FWD=ss keeps the SS kernel of mlp_tc_2sm.cu (activations in shared memory).
+static inline bool use_ts_forward() {
+  static const bool v = [] {
+    const char* e = getenv("HN_TC_FWD");
+    return e == nullptr || e[0] != 's';
+  }();
+  return v;
+}
 
 int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples) {
   TcPlan plan;
@@ -147,6 +162,10 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
     if (!use_relu_bits()) memset(bufs.bits, 0, sizeof(bufs.bits));
   }
+  if (use_ts_forward() && !plan.ts_chunks.empty())
+    return launch_field_ts(plan, static_cast<const uint8_t*>(packed), n_samples, n_samples_dev, x_skel, hann_w,
+                           ignore_non_rigid ? 1 : 0, raw, xyz, offsets, save_for_backward ? &bufs : nullptr, sms,
+                           as_stream(stream));
   return launch_field_tc2(plan, static_cast<const uint8_t*>(packed), n_samples, n_samples_dev, x_skel, hann_w,
                           ignore_non_rigid ? 1 : 0, raw, xyz, offsets, save_for_backward ? &bufs : nullptr, sms,
                           as_stream(stream));

@@ -1,0 +1,457 @@
+// Canonical field, tensor-core forward with the hidden activations in TENSOR MEMORY ("TS" form of tcgen05.mma):
+//
+//   hann-PE -> non-rigid MLP -> xyz = x_skel + offset -> PE -> canonical MLP -> raw      (one persistent kernel)
+//
+// The SS-form kernel (mlp_tc_2sm.cu) keeps the activations of two tile sets in shared memory and is bound by the
+// shared-memory bandwidth: per 256-wide layer and SM the tensor core reads 128 KB of A and 128 KB of B, the epilogue
+// writes 128 KB, the weight ring takes 64 KB (+ 128 KB read by the image stores when training) - 4000-5000 clk at
+// 128 B/clk against 4096 clk of MMA time, and an epilogue that overlaps MMAs stretches both (measured).
+// Here the A operand of every hidden layer is read from tensor memory and written there by the epilogue
+// (tcgen05.ld -> ReLU -> bf16 -> tcgen05.st), training images leave the registers with 16-byte global stores (a warp
+// writes two full 256-byte runs of the T16 image), and shared memory only holds the weight ring and the 16 KB
+// encoding blocks: 128 KB of B reads + 64 KB of ring writes per layer and SM.
+//
+//   * CTA pair (tcgen05 cta_group::2), ONE 128-row tile per CTA: M = 256 MMAs, each CTA streams half of every weight
+//     chunk (rows [0, N/2) / [N/2, N)) through an 8 x 16 KB ring, as in the SS kernel;
+//   * tensor memory per CTA (512 columns): A0 [0,128) | A1 [128,256) (bf16 pairs: column c = features 2c, 2c + 1;
+//     layer l reads the buffer layer l - 1 wrote and its epilogue writes the other one) | D0 [256,384) | D1 [384,512);
+//   * a 256-wide layer is two N = 128 halves: half 0 accumulates into D0, half 1 into D1.  The epilogue of half 0 (8 of
+//     the 16 epilogue warps) runs under the MMAs of half 1, and the epilogue of half 1 under the first K = 128 steps
+//     of the NEXT layer's half 0, which only need features [0,128) - written by the epilogue of half 0 long before.
+//     Two mbarriers a_ready[0/1] (features [0,128) / [128,256) stored, accumulator half drained) gate the issuer;
+//   * encoding / bias steps stay SS: the encoding block of the current MLP is an ordinary shared-memory operand
+//     (constant-1 column x bias row, as in the SS kernel);
+//   * 128-wide layers (non-rigid MLP) and the N = 16 output layers use D0 only.
+//
+// Outputs are those of the SS kernel bit for bit in layout (raw / xyz / offsets, T16 activation and encoding images,
+// 1-bit ReLU mask images), so the backward chain and the weight-gradient kernel are unchanged.
+// Reference semantics: embedders/hannw_fourier.py:38-49, embedders/fourier.py:9-38,
+// non_rigid_motion_mlps/mlp_offset.py:74-114, canonical_mlps/mlp_rgb_sigma.py:132-206.
+#include <cstdlib>
+
+#include "mlp_tc_plan.cuh"
+#include "mlp_tc_enc.cuh"
+#include "mlp_tc_2sm.cuh"
+
+namespace hn {
+
+namespace ts {
+constexpr int kStagesTs = 8;
+constexpr uint32_t kStageBytesTs = 16384;                               // per CTA (half a 32 KB chunk)
+constexpr uint32_t kRingOffTs = 2 * kActPeTile;                        // two encoding blocks of 16 KB in front
+constexpr uint32_t kBarOffTs = kRingOffTs + kStagesTs * kStageBytesTs;
+// barriers: full[8] floc[8] empty[8] acc_full[2] a_ready[2] pe_ready[2], then the tmem slot
+constexpr uint32_t kSmemTs = kBarOffTs + 512;
+constexpr int kEpiWarpsTs = 16;
+constexpr int kThreadsTs = (2 + kEpiWarpsTs) * 32;                     // producer, issuer (relay in the peer), epilogue
+constexpr uint32_t kColA = 0, kColD = 256;
+static_assert(kSmemTs <= 232448, "shared memory budget");
+}  // namespace ts
+
+struct TsLoadTab {            // producer: x = byte offset of the chunk in the weight image, y = bytes (both halves)
+  uint2 e[kMaxChunks];
+};
+
+__device__ __forceinline__ void umma2_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one 8-column chunk `ch` of an encoding row (columns as in write_encoding_half of mlp_tc_enc.cuh) -> the shared-memory
+// operand block and, when training, the T16 image row
+template <bool kIncludeInput>
+__device__ __forceinline__ void write_encoding_chunk(uint32_t region, int row, int ch, const float x[3], int n_freqs,
+                                                     const float* __restrict__ weights, int pad, uint8_t* img_row) {
+  constexpr int base = kIncludeInput ? 3 : 0;
+  if (ch * 8 >= pad) return;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = ch * 8 + i;
+    float val = 0.0f;
+    if (c < base) {
+      val = c == 0 ? x[0] : (c == 1 ? x[1] : x[2]);
+    } else {
+      const int cc = c - base, k = cc / 6, r = cc - 6 * k, a = r >= 3 ? r - 3 : r;
+      if (k < n_freqs) {
+        const float xa = a == 0 ? x[0] : (a == 1 ? x[1] : x[2]);
+        const float arg = xa * (float)(1 << k);
+        const float t = r >= 3 ? __cosf(arg) : __sinf(arg);
+        val = weights ? __ldg(weights + k) * t : t;            // global pointer: no dynamically indexed registers
+      }
+    }
+    v[i] = val;
+  }
+  if (ch * 8 + 8 == pad) v[7] = 1.0f;
+  store8(region, row, ch, v, img_row);
+}
+
+template <bool kStore>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ts::kThreadsTs, 1)
+field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ TsLoadTab ltab, int n_chunks, int first_chunk,
+                const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
+                const float* __restrict__ x_skel, const float* __restrict__ hann_w, int ignore_non_rigid,
+                float* __restrict__ raw, float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs) {
+  using namespace ts;
+  const int64_t n_samples = n_dev ? min(max(__ldg(n_dev), (int64_t)0), n_cap) : n_cap;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
+  const uint8_t* image = packed + hdr->image_off;
+
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_ring = s_base + kRingOffTs;
+  const uint32_t s_full = s_base + kBarOffTs;                // leader: own bulk copy + forwarded arrive of the peer
+  const uint32_t s_floc = s_full + kStagesTs * 8;            // peer: its own bulk copy
+  const uint32_t s_empty = s_floc + kStagesTs * 8;           // both: multicast commit of the issuer
+  const uint32_t s_acc_full = s_empty + kStagesTs * 8;       // both: accumulator half complete (multicast commit)
+  const uint32_t s_a_ready = s_acc_full + 2 * 8;             // leader: 8 epilogue warps x 2 CTAs per half
+  const uint32_t s_pe_ready = s_a_ready + 2 * 8;             // leader: 16 epilogue warps x 2 CTAs per encoding block
+  const uint32_t s_tmem_slot = s_pe_ready + 2 * 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOffTs + (3 * kStagesTs + 6) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t n_duos = (n_samples + 2 * kTileM - 1) / (2 * kTileM);           // 2 tiles = 256 samples per pass
+  const int64_t n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int nr_layers = (int)hdr->nr_layers, cn_layers = (int)hdr->cn_layers;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStagesTs; ++s) {
+      mbar_init(s_full + s * 8, 2);
+      mbar_init(s_floc + s * 8, 1);
+      mbar_init(s_empty + s * 8, 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(s_acc_full + h * 8, 1);
+      mbar_init(s_a_ready + h * 8, 2 * (kEpiWarpsTs / 2));
+      mbar_init(s_pe_ready + h * 8, 2 * kEpiWarpsTs);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {            // the same warp of both CTAs allocates collectively
+    tmem_alloc2(s_tmem_slot, kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();         // barrier inits visible before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: this CTA's half of every chunk =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t s_done = leader ? s_full : s_floc;
+      for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
+        for (int c = first_chunk; c < n_chunks; ++c) {
+          const uint2 e = ltab.e[c];
+          const uint32_t half = e.y >> 1;
+          mbar_wait(s_empty + stage * 8, phase ^ 1, 1);
+          mbar_expect_tx(s_done + stage * 8, half);
+          tma_bulk_g2s(s_ring + stage * kStageBytesTs, image + e.x + rank * half, half, s_done + stage * 8);
+          if (++stage == (uint32_t)kStagesTs) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader): the whole warp runs the loop, one elected lane issues =====================
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t pe_lo0 = ((s_base & 0x3FFFFu) >> 4) | ((kLboA >> 4) << 16);
+      const uint32_t pe_lo1 = (((s_base + kActPeTile) & 0x3FFFFu) >> 4) | ((kLboA >> 4) << 16);
+      const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
+      uint32_t stage = 0, phase = 0, full_ok = 0;
+      uint32_t a_phase0 = 0, a_phase1 = 0, pe_phase0 = 0, pe_phase1 = 0;
+      for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
+        for (int c = first_chunk; c < n_chunks; ++c) {
+          const uint2 e = itab.e[c];
+          const uint32_t a_off = e.x & 0xFFFFu, n = e.x >> 16;
+          const uint32_t ksteps = e.y & 0xFFu, flags = (e.y >> 8) & 0xFFu, flags2 = (e.y >> 16) & 0xFFu;
+          if (flags & kTsWaitPe) {
+            if (flags & kTsPeCn) { mbar_wait(s_pe_ready + 8, pe_phase1, 6); pe_phase1 ^= 1; }
+            else { mbar_wait(s_pe_ready, pe_phase0, 6); pe_phase0 ^= 1; }
+          }
+          if (flags & kTsWaitA0) { mbar_wait(s_a_ready, a_phase0, 2); a_phase0 ^= 1; }
+          if (flags & kTsWaitA1) { mbar_wait(s_a_ready + 8, a_phase1, 2); a_phase1 ^= 1; }
+          if (!full_ok) mbar_wait(s_full + stage * 8, phase, 3);
+          tc_fence_after();
+          {   // probe the NEXT chunk's weights now: the round trip overlaps the MMA issue below
+            const uint32_t ns = stage + 1 == (uint32_t)kStagesTs ? 0u : stage + 1;
+            full_ok = mbar_test_wait(s_full + ns * 8, ns == 0u ? phase ^ 1u : phase);
+          }
+          const uint32_t idesc = make_idesc2(n);
+          const uint32_t d_tmem = tmem_base + kColD + ((flags & kTsD1) ? 128u : 0u);
+          uint32_t b_lo = (ring_lo + stage * (kStageBytesTs >> 4)) | ((n >> 1) << 16);    // LBO = (n/2) * 16 bytes
+          if (elect_one()) {
+            uint32_t acc = (flags & kTsFirst) ? 0u : 1u;
+            if (flags & kTsSS) {
+              uint32_t a_lo = ((flags & kTsPeCn) ? pe_lo1 : pe_lo0) + a_off * (kLboA >> 4);
+              for (uint32_t k = 0; k < ksteps; ++k) {
+                umma2_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+                acc = 1u;
+                a_lo += (2u * kLboA) >> 4;
+                b_lo += n;
+              }
+            } else {
+              uint32_t a_t = tmem_base + kColA + ((flags2 & 1u) ? 128u : 0u) + a_off;
+              for (uint32_t k = 0; k < ksteps; ++k) {
+                umma2_ts_bf16(d_tmem, a_t, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+                acc = 1u;
+                a_t += 8u;                                   // 16 bf16 of K = 8 columns
+                b_lo += n;
+              }
+            }
+            umma2_commit_mc(s_empty + stage * 8);            // the slot is free in both CTAs once these MMAs retire
+            if (flags & kTsLast) umma2_commit_mc(s_acc_full + ((flags & kTsD1) ? 8u : 0u));
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)kStagesTs) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
+      // ===================== relay (peer): forwards "my half of the chunk has landed" to the leader =====================
+      const uint32_t full_remote = mapa_cluster(s_full, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
+        for (int c = first_chunk; c < n_chunks; ++c) {
+          mbar_wait(s_floc + stage * 8, phase, 5);
+          mbar_arrive_remote(full_remote + stage * 8);
+          if (++stage == (uint32_t)kStagesTs) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2 .. 17) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int nh = ew >> 3;                       // accumulator half this warp drains (features [128 nh, 128 nh + 128))
+    const int sub = (ew >> 2) & 1;                // which 64 of those 128 columns
+    const int part = nh * 2 + sub;                // 0..3: share of the per-row work among the four warps of a quarter
+    const int row = quarter * 32 + lane;          // row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t pe_nr = s_base, pe_cn = s_base + kActPeTile;
+    const uint32_t bar_a = mapa_cluster(s_a_ready + (uint32_t)nh * 8, 0);            // in the leader
+    const uint32_t bar_pe0 = mapa_cluster(s_pe_ready, 0), bar_pe1 = mapa_cluster(s_pe_ready + 8, 0);
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    const int nr_freqs = (int)hdr->nr_freqs, cn_freqs = (int)hdr->cn_freqs;
+    const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
+    const int nr_width = (int)hdr->nr_width, cn_width = (int)hdr->cn_width;
+
+    // encoding block of one MLP for this thread's row: the four warps of a quarter write two 8-column chunks each
+    auto encode = [&](bool cn, const float p[3], int64_t tile_idx, bool store) {
+      const int pad = cn ? cn_pad : nr_pad;
+      uint8_t* img = (kStore && store) ? bufs.pe[cn ? 1 : 0] + image_row_offset(tile_idx, row, pad) : nullptr;
+      if (cn) {
+        write_encoding_chunk<true>(pe_cn, row, part, p, cn_freqs, nullptr, pad, img);
+        write_encoding_chunk<true>(pe_cn, row, part + 4, p, cn_freqs, nullptr, pad, img);
+      } else {
+        write_encoding_chunk<false>(pe_nr, row, part, p, nr_freqs, hann_w, pad, img);
+        write_encoding_chunk<false>(pe_nr, row, part + 4, p, nr_freqs, hann_w, pad, img);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(cn ? bar_pe1 : bar_pe0);
+    };
+    auto load_x = [&](int64_t duo, float p[3]) {
+      const int64_t sample = (duo * 2 + (int64_t)rank) * kTileM + row;
+      const bool ok = duo < n_duos && sample < n_samples;
+      p[0] = ok ? __ldg(x_skel + sample * 3 + 0) : 0.f;
+      p[1] = ok ? __ldg(x_skel + sample * 3 + 1) : 0.f;
+      p[2] = ok ? __ldg(x_skel + sample * 3 + 2) : 0.f;
+    };
+    // hidden layer `l` of MLP `m` (width `width`): drain this warp's 64 accumulator columns into the A buffer (l & 1)
+    auto hidden = [&](int m, int l, int width, int64_t tile_idx, bool store) {
+      const bool two = width > 128;
+      mbar_wait(s_acc_full, acc_phase0, 4);
+      acc_phase0 ^= 1;
+      if (two && nh == 1) { mbar_wait(s_acc_full + 8, acc_phase1, 4); acc_phase1 ^= 1; }
+      if (two || nh == 0) {
+        tc_fence_after();
+        const int col0 = nh * 128 + sub * 64;                                  // first feature this warp owns
+        const uint32_t t_d = t_lane + kColD + (uint32_t)col0;
+        const uint32_t t_a = t_lane + kColA + ((l & 1) ? 128u : 0u) + (uint32_t)(col0 >> 1);
+        uint8_t* img = nullptr;
+        uint8_t* bits_rec = nullptr;
+        if (kStore && store) {
+          img = bufs.h[m][l] + image_row_offset(tile_idx, row, width) + (size_t)(col0 >> 3) * 256;
+          uint8_t* b = bufs.bits[m][l];
+          // record (tile, half, row) of width / 2 columns: this warp's 64 columns are words [0,2) of half `sub`
+          // (width 128) or words [2 sub, 2 sub + 2) of half `nh` (width 256)
+          if (b) bits_rec = two ? b + relu_bits_offset(tile_idx, nh, row, 128) + sub * 8
+                                : b + relu_bits_offset(tile_idx, sub, row, 64);
+        }
+        uint32_t pk[32];
+        uint32_t m01[2] = {0u, 0u};
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_d + (uint32_t)(g * 32), v);
+          tmem_ld_wait();
+          uint32_t mm = 0u;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t h2 = pack_relu_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            pk[g * 16 + i] = h2;
+            if (kStore) mm = relu_bits_step(mm, h2);
+          }
+          m01[g] = mm;
+        }
+        tmem_st32(t_a, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(bar_a);
+        if (kStore && img) {
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(img + (size_t)c8 * 256) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+          if (bits_rec) *reinterpret_cast<uint2*>(bits_rec) = make_uint2(m01[0], m01[1]);
+        }
+      }
+      if (two && nh == 0) { mbar_wait(s_acc_full + 8, acc_phase1, 4); acc_phase1 ^= 1; }    // stay in step with the barrier
+    };
+
+    float x[3];
+    load_x(cluster_id, x);
+    if (cluster_id < n_duos) {
+      const int64_t t0 = cluster_id * 2 + (int64_t)rank;
+      encode(ignore_non_rigid != 0, x, t0, t0 < bufs.n_tiles);
+    }
+    for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
+      const int64_t tile_idx = duo * 2 + (int64_t)rank;
+      const int64_t sample = tile_idx * kTileM + row;
+      const bool valid = sample < n_samples;
+      const bool store = kStore && tile_idx < bufs.n_tiles;      // the training images hold ceil(P/128) tiles
+      float q[3] = {x[0], x[1], x[2]};                           // position fed to the canonical encoding
+      if (!ignore_non_rigid) {
+        for (int l = 0; l + 1 < nr_layers; ++l) hidden(0, l, nr_width, tile_idx, store);
+        // output layer: offsets in accumulator columns [0,3) of D0; every warp reads them (all need q for the encoding)
+        mbar_wait(s_acc_full, acc_phase0, 4);
+        acc_phase0 ^= 1;
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16(t_lane + kColD, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float o0 = __uint_as_float(v[0]), o1 = __uint_as_float(v[1]), o2 = __uint_as_float(v[2]);
+        q[0] = x[0] + o0; q[1] = x[1] + o1; q[2] = x[2] + o2;
+        if (valid && part == 0) {
+          off_out[sample * 3 + 0] = o0; off_out[sample * 3 + 1] = o1; off_out[sample * 3 + 2] = o2;
+        }
+        encode(true, q, tile_idx, store);
+      }
+      for (int l = 0; l + 1 < cn_layers; ++l) hidden(1, l, cn_width, tile_idx, store);
+      {
+        mbar_wait(s_acc_full, acc_phase0, 4);
+        acc_phase0 ^= 1;
+        tc_fence_after();
+        if (part == 0) {
+          uint32_t v[16];
+          tmem_ld16(t_lane + kColD, v);
+          tmem_ld_wait();
+          if (valid) {
+            float4 r;
+            r.x = __uint_as_float(v[0]); r.y = __uint_as_float(v[1]);
+            r.z = __uint_as_float(v[2]); r.w = __uint_as_float(v[3]);
+            reinterpret_cast<float4*>(raw)[sample] = r;
+            xyz_out[sample * 3 + 0] = q[0]; xyz_out[sample * 3 + 1] = q[1]; xyz_out[sample * 3 + 2] = q[2];
+            if (ignore_non_rigid) {
+              off_out[sample * 3 + 0] = 0.f; off_out[sample * 3 + 1] = 0.f; off_out[sample * 3 + 2] = 0.f;
+            }
+          }
+        }
+        tc_fence_before();
+      }
+      // next pass: positions and first encoding block (its arrive also tells the issuer that D0 has been drained)
+      const int64_t next = duo + n_clusters;
+      load_x(next, x);
+      if (next < n_duos) {
+        const int64_t tn = next * 2 + (int64_t)rank;
+        encode(ignore_non_rigid != 0, x, tn, kStore && tn < bufs.n_tiles);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peer may still arrive on / commit into this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+// Launch: persistent, as many clusters as can be co-resident.  Returns <0 / cudaError_t like every entry point.
+int launch_field_ts(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
+                    const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
+                    const TrainBufs* bufs, int sms, cudaStream_t st) {
+  using namespace ts;
+  if (plan.ts_chunks.empty()) return fail_arg("hn_field_fwd: the TS kernel needs MLP widths of 128 or 256");
+  static int max_clusters_cached = 0;
+  if (max_clusters_cached == 0) {
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTs),
+                      "hn_field_fwd/ts smem attr"));
+    HN_TRY(check_cuda(cudaFuncSetAttribute(field_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTs),
+                      "hn_field_fwd/ts smem attr"));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * (sms / 2)));
+    cfg.blockDim = dim3(kThreadsTs);
+    cfg.dynamicSmemBytes = kSmemTs;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    HN_TRY(check_cuda(cudaOccupancyMaxActiveClusters(&n, field_ts_kernel<false>, &cfg), "hn_field_fwd/ts occupancy"));
+    if (n <= 0) return fail_arg("hn_field_fwd: no 2-CTA cluster of the TS kernel fits on this device");
+    max_clusters_cached = n;
+  }
+  IssueTab itab;
+  TsLoadTab ltab;
+  memset(&itab, 0, sizeof(itab));
+  memset(&ltab, 0, sizeof(ltab));
+  int first_chunk = 0;
+  for (size_t c = 0; c < plan.ts_chunks.size(); ++c) {
+    const TsChunk& ch = plan.ts_chunks[c];
+    itab.e[c] = make_uint2((uint32_t)ch.a_off | ((uint32_t)ch.n << 16),
+                           (uint32_t)ch.ksteps | ((uint32_t)ch.flags << 8) | ((uint32_t)ch.flags2 << 16));
+    ltab.e[c] = make_uint2(ch.w_off, ch.bytes);
+    if (ignore_non_rigid && (ch.flags2 & 2)) first_chunk = (int)c + 1;      // chunks of the skipped MLP are skipped too
+  }
+  const int64_t n_duos = ceil_div<int64_t>(n_samples, 2 * kTileM);
+  const unsigned grid = 2u * (unsigned)std::min<int64_t>(n_duos, (int64_t)max_clusters_cached);
+  const int n_chunks = (int)plan.ts_chunks.size();
+  if (bufs) {
+    field_ts_kernel<true><<<grid, kThreadsTs, kSmemTs, st>>>(itab, ltab, n_chunks, first_chunk, packed, n_samples, n_samples_dev,
+                                                             x_skel, hann_w, ignore_non_rigid, raw, xyz, offsets, *bufs);
+  } else {
+    TrainBufs none;
+    memset(&none, 0, sizeof(none));
+    field_ts_kernel<false><<<grid, kThreadsTs, kSmemTs, st>>>(itab, ltab, n_chunks, first_chunk, packed, n_samples, n_samples_dev,
+                                                              x_skel, hann_w, ignore_non_rigid, raw, xyz, offsets, none);
+  }
+  return launched("hn_field_fwd/tcgen05 ts");
+}
+
+}  // namespace hn

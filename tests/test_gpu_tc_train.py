@@ -469,17 +469,20 @@ def test_relu_mask_images_match_activation_read(tmp_path, P, ignore):
     print(f'[parity] ReLU mask images vs activation read [P={P},ignore={ignore}]: worst rel L2 over {len(want.files)} tensors {worst:.2e}')
 
 
-@pytest.mark.parametrize('variant', ['2sm-8-stages', 'read-activations'])
+@pytest.mark.parametrize('variant', ['ss-forward', '2sm-8-stages', 'read-activations'])
 def test_other_forward_kernels_parity(variant):
-    """The tcgen05 forward kernel is the cta_group::2 kernel of csrc/mlp_tc_2sm.cu with a 4 x 16 KB ring.  Its two
-    build-time-equivalent variants must pass the same forward parity and training tests: an 8 x 8 KB ring
-    (HN_TC_2SM_STAGES=8) and the backward chain masking with the stored activations instead of the 1-bit images
-    (HN_TC_RELU_BITS=0).  The choice is read once per process (the weight image depends on it), hence the subprocess."""
+    """The default tcgen05 forward kernel keeps the hidden activations in tensor memory (csrc/mlp_tc_ts.cu).  The
+    alternatives must pass the same forward parity and training tests: HN_TC_FWD=ss (activations in shared memory,
+    csrc/mlp_tc_2sm.cu, 4 x 16 KB ring), the same with an 8 x 8 KB ring (HN_TC_2SM_STAGES=8), and the backward chain
+    masking with the stored activations instead of the 1-bit images (HN_TC_RELU_BITS=0).  The choices are read once
+    per process, hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
-    if variant == '2sm-8-stages':
-        env['HN_TC_2SM_STAGES'] = '8'
+    if variant == 'ss-forward':
+        env['HN_TC_FWD'] = 'ss'
+    elif variant == '2sm-8-stages':
+        env['HN_TC_FWD'], env['HN_TC_2SM_STAGES'] = 'ss', '8'
     else:
         env['HN_TC_RELU_BITS'] = '0'      # backward chain masks with the stored activations instead of the 1-bit images
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', '-k',
