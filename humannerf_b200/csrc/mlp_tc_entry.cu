@@ -46,8 +46,10 @@ __global__ void pack_weights_kernel(const PackJob* __restrict__ jobs, int n_jobs
     o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
     size_t dst = (size_t)kg * job.n * 16 + (size_t)n * 16;
     if (job.split) {
+      // two half images (rows [0, n/2) then [n/2, n)); a TS job fills K rows [dst_k0, dst_k0 + kc) of a dst_kc-row chunk
       const int nh = job.n >> 1, r = n >= nh ? 1 : 0;
-      dst = (size_t)r * (job.kc / 8) * nh * 16 + (size_t)kg * nh * 16 + (size_t)(n - r * nh) * 16;
+      const int kc_img = job.dst_kc > 0 ? job.dst_kc : job.kc, kg_img = kg + job.dst_k0 / 8;
+      dst = (size_t)r * (kc_img / 8) * nh * 16 + (size_t)kg_img * nh * 16 + (size_t)(n - r * nh) * 16;
     }
     *reinterpret_cast<uint4*>(image + job.w_off + dst) = o;
   }

@@ -57,29 +57,31 @@ struct BwdRound {
 };
 static_assert(sizeof(BwdRound) == 8, "BwdRound must be 8 bytes");
 
-// One weight chunk of the TS-mode forward kernel (mlp_tc_ts.cu): the A operand of the hidden layers lives in TENSOR
-// memory (written by the epilogue with tcgen05.st), only the encoding / bias steps read A from shared memory.  A layer
-// of width 256 is computed as two N = 128 halves into the accumulator halves D0 / D1; per half: [encoding or bias
-// chunk, SS] then [hidden chunks of K = 128, TS].
+// One weight chunk of the TS-mode forward kernel (mlp_tc_ts.cu) = everything one accumulator half of one layer needs:
+// the A operand of the hidden layers lives in TENSOR memory (written by the epilogue with tcgen05.st), only the
+// encoding / bias step reads A from shared memory.  A layer of width 256 is computed as two N = 128 halves into the
+// accumulator halves D0 / D1.  K rows of the chunk, in issue order: [encoding block incl. the bias row, or the 16-row
+// bias step: SS] [hidden features [0,128): TS] [hidden features [128,256): TS, issued after a_ready[1]].
 struct TsChunk {
   uint32_t w_off;     // byte offset inside the weight image (two half images, one per CTA of the pair)
   uint32_t bytes;     // both halves together
-  uint16_t a_off;     // SS: index of the first core matrix (8 K columns) inside the encoding block; TS: first TMEM column
   uint16_t n;         // MMA N (128 or 16)
-  uint8_t ksteps;     // K / 16
+  uint8_t ss_a_off;   // index of the first core matrix (8 K columns) of the SS step inside the encoding block
+  uint8_t ss_ksteps;  // K / 16 of the SS step
+  uint8_t ts0_ksteps; // K / 16 of the hidden features [0,128)
+  uint8_t ts1_ksteps; // K / 16 of the hidden features [128,256) (0: none)
   uint8_t flags;      // kTs* below
   uint8_t flags2;     // bit0: A buffer (TS), bit1: chunk of the non-rigid MLP
-  uint8_t reserved;
 };
 static_assert(sizeof(TsChunk) == 16, "TsChunk must be 16 bytes");
-constexpr uint8_t kTsFirst = 1;    // first MMA of its accumulator half overwrites (no accumulate)
-constexpr uint8_t kTsLast = 2;     // last chunk of its accumulator half: commit acc_full[half]
-constexpr uint8_t kTsSS = 4;       // A operand from the encoding block in shared memory
+constexpr uint8_t kTsOut = 1;      // output layer: its completion is signalled on out_full (all epilogue warps wait there)
 constexpr uint8_t kTsD1 = 8;       // accumulator half 1
-constexpr uint8_t kTsWaitA0 = 16;  // issue only after a_ready[0] (previous layer's epilogue of features [0,128))
-constexpr uint8_t kTsWaitA1 = 32;  // ... a_ready[1] (features [128,256))
+constexpr uint8_t kTsWaitA0 = 16;  // issue only after a_ready[0] (previous layer's epilogue of features [0,128) / D0 drained)
+constexpr uint8_t kTsWaitA1 = 32;  // the [128,256) steps wait for a_ready[1]
 constexpr uint8_t kTsWaitPe = 64;  // ... pe_ready[mlp] (encoding block written; previous output accumulator drained)
-constexpr uint8_t kTsPeCn = 128;   // SS chunk reads the canonical encoding block (else the non-rigid one)
+constexpr uint8_t kTsPeCn = 128;   // the SS step reads the canonical encoding block (else the non-rigid one)
+constexpr int kMaxTsChunks = 40;
+constexpr uint32_t kTsStageBytes = 40960;      // per CTA: half of the largest chunk (N = 128, K = 64 + 256)
 
 struct TcHeader {
   uint32_t magic, n_chunks, table_off, image_off, total_bytes, reserved;
@@ -141,6 +143,7 @@ struct PackJob {            // one per chunk, consumed by pack_weights_kernel
   int32_t transpose;        // 0: B[n][k] = src[n][col0 + k];  1: B[n][k] = src[row0 + k][col0 + n]
   int32_t src_row0;
   uint32_t w_off;           // destination byte offset inside the image
+  int32_t dst_k0, dst_kc;   // dst_kc > 0: the job fills K rows [dst_k0, dst_k0 + kc) of a chunk of dst_kc K rows (TS chunks)
   int32_t src_n0;           // non-transposed: first source row (B[n][k] = src[src_n0 + n][col0 + k], bias[src_n0 + n])
   int32_t split;            // 1: the chunk is stored as two half images (rows [0,n/2) then [n/2,n)), one per CTA of a
                             // cta_group::2 pair: addr = r*(kc/8)*(n/2)*16 + (k/8)*(n/2)*16 + n'*16
@@ -288,21 +291,16 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
 
   // ---- TS-mode forward (mlp_tc_ts.cu): see TsChunk -------------------------------------------------------
   if ((p->nr_width == 128 || p->nr_width == 256) && (p->cn_width == 128 || p->cn_width == 256)) {
-    auto add_ts = [&](const float* W, int ldw, int n0, int valid_n, int n, int col0, int valid_k, int kc, int a_off,
-                      uint8_t flags, uint8_t flags2, int bias_row, const float* bias, const float* fold_w, int fold_ld,
-                      int fold_k) {
-      TsChunk c;
-      memset(&c, 0, sizeof(c));
-      c.w_off = w_off; c.bytes = (uint32_t)(n * kc * 2); c.a_off = (uint16_t)a_off; c.n = (uint16_t)n;
-      c.ksteps = (uint8_t)(kc / 16); c.flags = flags; c.flags2 = flags2;
-      plan.ts_chunks.push_back(c);
+    // one pack job per K segment of a chunk
+    auto add_seg = [&](const float* W, int ldw, int n0, int valid_n, int n, int col0, int valid_k, int kc, int dst_k0,
+                       int dst_kc, int bias_row, const float* bias, const float* fold_w, int fold_ld, int fold_k) {
       PackJob j;
       memset(&j, 0, sizeof(j));
       j.src = W; j.src_ld = ldw; j.src_n0 = n0; j.valid_n = std::max(0, std::min(n, valid_n - n0)); j.n = n; j.kc = kc;
       j.w_off = w_off; j.src_col0 = col0; j.valid_k = valid_k; j.split = 1; j.bias_row = bias_row;
+      j.dst_k0 = dst_k0; j.dst_kc = dst_kc;
       if (bias_row >= 0) { j.bias = bias; j.fold_w = fold_w; j.fold_ld = fold_ld; j.fold_k = fold_k; }
       plan.jobs.push_back(j);
-      w_off += c.bytes;
     };
     for (int m = 0; m < 2; ++m) {
       const float* const* W = m == 0 ? p->nr_w : p->cn_w;
@@ -319,33 +317,32 @@ inline int make_tc_plan(const hn_field_params* p, TcPlan& plan) {
         const bool in_pe = l == 0 || l == skip;
         const int pe_col = (l == 0) ? lead : (pe_first ? 0 : width);
         const int h_col = (l == skip && pe_first) ? pe : 0;
-        const uint8_t a_buf = (uint8_t)((l + 1) & 1);                 // layer l - 1 wrote buffer (l - 1) & 1
+        const int k_ss = in_pe ? pe_pad : 16, k_ts = l > 0 ? width : 0, k_tot = k_ss + k_ts;
         for (int dh = 0; dh < halves; ++dh) {
           const int n0 = dh * 128;
-          const uint8_t fd = dh ? kTsD1 : 0;
-          const int n_ts = l > 0 ? (out ? 1 : width / 128) : 0;       // hidden chunks that follow the SS chunk
-          uint8_t wait0 = 0;
-          if (dh == 0) wait0 = l == 0 ? kTsWaitPe : kTsWaitA0;
-          const uint8_t last_ss = n_ts == 0 ? kTsLast : 0;
+          TsChunk c;
+          memset(&c, 0, sizeof(c));
+          c.w_off = w_off; c.bytes = (uint32_t)(nn * k_tot * 2); c.n = (uint16_t)nn;
+          c.ss_a_off = (uint8_t)(in_pe ? 0 : (pe_pad - 16) / 8); c.ss_ksteps = (uint8_t)(k_ss / 16);
+          c.ts0_ksteps = (uint8_t)(std::min(k_ts, 128) / 16); c.ts1_ksteps = (uint8_t)(std::max(k_ts - 128, 0) / 16);
+          c.flags = (uint8_t)((dh ? kTsD1 : 0) | pe_sel | (out ? kTsOut : 0));
+          if (dh == 0) c.flags |= l == 0 ? kTsWaitPe : kTsWaitA0;
+          if (dh == 0 && c.ts1_ksteps) c.flags |= kTsWaitA1;
+          c.flags2 = (uint8_t)(f2m | ((l + 1) & 1));                 // layer l - 1 wrote A buffer (l - 1) & 1
+          plan.ts_chunks.push_back(c);
           if (in_pe)
-            add_ts(W[l], in_dim, n0, valid_total, nn, pe_col, pe, pe_pad, 0, (uint8_t)(kTsFirst | kTsSS | fd | wait0 | pe_sel | last_ss),
-                   f2m, pe_pad - 1, B[l], (l == 0 && lead > 0) ? W[l] : nullptr, in_dim, lead);
+            add_seg(W[l], in_dim, n0, valid_total, nn, pe_col, pe, pe_pad, 0, k_tot, pe_pad - 1, B[l],
+                    (l == 0 && lead > 0) ? W[l] : nullptr, in_dim, lead);
           else
-            add_ts(nullptr, 0, n0, valid_total, nn, 0, 0, 16, (pe_pad - 16) / 8, (uint8_t)(kTsFirst | kTsSS | fd | wait0 | pe_sel | last_ss),
-                   f2m, 15, B[l], nullptr, 0, 0);
-          for (int kh = 0; kh < n_ts; ++kh) {
-            const int kc = out ? width : 128;
-            uint8_t fl = (uint8_t)(fd | (kh == n_ts - 1 ? kTsLast : 0));
-            if (dh == 0 && (kh == 1 || (out && width > 128))) fl |= kTsWaitA1;
-            add_ts(W[l], in_dim, n0, valid_total, nn, h_col + kh * 128, kc, kc, kh * 64, fl, (uint8_t)(f2m | a_buf), -1, nullptr,
-                   nullptr, 0, 0);
-          }
+            add_seg(nullptr, 0, n0, valid_total, nn, 0, 0, 16, 0, k_tot, 15, B[l], nullptr, 0, 0);
+          if (k_ts > 0) add_seg(W[l], in_dim, n0, valid_total, nn, h_col, k_ts, k_ts, k_ss, k_tot, -1, nullptr, nullptr, 0, 0);
+          w_off += c.bytes;
         }
       }
     }
-    if ((int)plan.ts_chunks.size() > kMaxChunks) return fail_arg("hn_field(bf16): too many TS weight chunks");
+    if ((int)plan.ts_chunks.size() > kMaxTsChunks) return fail_arg("hn_field(bf16): too many TS weight chunks");
     for (const TsChunk& c : plan.ts_chunks)
-      if (c.bytes > 32768 || c.bytes % 32 || c.ksteps == 0) return fail_arg("hn_field(bf16): internal TS chunk size error");
+      if (c.bytes > 2 * kTsStageBytes || c.bytes % 32) return fail_arg("hn_field(bf16): internal TS chunk size error");
   }
 
   // ---- backward data: for layer l (last to first) dX = dZ_l W_l restricted to a column window.

@@ -12,7 +12,9 @@
 // encoding blocks: 128 KB of B reads + 64 KB of ring writes per layer and SM.
 //
 //   * CTA pair (tcgen05 cta_group::2), ONE 128-row tile per CTA: M = 256 MMAs, each CTA streams half of every weight
-//     chunk (rows [0, N/2) / [N/2, N)) through an 8 x 16 KB ring, as in the SS kernel;
+//     chunk (rows [0, N/2) / [N/2, N)) through a 4 x 40 KB ring; a chunk is everything one accumulator half of one layer
+//     needs (9 - 20 MMAs: a single issuer warp spends ~750 clk per chunk whatever its size - measured with 1 - 8 MMAs per
+//     chunk the issuer, not the tensor pipe, set the pace);
 //   * tensor memory per CTA (512 columns): A0 [0,128) | A1 [128,256) (bf16 pairs: column c = features 2c, 2c + 1;
 //     layer l reads the buffer layer l - 1 wrote and its epilogue writes the other one) | D0 [256,384) | D1 [384,512);
 //   * a 256-wide layer is two N = 128 halves: half 0 accumulates into D0, half 1 into D1.  The epilogue of half 0 (8 of
@@ -36,11 +38,11 @@
 namespace hn {
 
 namespace ts {
-constexpr int kStagesTs = 8;
-constexpr uint32_t kStageBytesTs = 16384;                               // per CTA (half a 32 KB chunk)
+constexpr int kStagesTs = 4;
+constexpr uint32_t kStageBytesTs = kTsStageBytes;                       // per CTA: half of one (layer, accumulator half) chunk
 constexpr uint32_t kRingOffTs = 2 * kActPeTile;                        // two encoding blocks of 16 KB in front
 constexpr uint32_t kBarOffTs = kRingOffTs + kStagesTs * kStageBytesTs;
-// barriers: full[8] floc[8] empty[8] acc_full[2] a_ready[2] pe_ready[2], then the tmem slot
+// barriers: full[4] floc[4] empty[4] acc_full[2] a_ready[2] pe_ready[2] out_full, then the tmem slot
 constexpr uint32_t kSmemTs = kBarOffTs + 512;
 constexpr int kEpiWarpsTs = 16;
 constexpr int kThreadsTs = (2 + kEpiWarpsTs) * 32;                     // producer, issuer (relay in the peer), epilogue
@@ -48,8 +50,20 @@ constexpr uint32_t kColA = 0, kColD = 256;
 static_assert(kSmemTs <= 232448, "shared memory budget");
 }  // namespace ts
 
-struct TsLoadTab {            // producer: x = byte offset of the chunk in the weight image, y = bytes (both halves)
-  uint2 e[kMaxChunks];
+// Timeline of one pass of cluster 0 (measurement builds only: HN_EXTRA_FLAGS=-DHN_TS_TRACE ./build.sh, read with
+// scripts/ts_trace.py): clock64 of the leader SM.  [0][c]: issuer, chunk c: {waits done, MMAs + commits issued};
+// [1][l] / [2][l]: epilogue warp 2 (half 0) / warp 10 (half 1), layer slot l: {accumulator seen, arrive done}.
+#ifdef HN_TS_TRACE
+__device__ long long g_ts_trace[3][128][2];
+#define HN_TS_T(role, idx, k) do { if (trace_on && lane == 0) g_ts_trace[role][idx][k] = clock64(); } while (0)
+#else
+#define HN_TS_T(role, idx, k) do { } while (0)
+#endif
+
+// Chunk schedule as a KERNEL PARAMETER (constant bank, warp-uniform loads; see IssueTab in mlp_tc_2sm.cuh):
+// x = n | flags << 16 | flags2 << 24, y = ss_a_off | ss_ksteps << 8 | ts0_ksteps << 16 | ts1_ksteps << 24, z = w_off, w = bytes
+struct TsTab {
+  uint4 e[kMaxTsChunks];
 };
 
 __device__ __forceinline__ void umma2_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -74,38 +88,52 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// one 8-column chunk `ch` of an encoding row (columns as in write_encoding_half of mlp_tc_enc.cuh) -> the shared-memory
-// operand block and, when training, the T16 image row
-template <bool kIncludeInput>
-__device__ __forceinline__ void write_encoding_chunk(uint32_t region, int row, int ch, const float x[3], int n_freqs,
+// one 8-column chunk kCh of an encoding row (columns as in write_encoding_half of mlp_tc_enc.cuh; the column ->
+// (frequency, axis, sin / cos) map is static) -> the shared-memory operand block and, when training, the T16 image row
+template <bool kIncludeInput, int kCh>
+__device__ __forceinline__ void write_encoding_chunk(uint32_t region, int row, const float x[3], int n_freqs,
                                                      const float* __restrict__ weights, int pad, uint8_t* img_row) {
   constexpr int base = kIncludeInput ? 3 : 0;
-  if (ch * 8 >= pad) return;
+  if (kCh * 8 >= pad) return;
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = ch * 8 + i;
+    const int c = kCh * 8 + i;
     float val = 0.0f;
     if (c < base) {
-      val = c == 0 ? x[0] : (c == 1 ? x[1] : x[2]);
+      val = x[c < 3 ? c : 0];
     } else {
       const int cc = c - base, k = cc / 6, r = cc - 6 * k, a = r >= 3 ? r - 3 : r;
-      if (k < n_freqs) {
-        const float xa = a == 0 ? x[0] : (a == 1 ? x[1] : x[2]);
-        const float arg = xa * (float)(1 << k);
+      if (k < 10 && k < n_freqs) {
+        const float arg = x[a] * (float)(1 << k);
         const float t = r >= 3 ? __cosf(arg) : __sinf(arg);
-        val = weights ? __ldg(weights + k) * t : t;            // global pointer: no dynamically indexed registers
+        val = weights ? __ldg(weights + k) * t : t;
       }
     }
     v[i] = val;
   }
-  if (ch * 8 + 8 == pad) v[7] = 1.0f;
-  store8(region, row, ch, v, img_row);
+  if (kCh * 8 + 8 == pad) v[7] = 1.0f;
+  store8(region, row, kCh, v, img_row);
+}
+// the share of warp `part` (0..3) of a row's encoding: chunks part and part + 4
+template <bool kIncludeInput>
+__device__ __forceinline__ void write_encoding_part(uint32_t region, int row, int part, const float x[3], int n_freqs,
+                                                    const float* __restrict__ weights, int pad, uint8_t* img_row) {
+  switch (part) {
+    case 0: write_encoding_chunk<kIncludeInput, 0>(region, row, x, n_freqs, weights, pad, img_row);
+            write_encoding_chunk<kIncludeInput, 4>(region, row, x, n_freqs, weights, pad, img_row); break;
+    case 1: write_encoding_chunk<kIncludeInput, 1>(region, row, x, n_freqs, weights, pad, img_row);
+            write_encoding_chunk<kIncludeInput, 5>(region, row, x, n_freqs, weights, pad, img_row); break;
+    case 2: write_encoding_chunk<kIncludeInput, 2>(region, row, x, n_freqs, weights, pad, img_row);
+            write_encoding_chunk<kIncludeInput, 6>(region, row, x, n_freqs, weights, pad, img_row); break;
+    default: write_encoding_chunk<kIncludeInput, 3>(region, row, x, n_freqs, weights, pad, img_row);
+             write_encoding_chunk<kIncludeInput, 7>(region, row, x, n_freqs, weights, pad, img_row); break;
+  }
 }
 
 template <bool kStore>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ts::kThreadsTs, 1)
-field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ TsLoadTab ltab, int n_chunks, int first_chunk,
+field_ts_kernel(const __grid_constant__ TsTab tab, int n_chunks, int first_chunk,
                 const uint8_t* __restrict__ packed, int64_t n_cap, const int64_t* __restrict__ n_dev,
                 const float* __restrict__ x_skel, const float* __restrict__ hann_w, int ignore_non_rigid,
                 float* __restrict__ raw, float* __restrict__ xyz_out, float* __restrict__ off_out, const TrainBufs bufs) {
@@ -123,8 +151,9 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
   const uint32_t s_acc_full = s_empty + kStagesTs * 8;       // both: accumulator half complete (multicast commit)
   const uint32_t s_a_ready = s_acc_full + 2 * 8;             // leader: 8 epilogue warps x 2 CTAs per half
   const uint32_t s_pe_ready = s_a_ready + 2 * 8;             // leader: 16 epilogue warps x 2 CTAs per encoding block
-  const uint32_t s_tmem_slot = s_pe_ready + 2 * 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOffTs + (3 * kStagesTs + 6) * 8);
+  const uint32_t s_out_full = s_pe_ready + 2 * 8;            // both: accumulator of an OUTPUT layer complete
+  const uint32_t s_tmem_slot = s_out_full + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOffTs + (3 * kStagesTs + 7) * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -144,6 +173,7 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
       mbar_init(s_a_ready + h * 8, 2 * (kEpiWarpsTs / 2));
       mbar_init(s_pe_ready + h * 8, 2 * kEpiWarpsTs);
     }
+    mbar_init(s_out_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {            // the same warp of both CTAs allocates collectively
@@ -163,11 +193,10 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
       const uint32_t s_done = leader ? s_full : s_floc;
       for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
         for (int c = first_chunk; c < n_chunks; ++c) {
-          const uint2 e = ltab.e[c];
-          const uint32_t half = e.y >> 1;
+          const uint32_t w_off = tab.e[c].z, half = tab.e[c].w >> 1;
           mbar_wait(s_empty + stage * 8, phase ^ 1, 1);
           mbar_expect_tx(s_done + stage * 8, half);
-          tma_bulk_g2s(s_ring + stage * kStageBytesTs, image + e.x + rank * half, half, s_done + stage * 8);
+          tma_bulk_g2s(s_ring + stage * kStageBytesTs, image + w_off + rank * half, half, s_done + stage * 8);
           if (++stage == (uint32_t)kStagesTs) { stage = 0; phase ^= 1; }
         }
       }
@@ -181,49 +210,69 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
       const uint32_t ring_lo = (s_ring & 0x3FFFFu) >> 4;
       uint32_t stage = 0, phase = 0, full_ok = 0;
       uint32_t a_phase0 = 0, a_phase1 = 0, pe_phase0 = 0, pe_phase1 = 0;
-      for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
+      int pass = 0;
+      for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters, ++pass) {
+#ifdef HN_TS_TRACE
+        const bool trace_on = cluster_id == 0 && pass == 3;
+#endif
         for (int c = first_chunk; c < n_chunks; ++c) {
-          const uint2 e = itab.e[c];
-          const uint32_t a_off = e.x & 0xFFFFu, n = e.x >> 16;
-          const uint32_t ksteps = e.y & 0xFFu, flags = (e.y >> 8) & 0xFFu, flags2 = (e.y >> 16) & 0xFFu;
+          const uint32_t ex = tab.e[c].x, ey = tab.e[c].y;
+          const uint32_t n = ex & 0xFFFFu, flags = (ex >> 16) & 0xFFu, flags2 = ex >> 24;
+          const uint32_t ss_a_off = ey & 0xFFu, ss_k = (ey >> 8) & 0xFFu, ts0_k = (ey >> 16) & 0xFFu, ts1_k = ey >> 24;
           if (flags & kTsWaitPe) {
             if (flags & kTsPeCn) { mbar_wait(s_pe_ready + 8, pe_phase1, 6); pe_phase1 ^= 1; }
             else { mbar_wait(s_pe_ready, pe_phase0, 6); pe_phase0 ^= 1; }
           }
           if (flags & kTsWaitA0) { mbar_wait(s_a_ready, a_phase0, 2); a_phase0 ^= 1; }
-          if (flags & kTsWaitA1) { mbar_wait(s_a_ready + 8, a_phase1, 2); a_phase1 ^= 1; }
           if (!full_ok) mbar_wait(s_full + stage * 8, phase, 3);
           tc_fence_after();
+          HN_TS_T(0, c, 0);
           {   // probe the NEXT chunk's weights now: the round trip overlaps the MMA issue below
             const uint32_t ns = stage + 1 == (uint32_t)kStagesTs ? 0u : stage + 1;
             full_ok = mbar_test_wait(s_full + ns * 8, ns == 0u ? phase ^ 1u : phase);
           }
           const uint32_t idesc = make_idesc2(n);
           const uint32_t d_tmem = tmem_base + kColD + ((flags & kTsD1) ? 128u : 0u);
-          uint32_t b_lo = (ring_lo + stage * (kStageBytesTs >> 4)) | ((n >> 1) << 16);    // LBO = (n/2) * 16 bytes
+          const uint32_t a_t0 = tmem_base + kColA + ((flags2 & 1u) ? 128u : 0u);
+          const uint32_t b_lo0 = (ring_lo + stage * (kStageBytesTs >> 4)) | ((n >> 1) << 16);    // LBO = (n/2) * 16 bytes
+          const uint32_t b_lo1 = b_lo0 + (ss_k + ts0_k) * n;          // one K step = two core-matrix groups of n/2 rows x 16 B, >> 4
           if (elect_one()) {
-            uint32_t acc = (flags & kTsFirst) ? 0u : 1u;
-            if (flags & kTsSS) {
-              uint32_t a_lo = ((flags & kTsPeCn) ? pe_lo1 : pe_lo0) + a_off * (kLboA >> 4);
-              for (uint32_t k = 0; k < ksteps; ++k) {
-                umma2_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
-                acc = 1u;
-                a_lo += (2u * kLboA) >> 4;
-                b_lo += n;
-              }
-            } else {
-              uint32_t a_t = tmem_base + kColA + ((flags2 & 1u) ? 128u : 0u) + a_off;
-              for (uint32_t k = 0; k < ksteps; ++k) {
-                umma2_ts_bf16(d_tmem, a_t, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
-                acc = 1u;
-                a_t += 8u;                                   // 16 bf16 of K = 8 columns
-                b_lo += n;
-              }
+            // the chunk is a whole accumulator half of a layer: the first MMA overwrites
+            uint32_t acc = 0u;
+            uint32_t b_lo = b_lo0;
+            uint32_t a_lo = ((flags & kTsPeCn) ? pe_lo1 : pe_lo0) + ss_a_off * (kLboA >> 4);
+            for (uint32_t k = 0; k < ss_k; ++k) {
+              umma2_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+              acc = 1u;
+              a_lo += (2u * kLboA) >> 4;
+              b_lo += n;
             }
-            umma2_commit_mc(s_empty + stage * 8);            // the slot is free in both CTAs once these MMAs retire
-            if (flags & kTsLast) umma2_commit_mc(s_acc_full + ((flags & kTsD1) ? 8u : 0u));
+            uint32_t a_t = a_t0;
+            for (uint32_t k = 0; k < ts0_k; ++k) {
+              umma2_ts_bf16(d_tmem, a_t, ((uint64_t)desc_hi << 32) | b_lo, idesc, 1u);
+              a_t += 8u;                                     // 16 bf16 of K = 8 columns
+              b_lo += n;
+            }
           }
           __syncwarp();
+          if (flags & kTsWaitA1) {                           // features [128,256) of the previous layer stored, D1 drained
+            mbar_wait(s_a_ready + 8, a_phase1, 2);
+            a_phase1 ^= 1;
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            uint32_t a_t = a_t0 + 64u;
+            uint32_t b_lo = b_lo1;
+            for (uint32_t k = 0; k < ts1_k; ++k) {
+              umma2_ts_bf16(d_tmem, a_t, ((uint64_t)desc_hi << 32) | b_lo, idesc, 1u);
+              a_t += 8u;
+              b_lo += n;
+            }
+            umma2_commit_mc(s_empty + stage * 8);            // the slot is free in both CTAs once these MMAs retire
+            umma2_commit_mc((flags & kTsOut) ? s_out_full : s_acc_full + ((flags & kTsD1) ? 8u : 0u));
+          }
+          __syncwarp();
+          HN_TS_T(0, c, 1);
           if (++stage == (uint32_t)kStagesTs) { stage = 0; phase ^= 1; }
         }
       }
@@ -251,7 +300,7 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
     const uint32_t pe_nr = s_base, pe_cn = s_base + kActPeTile;
     const uint32_t bar_a = mapa_cluster(s_a_ready + (uint32_t)nh * 8, 0);            // in the leader
     const uint32_t bar_pe0 = mapa_cluster(s_pe_ready, 0), bar_pe1 = mapa_cluster(s_pe_ready + 8, 0);
-    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0, out_phase = 0;
     const int nr_freqs = (int)hdr->nr_freqs, cn_freqs = (int)hdr->cn_freqs;
     const int nr_pad = (int)hdr->nr_pe_pad, cn_pad = (int)hdr->cn_pe_pad;
     const int nr_width = (int)hdr->nr_width, cn_width = (int)hdr->cn_width;
@@ -260,13 +309,8 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
     auto encode = [&](bool cn, const float p[3], int64_t tile_idx, bool store) {
       const int pad = cn ? cn_pad : nr_pad;
       uint8_t* img = (kStore && store) ? bufs.pe[cn ? 1 : 0] + image_row_offset(tile_idx, row, pad) : nullptr;
-      if (cn) {
-        write_encoding_chunk<true>(pe_cn, row, part, p, cn_freqs, nullptr, pad, img);
-        write_encoding_chunk<true>(pe_cn, row, part + 4, p, cn_freqs, nullptr, pad, img);
-      } else {
-        write_encoding_chunk<false>(pe_nr, row, part, p, nr_freqs, hann_w, pad, img);
-        write_encoding_chunk<false>(pe_nr, row, part + 4, p, nr_freqs, hann_w, pad, img);
-      }
+      if (cn) write_encoding_part<true>(pe_cn, row, part, p, cn_freqs, nullptr, pad, img);
+      else write_encoding_part<false>(pe_nr, row, part, p, nr_freqs, hann_w, pad, img);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(cn ? bar_pe1 : bar_pe0);
@@ -279,13 +323,20 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
       p[2] = ok ? __ldg(x_skel + sample * 3 + 2) : 0.f;
     };
     // hidden layer `l` of MLP `m` (width `width`): drain this warp's 64 accumulator columns into the A buffer (l & 1)
+    int tr_slot = 0;
+    bool trace_on = false;
+    (void)tr_slot; (void)trace_on;
     auto hidden = [&](int m, int l, int width, int64_t tile_idx, bool store) {
       const bool two = width > 128;
-      mbar_wait(s_acc_full, acc_phase0, 4);
-      acc_phase0 ^= 1;
-      if (two && nh == 1) { mbar_wait(s_acc_full + 8, acc_phase1, 4); acc_phase1 ^= 1; }
+      // Each barrier is waited for ONLY by the warps whose arrivals gate its next phase (acc_full[0]: group 0 through
+      // a_ready[0]; acc_full[1]: group 1 through a_ready[1]), so no waiter can fall two phases behind and alias the
+      // parity.  (A version in which group 0 also waited for acc_full[1] "to stay in step" dead-locked under the
+      // training variant's stores: a warp delayed between its a_ready[0] arrive and that wait missed two phases.)
+      if (nh == 0) { mbar_wait(s_acc_full, acc_phase0, 4); acc_phase0 ^= 1; }
+      else if (two) { mbar_wait(s_acc_full + 8, acc_phase1, 4); acc_phase1 ^= 1; }
       if (two || nh == 0) {
         tc_fence_after();
+        HN_TS_T(1 + nh, tr_slot, 0);
         const int col0 = nh * 128 + sub * 64;                                  // first feature this warp owns
         const uint32_t t_d = t_lane + kColD + (uint32_t)col0;
         const uint32_t t_a = t_lane + kColA + ((l & 1) ? 128u : 0u) + (uint32_t)(col0 >> 1);
@@ -320,6 +371,7 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_a);
+        HN_TS_T(1 + nh, tr_slot, 1);
         if (kStore && img) {
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
@@ -327,7 +379,7 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
           if (bits_rec) *reinterpret_cast<uint2*>(bits_rec) = make_uint2(m01[0], m01[1]);
         }
       }
-      if (two && nh == 0) { mbar_wait(s_acc_full + 8, acc_phase1, 4); acc_phase1 ^= 1; }    // stay in step with the barrier
+      ++tr_slot;
     };
 
     float x[3];
@@ -336,18 +388,25 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
       const int64_t t0 = cluster_id * 2 + (int64_t)rank;
       encode(ignore_non_rigid != 0, x, t0, t0 < bufs.n_tiles);
     }
-    for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters) {
+    int pass = 0;
+    for (int64_t duo = cluster_id; duo < n_duos; duo += n_clusters, ++pass) {
+      tr_slot = 0;
+      trace_on = blockIdx.x == 0 && pass == 3 && (ew == 0 || ew == 8);
       const int64_t tile_idx = duo * 2 + (int64_t)rank;
       const int64_t sample = tile_idx * kTileM + row;
       const bool valid = sample < n_samples;
       const bool store = kStore && tile_idx < bufs.n_tiles;      // the training images hold ceil(P/128) tiles
       float q[3] = {x[0], x[1], x[2]};                           // position fed to the canonical encoding
+      float xn[3];
+      load_x(duo + n_clusters, xn);                              // the next pass's positions: ~1 us of latency hidden under this pass
       if (!ignore_non_rigid) {
         for (int l = 0; l + 1 < nr_layers; ++l) hidden(0, l, nr_width, tile_idx, store);
-        // output layer: offsets in accumulator columns [0,3) of D0; every warp reads them (all need q for the encoding)
-        mbar_wait(s_acc_full, acc_phase0, 4);
-        acc_phase0 ^= 1;
+        // output layer: offsets in accumulator columns [0,3) of D0; every warp reads them (all need q for the encoding).
+        // out_full is waited for by all 16 warps, and all of them arrive on pe_ready between two of its phases.
+        mbar_wait(s_out_full, out_phase, 4);
+        out_phase ^= 1;
         tc_fence_after();
+        HN_TS_T(1 + nh, tr_slot, 0);
         uint32_t v[16];
         tmem_ld16(t_lane + kColD, v);
         tmem_ld_wait();
@@ -358,12 +417,15 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
           off_out[sample * 3 + 0] = o0; off_out[sample * 3 + 1] = o1; off_out[sample * 3 + 2] = o2;
         }
         encode(true, q, tile_idx, store);
+        HN_TS_T(1 + nh, tr_slot, 1);
+        ++tr_slot;
       }
       for (int l = 0; l + 1 < cn_layers; ++l) hidden(1, l, cn_width, tile_idx, store);
       {
-        mbar_wait(s_acc_full, acc_phase0, 4);
-        acc_phase0 ^= 1;
+        mbar_wait(s_out_full, out_phase, 4);
+        out_phase ^= 1;
         tc_fence_after();
+        HN_TS_T(1 + nh, tr_slot, 0);
         if (part == 0) {
           uint32_t v[16];
           tmem_ld16(t_lane + kColD, v);
@@ -383,11 +445,12 @@ field_ts_kernel(const __grid_constant__ IssueTab itab, const __grid_constant__ T
       }
       // next pass: positions and first encoding block (its arrive also tells the issuer that D0 has been drained)
       const int64_t next = duo + n_clusters;
-      load_x(next, x);
+      x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
       if (next < n_duos) {
         const int64_t tn = next * 2 + (int64_t)rank;
         encode(ignore_non_rigid != 0, x, tn, kStore && tn < bufs.n_tiles);
       }
+      HN_TS_T(1 + nh, tr_slot, 1);
     }
   }
 
@@ -427,31 +490,36 @@ int launch_field_ts(const TcPlan& plan, const uint8_t* packed, int64_t n_samples
     if (n <= 0) return fail_arg("hn_field_fwd: no 2-CTA cluster of the TS kernel fits on this device");
     max_clusters_cached = n;
   }
-  IssueTab itab;
-  TsLoadTab ltab;
-  memset(&itab, 0, sizeof(itab));
-  memset(&ltab, 0, sizeof(ltab));
+  TsTab tab;
+  memset(&tab, 0, sizeof(tab));
   int first_chunk = 0;
   for (size_t c = 0; c < plan.ts_chunks.size(); ++c) {
     const TsChunk& ch = plan.ts_chunks[c];
-    itab.e[c] = make_uint2((uint32_t)ch.a_off | ((uint32_t)ch.n << 16),
-                           (uint32_t)ch.ksteps | ((uint32_t)ch.flags << 8) | ((uint32_t)ch.flags2 << 16));
-    ltab.e[c] = make_uint2(ch.w_off, ch.bytes);
+    tab.e[c] = make_uint4((uint32_t)ch.n | ((uint32_t)ch.flags << 16) | ((uint32_t)ch.flags2 << 24),
+                          (uint32_t)ch.ss_a_off | ((uint32_t)ch.ss_ksteps << 8) | ((uint32_t)ch.ts0_ksteps << 16) |
+                              ((uint32_t)ch.ts1_ksteps << 24),
+                          ch.w_off, ch.bytes);
     if (ignore_non_rigid && (ch.flags2 & 2)) first_chunk = (int)c + 1;      // chunks of the skipped MLP are skipped too
   }
   const int64_t n_duos = ceil_div<int64_t>(n_samples, 2 * kTileM);
   const unsigned grid = 2u * (unsigned)std::min<int64_t>(n_duos, (int64_t)max_clusters_cached);
   const int n_chunks = (int)plan.ts_chunks.size();
   if (bufs) {
-    field_ts_kernel<true><<<grid, kThreadsTs, kSmemTs, st>>>(itab, ltab, n_chunks, first_chunk, packed, n_samples, n_samples_dev,
+    field_ts_kernel<true><<<grid, kThreadsTs, kSmemTs, st>>>(tab, n_chunks, first_chunk, packed, n_samples, n_samples_dev,
                                                              x_skel, hann_w, ignore_non_rigid, raw, xyz, offsets, *bufs);
   } else {
     TrainBufs none;
     memset(&none, 0, sizeof(none));
-    field_ts_kernel<false><<<grid, kThreadsTs, kSmemTs, st>>>(itab, ltab, n_chunks, first_chunk, packed, n_samples, n_samples_dev,
+    field_ts_kernel<false><<<grid, kThreadsTs, kSmemTs, st>>>(tab, n_chunks, first_chunk, packed, n_samples, n_samples_dev,
                                                               x_skel, hann_w, ignore_non_rigid, raw, xyz, offsets, none);
   }
   return launched("hn_field_fwd/tcgen05 ts");
 }
+
+#ifdef HN_TS_TRACE
+extern "C" int hn_ts_trace_read(long long* out_host) {      // measurement builds only; not declared in the public header
+  return (int)cudaMemcpyFromSymbol(out_host, g_ts_trace, sizeof(long long) * 3 * 128 * 2);
+}
+#endif
 
 }  // namespace hn
