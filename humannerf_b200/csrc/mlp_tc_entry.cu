@@ -65,14 +65,22 @@ int launch_field_ts(const TcPlan& plan, const uint8_t* packed, int64_t n_samples
                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
                     const TrainBufs* bufs, int sms, cudaStream_t st);
 
-// Forward kernel selection, read once per process: the TS kernel (hidden activations in tensor memory, mlp_tc_ts.cu) is the
-// default whenever the MLP widths allow it; HN_TC_FWD=ss keeps the SS kernel of mlp_tc_2sm.cu (activations in shared memory).
-static inline bool use_ts_forward() {
-  static const bool v = [] {
+// Forward kernel selection, read once per process.  Default ("auto"): rendering (nothing saved for backward) runs the TS
+// kernel (hidden activations in tensor memory, mlp_tc_ts.cu: 28.7 instead of 33.5 ms per 512 x 512 frame), training the
+// SS kernel of mlp_tc_2sm.cu (activations in shared memory, image stores through the TMA: 1.40 against 1.45 ms per
+// 6144-ray step - with the image stores both kernels are paced by the store path and the L2).
+// HN_TC_FWD=ts / ss forces one kernel for both.
+static inline int ts_forward_mode() {        // 0 auto, 1 ts, 2 ss
+  static const int v = [] {
     const char* e = getenv("HN_TC_FWD");
-    return e == nullptr || e[0] != 's';
+    if (e == nullptr) return 0;
+    return e[0] == 't' ? 1 : (e[0] == 's' ? 2 : 0);
   }();
   return v;
+}
+static inline bool use_ts_forward(bool save_for_backward) {
+  const int m = ts_forward_mode();
+  return m == 1 || (m == 0 && !save_for_backward);
 }
 
 int64_t tc_train_workspace_bytes(const hn_field_params* p, int64_t n_samples) {
@@ -164,7 +172,7 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
     if (!use_relu_bits()) memset(bufs.bits, 0, sizeof(bufs.bits));
   }
-  if (use_ts_forward() && !plan.ts_chunks.empty())
+  if (use_ts_forward(save_for_backward != 0) && !plan.ts_chunks.empty())
     return launch_field_ts(plan, static_cast<const uint8_t*>(packed), n_samples, n_samples_dev, x_skel, hann_w,
                            ignore_non_rigid ? 1 : 0, raw, xyz, offsets, save_for_backward ? &bufs : nullptr, sms,
                            as_stream(stream));

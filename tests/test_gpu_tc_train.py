@@ -469,17 +469,19 @@ def test_relu_mask_images_match_activation_read(tmp_path, P, ignore):
     print(f'[parity] ReLU mask images vs activation read [P={P},ignore={ignore}]: worst rel L2 over {len(want.files)} tensors {worst:.2e}')
 
 
-@pytest.mark.parametrize('variant', ['ss-forward', '2sm-8-stages', 'read-activations'])
+@pytest.mark.parametrize('variant', ['ts-forward', 'ss-forward', '2sm-8-stages', 'read-activations'])
 def test_other_forward_kernels_parity(variant):
-    """The default tcgen05 forward kernel keeps the hidden activations in tensor memory (csrc/mlp_tc_ts.cu).  The
-    alternatives must pass the same forward parity and training tests: HN_TC_FWD=ss (activations in shared memory,
-    csrc/mlp_tc_2sm.cu, 4 x 16 KB ring), the same with an 8 x 8 KB ring (HN_TC_2SM_STAGES=8), and the backward chain
-    masking with the stored activations instead of the 1-bit images (HN_TC_RELU_BITS=0).  The choices are read once
-    per process, hence the subprocess."""
+    """By default rendering runs the TS forward kernel (hidden activations in tensor memory, csrc/mlp_tc_ts.cu) and
+    training the SS kernel (activations in shared memory, csrc/mlp_tc_2sm.cu).  Every combination must pass the same
+    forward parity and training tests: HN_TC_FWD=ts / ss (one kernel for both), the SS kernel with an 8 x 8 KB ring
+    (HN_TC_2SM_STAGES=8), and the backward chain masking with the stored activations instead of the 1-bit images
+    (HN_TC_RELU_BITS=0).  The choices are read once per process, hence the subprocess."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
-    if variant == 'ss-forward':
+    if variant == 'ts-forward':
+        env['HN_TC_FWD'] = 'ts'
+    elif variant == 'ss-forward':
         env['HN_TC_FWD'] = 'ss'
     elif variant == '2sm-8-stages':
         env['HN_TC_FWD'], env['HN_TC_2SM_STAGES'] = 'ss', '8'
