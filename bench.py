@@ -407,6 +407,8 @@ def main():
     cfg.b200.jitter_rng = 'device'
     cfg.b200.heavy_outputs = False
     cfg.N_samples = N_SAMPLES
+    if os.environ.get('HN_DECODER'):
+        cfg.b200.decoder = os.environ['HN_DECODER']          # A/B switch: 'hn' (default) or 'cudnn'
     torch.manual_seed(0)
     net = Network()
     net.load_state_dict(syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True))

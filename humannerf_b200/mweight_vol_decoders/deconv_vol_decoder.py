@@ -1,7 +1,10 @@
 """Motion-weight volume decoder, plugin-compatible with reference
 `core/nets/human_nerf/mweight_vol_decoders/deconv_vol_decoder.py:8-33`:
-softmax(decoder(const_embedding) + log(prior)) over the 25 channels.  Runs once per forward on
-cuDNN (dense transposed convolutions); SURVEY.md section 8 keeps it in PyTorch."""
+softmax(decoder(const_embedding) + log(prior)) over the 25 channels.  On a CUDA device the whole module - linear
+layer, the five transposed convolutions, LeakyReLUs, softmax with the prior, and their backward - runs on the
+hand-written kernels of csrc/vol_decoder.cu (`ops.vol_decoder`, fp32, deterministic); `cfg.b200.decoder = 'cudnn'`
+keeps the PyTorch / cuDNN path (TF32 on the bf16 path) as an A/B arm.  CPU tensors (construction-time tests, the
+oracle arm) always take the PyTorch path."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -21,7 +24,20 @@ class MotionWeightVolumeDecoder(nn.Module):
         # TF32 transposed convolutions are ~0.4 ms per training step faster than cuDNN's fp32 engine
         self.allow_tf32 = False
 
+    def _use_kernels(self, prior) -> bool:
+        from humannerf_b200.config import get_cfg
+        mode = str(get_cfg().get('b200', {}).get('decoder', 'hn')).lower()
+        return prior.is_cuda and mode != 'cudnn'
+
     def forward(self, motion_weights_priors, **_):
+        if self._use_kernels(motion_weights_priors):
+            from humannerf_b200 import ops
+            convs = [m for m in self.decoder.block_conv if isinstance(m, nn.ConvTranspose3d)]
+            lin = self.decoder.block_mlp[0]
+            prior = motion_weights_priors[0] if motion_weights_priors.dim() == 5 else motion_weights_priors
+            vol = ops.vol_decoder(self.const_embedding, lin.weight, lin.bias, prior, [c.weight for c in convs],
+                                  [c.bias for c in convs])
+            return vol[None, ...]
         # on the fp32 parity path TF32 is off: its 10-bit mantissa moves the sampled blend weights by 1e-4
         # and breaks the 1e-4 output parity with the reference
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=bool(self.allow_tf32)):

@@ -261,6 +261,84 @@ def pose_fk(rvec: Optional[torch.Tensor], dst_Rs: torch.Tensor, dst_Ts: torch.Te
 
 
 # ---------------------------------------------------------------------------
+# a7: motion-weight volume decoder (Linear + LeakyReLU, transposed convolutions, softmax with the prior)
+# ---------------------------------------------------------------------------
+class _VolDecoder(torch.autograd.Function):
+    """inputs: embedding (E), lin_w (H, E), lin_b (H), prior (C, V, V, V), then conv weights and biases
+    [w0, b0, w1, b1, ...] - weights (C_in, C_out, 4, 4, 4) in channels_last_3d strides."""
+
+    @staticmethod
+    def forward(ctx, embedding, lin_w, lin_b, prior, *wb):
+        lib = _lib.load()
+        ws_, bs_ = list(wb[0::2]), list(wb[1::2])
+        n_conv = len(ws_)
+        for w in ws_:
+            if not (w.dim() == 5 and w.is_contiguous(memory_format=torch.channels_last_3d)) or w.dtype != torch.float32:
+                raise RuntimeError('humannerf_b200.vol_decoder: transposed-convolution weights must be fp32 in '
+                                   'channels_last_3d strides ([C_in][kz][ky][kx][C_out])')
+        channels = [int(ws_[0].shape[0])] + [int(w.shape[1]) for w in ws_]
+        ch = (C.c_int * (n_conv + 1))(*channels)
+        E, H = int(embedding.numel()), int(lin_w.shape[0])
+        embedding, lin_w, lin_b, prior = _f32c(embedding).reshape(-1), _f32c(lin_w), _f32c(lin_b), _f32c(prior)
+        bs_ = [_f32c(b) for b in bs_]
+        dev = embedding.device
+        side = 1 << n_conv
+        assert tuple(prior.shape) == (channels[-1], side, side, side), (prior.shape, channels, side)
+        wbytes = int(lib.hn_vol_decoder_workspace_bytes(E, H, n_conv, ch))
+        sbytes = int(lib.hn_vol_decoder_scratch_bytes(E, H, n_conv, ch))
+        if wbytes < 0 or sbytes < 0:
+            check(-1, 'vol_decoder_workspace_bytes')
+        ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        vol = torch.empty_like(prior)
+        wp = (C.c_void_p * n_conv)(*[w.data_ptr() for w in ws_])
+        bp = (C.c_void_p * n_conv)(*[b.data_ptr() for b in bs_])
+        with torch.cuda.device(dev), _timed('vol_decoder_fwd'):
+            check(lib.hn_vol_decoder_fwd(E, H, n_conv, ch, ptr(embedding), ptr(lin_w), ptr(lin_b), wp, bp, ptr(prior), ptr(vol),
+                                         ptr(ws), wbytes, ptr(scratch), sbytes, stream_ptr()), 'vol_decoder_fwd')
+        ctx.geom = (E, H, n_conv, channels)
+        ctx.ws = ws
+        ctx.save_for_backward(embedding, lin_w, vol, *ws_)
+        return vol
+
+    @staticmethod
+    def backward(ctx, g_vol):
+        lib = _lib.load()
+        E, H, n_conv, channels = ctx.geom
+        embedding, lin_w, vol, *ws_ = ctx.saved_tensors
+        ch = (C.c_int * (n_conv + 1))(*channels)
+        dev = vol.device
+        g_vol = _f32c(g_vol)
+        d_e, d_lw = torch.empty_like(embedding), torch.empty_like(lin_w)
+        d_lb = torch.empty(H, dtype=torch.float32, device=dev)
+        d_w = [torch.empty_like(w) for w in ws_]                 # preserve_format: the parameter's NDHWC strides
+        d_b = [torch.empty(int(w.shape[1]), dtype=torch.float32, device=dev) for w in ws_]
+        sbytes = int(lib.hn_vol_decoder_scratch_bytes(E, H, n_conv, ch))
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        wp = (C.c_void_p * n_conv)(*[w.data_ptr() for w in ws_])
+        dwp = (C.c_void_p * n_conv)(*[w.data_ptr() for w in d_w])
+        dbp = (C.c_void_p * n_conv)(*[b.data_ptr() for b in d_b])
+        with torch.cuda.device(dev), _timed('vol_decoder_bwd'):
+            check(lib.hn_vol_decoder_bwd(E, H, n_conv, ch, ptr(embedding), ptr(lin_w), wp, ptr(vol), ptr(g_vol), ptr(ctx.ws),
+                                         ctx.ws.numel(), ptr(scratch), sbytes, ptr(d_e), ptr(d_lw), ptr(d_lb), dwp, dbp,
+                                         stream_ptr()), 'vol_decoder_bwd')
+        ctx.ws = None
+        out = [d_e, d_lw, d_lb, None]
+        for w, b in zip(d_w, d_b):
+            out += [w, b]
+        return tuple(out)
+
+
+def vol_decoder(embedding, lin_w, lin_b, prior, conv_weights, conv_biases):
+    """softmax_c(ConvDecoder3D(embedding) + log prior) -> (C, V, V, V) (deconv_vol_decoder.py:25-33, network_util.py:12-50)
+    on the hand-written kernels of csrc/vol_decoder.cu; differentiable in everything but the prior."""
+    wb = []
+    for w, b in zip(conv_weights, conv_biases):
+        wb += [w, b]
+    return _VolDecoder.apply(embedding, lin_w, lin_b, prior, *wb)
+
+
+# ---------------------------------------------------------------------------
 # canonical field (hann-PE -> non-rigid MLP -> PE -> canonical MLP)
 # ---------------------------------------------------------------------------
 class FieldSpec:
