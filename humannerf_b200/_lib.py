@@ -90,8 +90,8 @@ SIGNATURES = {
     'hn_gather_rows': (_int, [_i64, _int, _p, _p, _p, _p]),
     'hn_vol_decoder_workspace_bytes': (_i64, [_int, _int, _int, _p]),
     'hn_vol_decoder_scratch_bytes': (_i64, [_int, _int, _int, _p]),
-    'hn_vol_decoder_fwd': (_int, [_int, _int, _int] + [_p] * 9 + [_i64, _p, _i64, _p]),
-    'hn_vol_decoder_bwd': (_int, [_int, _int, _int] + [_p] * 7 + [_i64, _p, _i64] + [_p] * 6),
+    'hn_vol_decoder_fwd': (_int, [_int, _int, _int] + [_p] * 9 + [_i64, _p, _i64, _int, _p]),
+    'hn_vol_decoder_bwd': (_int, [_int, _int, _int] + [_p] * 7 + [_i64, _p, _i64] + [_p] * 5 + [_int, _p]),
     'hn_patch_prepare': (_int, [_int, _int] + [_p] * 7),
     'hn_select_patches': (_int, [_int, _int, _int, _int, C.c_double] + [_p] * 22),
     'hn_lpips_head_fwd': (_int, [_int, _int, _int, _p, _i64, _i64, _i64, _p, _p, _p]),

@@ -156,9 +156,9 @@ _DEFAULTS: Dict[str, Any] = {
         'mlp_precision': 'fp32',
         # keep the heavy per-sample outputs (weights (R,S,24) ...) in the dict
         'heavy_outputs': True,
-        # motion-weight volume decoder: 'hn' = hand-written kernels (csrc/vol_decoder.cu, fp32, deterministic),
-        # 'cudnn' = PyTorch / cuDNN transposed convolutions (TF32 on the bf16 path)
-        'decoder': 'hn',
+        # motion-weight volume decoder: 'hn' = hand-written kernels (csrc/vol_decoder.cu), 'cudnn' = PyTorch / cuDNN
+        # transposed convolutions, 'auto' = 'hn' on the fp32 parity path, 'cudnn' (TF32) on the bf16 path
+        'decoder': 'auto',
         # cache the decoded motion-weight volume across eval frames
         'cache_eval_volume': False,
         # stratified-jitter noise: 'reference' = CPU default generator like network.py:468

@@ -1,4 +1,4 @@
-// a7: the motion-weight volume decoder, forward and backward, hand-written (fp32 SIMT, deterministic).
+// a7: the motion-weight volume decoder, forward and backward, hand-written (fp32 storage, deterministic).
 //   reference: core/nets/human_nerf/mweight_vol_decoders/deconv_vol_decoder.py:25-33 (softmax(decoder(const_embedding)
 //   + log(prior))), core/utils/network_util.py:12-50 ConvDecoder3D (Linear + LeakyReLU(0.2), then ConvTranspose3d(k4, s2,
 //   p1) layers with LeakyReLU(0.2) in between).
@@ -13,7 +13,8 @@
 // their gradients written in the parameters' own NDHWC strides ([Cin][kz][ky][kx][Cout], network.py keeps them in
 // torch.channels_last_3d), so nothing is transposed or re-strided per step.
 //
-// One tiled SIMT kernel (64 x 64 x 16 tiles, 4 x 4 per thread) with three operand loaders (forward / data gradient /
+// One tiled kernel (64 x 64 x 16 tiles; warp-level mma.sync m16n8k8 TF32 - 3xTF32 with fp32-level accuracy on the
+// HN_PRECISION_FP32 parity path, plain TF32 on the HN_PRECISION_BF16 path) with three operand loaders (forward / data gradient /
 // weight gradient); layers whose GEMM has few rows (the 1^3, 2^3, 4^3 volumes: weight-bandwidth bound) are split over K
 // into a partial buffer that a finishing kernel reduces in a fixed order (bias / LeakyReLU / LeakyReLU' fused) - no
 // atomics anywhere, results are bit-reproducible.  The last layer's finishing step is softmax(logits + log prior)
@@ -27,7 +28,7 @@ namespace hn {
 
 constexpr int kDecMaxConv = 8;
 constexpr float kLeaky = 0.2f;
-constexpr int kTile = 64, kTileK = 16, kTileStride = kTile + 4;
+constexpr int kTile = 64, kTileK = 16;
 
 struct DeconvArgs {
   int din;                 // input volume side (output side = 2 din)
@@ -47,29 +48,95 @@ struct DeconvArgs {
 __device__ __forceinline__ int tap_k(int p, int t) { return p == 0 ? (t == 0 ? 1 : 3) : (t == 0 ? 2 : 0); }
 __device__ __forceinline__ int tap_off(int p, int t) { return t == 0 ? 0 : (p == 0 ? -1 : 1); }
 
-// acc[4][4] += As[k][ty*4 + i] * Bs[k][tx*4 + j]
-__device__ __forceinline__ void tile_fma(const float* __restrict__ As, const float* __restrict__ Bs, int ty, int tx, float (&acc)[4][4]) {
+// Tensor-core tile product (warp-level mma.sync m16n8k8, TF32 operands, fp32 accumulate).  8 warps = 4 (rows) x 2 (cols):
+// warp (wm, wn) owns rows [16 wm, +16) x cols [32 wn, +32) of the 64 x 64 tile = 4 fragments of 16 x 8;
+// acc[f][i]: fragment f, i = 0..3 -> (row g + 8 (i >> 1), col 2 t + (i & 1)) with g = lane >> 2, t = lane & 3.
+// kX3 = true: every operand is split into two TF32 values (hi + lo) and the product is hi*hi + hi*lo + lo*hi ("3xTF32"):
+// fp32-level accuracy for the 1e-4 parity path; kX3 = false: plain TF32 (the bf16 path, like cuDNN's TF32 engines).
+// Operand tiles sit in shared memory in the layout their source is contiguous in, so every global -> shared copy is a
+// 16-byte cp.async: "row-major in k" tiles [64 rows][16 k] with a row stride of 20 floats, "k-major" tiles [16 k][64]
+// with a row stride of 72 floats - both strides make the fragment loads bank-conflict free.
+constexpr int kStrideRK = kTileK + 4;      // 20
+constexpr int kStrideKM = kTile + 8;       // 72
+constexpr int kTileFloats = kTile * kStrideRK > kTileK * kStrideKM ? kTile * kStrideRK : kTileK * kStrideKM;   // 1280
+constexpr int kDecStages = 4;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// A_RK / B_RK: the tile is row-major in k ([row][k], stride 20) instead of k-major ([k][row], stride 72)
+template <bool kX3, bool A_RK, bool B_RK>
+__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Bs, int warp, int lane, float (&acc)[4][4]) {
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int kk = 0; kk < kTileK; ++kk) {
-    const float4 a = *reinterpret_cast<const float4*>(As + kk * kTileStride + ty * 4);
-    const float4 b = *reinterpret_cast<const float4*>(Bs + kk * kTileStride + tx * 4);
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  for (int k8 = 0; k8 < kTileK; k8 += 8) {
+    float af[4];
+    if (A_RK) {
+      af[0] = As[(wm * 16 + g) * kStrideRK + k8 + t];     af[1] = As[(wm * 16 + g + 8) * kStrideRK + k8 + t];
+      af[2] = As[(wm * 16 + g) * kStrideRK + k8 + t + 4]; af[3] = As[(wm * 16 + g + 8) * kStrideRK + k8 + t + 4];
+    } else {
+      af[0] = As[(k8 + t) * kStrideKM + wm * 16 + g];     af[1] = As[(k8 + t) * kStrideKM + wm * 16 + g + 8];
+      af[2] = As[(k8 + t + 4) * kStrideKM + wm * 16 + g]; af[3] = As[(k8 + t + 4) * kStrideKM + wm * 16 + g + 8];
+    }
+    uint32_t a_hi[4], a_lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      a_hi[i] = to_tf32(af[i]);
+      if (kX3) a_lo[i] = to_tf32(af[i] - __uint_as_float(a_hi[i]));
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    for (int f = 0; f < 4; ++f) {
+      float bf[2];
+      if (B_RK) {
+        bf[0] = Bs[(wn * 32 + f * 8 + g) * kStrideRK + k8 + t]; bf[1] = Bs[(wn * 32 + f * 8 + g) * kStrideRK + k8 + t + 4];
+      } else {
+        bf[0] = Bs[(k8 + t) * kStrideKM + wn * 32 + f * 8 + g]; bf[1] = Bs[(k8 + t + 4) * kStrideKM + wn * 32 + f * 8 + g];
+      }
+      uint32_t b_hi[2], b_lo[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        b_hi[i] = to_tf32(bf[i]);
+        if (kX3) b_lo[i] = to_tf32(bf[i] - __uint_as_float(b_hi[i]));
+      }
+      if (kX3) {
+        mma_tf32(acc[f], a_lo, b_hi);          // small terms first
+        mma_tf32(acc[f], a_hi, b_lo);
+      }
+      mma_tf32(acc[f], a_hi, b_hi);
+    }
   }
+}
+
+// 16 bytes global -> shared (zero-filled when !valid); sources that are not 16-byte aligned (rows of 25 floats) go
+// element by element with `n_valid` leading elements copied and the rest zero-filled
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4x4(float* dst, const float* src, int n_valid) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + j)), "l"(j < n_valid ? src + j : src),
+                 "r"(j < n_valid ? 4 : 0) : "memory");
 }
 
 // MODE 0: forward.  grid = (m_tiles * n_tiles, 8 parity classes, k_splits); GEMM rows m = input-grid voxel, cols = cout.
 // MODE 1: data gradient.  grid = (m_tiles * n_tiles, 1, k_splits); rows = input voxel i, cols = cin, K = (tap, cout).
-// MODE 2: weight gradient.  grid = (m_tiles * n_tiles, 64 taps, 1); rows = cin, cols = cout, K = input voxel.
-template <int MODE>
+// MODE 2: weight gradient.  grid = (m_tiles * n_tiles, 64 taps, k_splits); rows = cin, cols = cout, K = input voxel.
+// Four-stage cp.async pipeline: the copies of tile k + 3 are issued before the MMAs of tile k.
+template <int MODE, bool kX3>
 __global__ void __launch_bounds__(256)
 deconv_gemm_kernel(const DeconvArgs g) {
-  __shared__ __align__(16) float As[kTileK * kTileStride];
-  __shared__ __align__(16) float Bs[kTileK * kTileStride];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  __shared__ __align__(16) float As[kDecStages][kTileFloats];
+  __shared__ __align__(16) float Bs[kDecStages][kTileFloats];
+  constexpr bool A_RK = MODE != 2, B_RK = MODE == 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int din = g.din, din3 = din * din * din, dout = 2 * din;
   const int M = MODE == 2 ? g.cin : din3;
   const int N = MODE == 0 ? g.cout : (MODE == 1 ? g.cin : g.cout);
@@ -80,12 +147,66 @@ deconv_gemm_kernel(const DeconvArgs g) {
   const int n_taps = MODE == 0 ? (din == 1 ? 1 : 8) : (din == 1 ? 8 : 64);
   const int k_total = MODE == 0 ? n_taps * g.cin : (MODE == 1 ? n_taps * cout_pad : din3);
   int k_begin = 0, k_end = k_total;
-  if (MODE != 2 && g.k_splits > 1) {
+  if (g.k_splits > 1) {
     k_begin = (int)blockIdx.z * g.k_per_split;
     k_end = min(k_total, k_begin + g.k_per_split);
   }
   const int pz = (blockIdx.y >> 2) & 1, py = (blockIdx.y >> 1) & 1, px = blockIdx.y & 1;      // MODE 0: parity class
   const int wz = blockIdx.y >> 4, wy = (blockIdx.y >> 2) & 3, wx = blockIdx.y & 3;           // MODE 2: tap
+  // copy roles: row-major-in-k tiles: thread = (row tid >> 2, k quad (tid & 3) * 4); k-major tiles: (k tid >> 4, quad (tid & 15) * 4)
+  const int r4 = tid >> 2, kq = (tid & 3) * 4, kr = tid >> 4, q16 = (tid & 15) * 4;
+  int vz = 0, vy = 0, vx = 0;                       // MODE 0 / 1: voxel of this thread's A row
+  if (MODE != 2) {
+    const int m = m0 + r4;
+    vz = m / (din * din); vy = (m / din) % din; vx = m % din;
+  }
+  const bool w_rows_aligned = (g.cout & 3) == 0;
+
+  auto issue = [&](int k0, int stage) {
+    float* as = As[stage];
+    float* bs = Bs[stage];
+    if (MODE == 0) {
+      // A(m, kk) = in[i(m, tap)][ci .. ci + 3]
+      const int kk = k0 + kq, tap = kk / g.cin, ci = kk - tap * g.cin;
+      const int iz = vz + tap_off(pz, (tap >> 2) & 1), iy = vy + tap_off(py, (tap >> 1) & 1), ix = vx + tap_off(px, tap & 1);
+      const bool ok = m0 + r4 < din3 && kk < k_end && iz >= 0 && iz < din && iy >= 0 && iy < din && ix >= 0 && ix < din;
+      cp_async16(as + r4 * kStrideRK + kq, ok ? g.in + ((size_t)(iz * din + iy) * din + ix) * g.cin + ci : g.in, ok);
+      // B(kk, n) = w[ci][k(p, tap)][n .. n + 3]
+      const int kb = k0 + kr, tapb = kb / g.cin, cib = kb - tapb * g.cin;
+      const int kidx = (tap_k(pz, (tapb >> 2) & 1) * 4 + tap_k(py, (tapb >> 1) & 1)) * 4 + tap_k(px, tapb & 1);
+      const float* src = g.w + ((size_t)cib * 64 + kidx) * g.cout + n0 + q16;
+      const int nv = kb < k_end ? max(0, min(4, N - (n0 + q16))) : 0;
+      if (w_rows_aligned) cp_async16(bs + kr * kStrideKM + q16, nv == 4 ? src : g.w, nv == 4);
+      else cp_async4x4(bs + kr * kStrideKM + q16, nv > 0 ? src : g.w, nv);
+    } else if (MODE == 1) {
+      // A(i, kk) = outside[o(i, tap)][co .. co + 3], kk = tap * cout_pad + co;  B(ci, kk) = w[ci][tap][co .. co + 3]
+      const int kk = k0 + kq, tl = kk / cout_pad, co = kk - tl * cout_pad;
+      // tap list: all 64 taps, or (din == 1) the 8 taps with k in {1, 2} per axis - the only ones that reach the 2^3 output
+      const int kz = din == 1 ? 1 + ((tl >> 2) & 1) : tl >> 4, ky = din == 1 ? 1 + ((tl >> 1) & 1) : (tl >> 2) & 3,
+                kx = din == 1 ? 1 + (tl & 1) : tl & 3;
+      const int oz = 2 * vz - 1 + kz, oy = 2 * vy - 1 + ky, ox = 2 * vx - 1 + kx;
+      const bool ok = kk < k_end && m0 + r4 < din3 && oz >= 0 && oz < dout && oy >= 0 && oy < dout && ox >= 0 && ox < dout;
+      const float* asrc = g.outside + ((size_t)(oz * dout + oy) * dout + ox) * g.ld_out + co;
+      // ld_out is a multiple of 4 and columns [cout, ld_out) of the gradient buffers are zero
+      const int av = ok ? max(0, min(4, g.ld_out - co)) : 0;
+      cp_async16(as + r4 * kStrideRK + kq, av == 4 ? asrc : g.outside, av == 4);
+      const int ci = n0 + r4;
+      const int bv = (kk < k_end && ci < N) ? max(0, min(4, g.cout - co)) : 0;
+      const float* bsrc = g.w + ((size_t)ci * 64 + (kz * 4 + ky) * 4 + kx) * g.cout + co;
+      if (w_rows_aligned) cp_async16(bs + r4 * kStrideRK + kq, bv == 4 ? bsrc : g.w, bv == 4);
+      else cp_async4x4(bs + r4 * kStrideRK + kq, bv > 0 ? bsrc : g.w, bv);
+    } else {
+      // A(ci, i) = in[i][ci .. ci + 3];  B(i, co) = outside[o(i, tap)][co .. co + 3]
+      const int i = k0 + kr;
+      const bool aok = i < k_end && m0 + q16 + 4 <= M;
+      cp_async16(as + kr * kStrideKM + q16, aok ? g.in + (size_t)i * g.cin + m0 + q16 : g.in, aok);
+      const int iz = i / (din * din), iy = (i / din) % din, ix = i % din;
+      const int oz = 2 * iz - 1 + wz, oy = 2 * iy - 1 + wy, ox = 2 * ix - 1 + wx;
+      const bool bok = i < k_end && oz >= 0 && oz < dout && oy >= 0 && oy < dout && ox >= 0 && ox < dout && n0 + q16 + 4 <= g.ld_out;
+      cp_async16(bs + kr * kStrideKM + q16, bok ? g.outside + ((size_t)(oz * dout + oy) * dout + ox) * g.ld_out + n0 + q16 : g.outside, bok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
   float acc[4][4];
 #pragma unroll
@@ -93,120 +214,47 @@ deconv_gemm_kernel(const DeconvArgs g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  // loader roles: A tile = 64 rows x 16 k (thread: row tid >> 2, k quad (tid & 3) * 4) for row-contiguous-in-k operands,
-  // or 16 k x 64 rows (thread: k tid >> 4, row quad (tid & 15) * 4) for k-major operands; B tile = 16 k x 64 cols
-  for (int k0 = k_begin; k0 < k_end; k0 += kTileK) {
-    if (MODE == 0) {
-      // A(m, kk) = in[i(m, tap)][ci .. ci + 3]: contiguous in k
-      const int r = tid >> 2, kq = (tid & 3) * 4;
-      const int m = m0 + r, kk = k0 + kq;
-      const int tap = kk / g.cin, ci = kk - tap * g.cin;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < din3 && kk < k_end) {
-        const int mz = m / (din * din), my = (m / din) % din, mx = m % din;
-        const int iz = mz + tap_off(pz, (tap >> 2) & 1), iy = my + tap_off(py, (tap >> 1) & 1), ix = mx + tap_off(px, tap & 1);
-        if (iz >= 0 && iz < din && iy >= 0 && iy < din && ix >= 0 && ix < din)
-          v = *reinterpret_cast<const float4*>(g.in + ((size_t)(iz * din + iy) * din + ix) * g.cin + ci);
-      }
-      As[(kq + 0) * kTileStride + r] = v.x; As[(kq + 1) * kTileStride + r] = v.y;
-      As[(kq + 2) * kTileStride + r] = v.z; As[(kq + 3) * kTileStride + r] = v.w;
-      // B(kk, n) = w[ci][k(p, tap)][n]: contiguous in n
-      const int kr = tid >> 4, nq = (tid & 15) * 4;
-      const int kb = k0 + kr;
-      const int tapb = kb / g.cin, cib = kb - tapb * g.cin;
-      const int kidx = (tap_k(pz, (tapb >> 2) & 1) * 4 + tap_k(py, (tapb >> 1) & 1)) * 4 + tap_k(px, tapb & 1);
-      const float* src = g.w + ((size_t)cib * 64 + kidx) * g.cout + n0 + nq;
-      float b[4] = {0.f, 0.f, 0.f, 0.f};
-      if (kb < k_end) {
-        if ((g.cout & 3) == 0 && n0 + nq + 4 <= N) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(src));
-          b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
-        } else {
+  const int n_steps = (k_end - k_begin + kTileK - 1) / kTileK;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (n0 + nq + j < N) b[j] = __ldg(src + j);
-        }
-      }
-      *reinterpret_cast<float4*>(Bs + kr * kTileStride + nq) = make_float4(b[0], b[1], b[2], b[3]);
-    } else if (MODE == 1) {
-      // A(i, kk) = outside[o(i, tap)][co .. co + 3], kk = tap * cout_pad + co: contiguous in k
-      const int r = tid >> 2, kq = (tid & 3) * 4;
-      const int i = m0 + r, kk = k0 + kq;
-      const int tl = kk / cout_pad, co = kk - tl * cout_pad;
-      // tap list: all 64 taps, or (din == 1) the 8 taps with k in {1, 2} per axis - the only ones that reach the 2^3 output
-      const int kz = din == 1 ? 1 + ((tl >> 2) & 1) : tl >> 4, ky = din == 1 ? 1 + ((tl >> 1) & 1) : (tl >> 2) & 3,
-                kx = din == 1 ? 1 + (tl & 1) : tl & 3;
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      if (i < din3 && kk < k_end) {
-        const int iz = i / (din * din), iy = (i / din) % din, ix = i % din;
-        const int oz = 2 * iz - 1 + kz, oy = 2 * iy - 1 + ky, ox = 2 * ix - 1 + kx;
-        if (oz >= 0 && oz < dout && oy >= 0 && oy < dout && ox >= 0 && ox < dout) {
-          const float* src = g.outside + ((size_t)(oz * dout + oy) * dout + ox) * g.ld_out + co;
-          if ((g.ld_out & 3) == 0 && co + 4 <= g.cout) {
-            const float4 q = *reinterpret_cast<const float4*>(src);
-            a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
-          } else {
+  for (int s = 0; s < kDecStages - 1; ++s) {
+    if (s < n_steps) issue(k_begin + s * kTileK, s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int step = 0; step < n_steps; ++step) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kDecStages - 2) : "memory");
+    __syncthreads();                                   // tile `step` has landed for every thread; tile step - 1 is no longer read
+    const int nxt = step + kDecStages - 1;
+    if (nxt < n_steps) issue(k_begin + nxt * kTileK, nxt % kDecStages);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* as = As[step % kDecStages];
+    const float* bs = Bs[step % kDecStages];
+    if (kX3) {
+      // tensor-core accumulation truncates: keep its error inside one 16-long partial sum and add the tiles up in
+      // round-to-nearest fp32
+      float part[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (co + j < g.cout) a[j] = src[j];
-          }
-        }
-      }
-      As[(kq + 0) * kTileStride + r] = a[0]; As[(kq + 1) * kTileStride + r] = a[1];
-      As[(kq + 2) * kTileStride + r] = a[2]; As[(kq + 3) * kTileStride + r] = a[3];
-      // B(kk, n = ci) = w[ci][tap][co]: contiguous in k for a fixed ci -> thread: column ci = tid >> 2, k quad
-      const int c = tid >> 2, ci = n0 + c;
-      const int kidx = (kz * 4 + ky) * 4 + kx;
-      float b[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ci < N && kk < k_end) {
-        const float* src = g.w + ((size_t)ci * 64 + kidx) * g.cout + co;
-        if ((g.cout & 3) == 0 && co + 4 <= g.cout) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(src));
-          b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
-        } else {
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (co + j < g.cout) b[j] = __ldg(src + j);
-        }
-      }
-      Bs[(kq + 0) * kTileStride + c] = b[0]; Bs[(kq + 1) * kTileStride + c] = b[1];
-      Bs[(kq + 2) * kTileStride + c] = b[2]; Bs[(kq + 3) * kTileStride + c] = b[3];
+        for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
+      tile_mma<true, A_RK, B_RK>(as, bs, warp, lane, part);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     } else {
-      // A(ci, i) = in[i][ci]: contiguous in the row index -> thread: k = tid >> 4, row quad
-      const int kr = tid >> 4, rq = (tid & 15) * 4;
-      const int i = k0 + kr;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < k_end && m0 + rq + 4 <= M) v = *reinterpret_cast<const float4*>(g.in + (size_t)i * g.cin + m0 + rq);
-      *reinterpret_cast<float4*>(As + kr * kTileStride + rq) = v;
-      // B(i, co) = outside[o(i, tap)][co]
-      float b[4] = {0.f, 0.f, 0.f, 0.f};
-      if (i < k_end) {
-        const int iz = i / (din * din), iy = (i / din) % din, ix = i % din;
-        const int oz = 2 * iz - 1 + wz, oy = 2 * iy - 1 + wy, ox = 2 * ix - 1 + wx;
-        if (oz >= 0 && oz < dout && oy >= 0 && oy < dout && ox >= 0 && ox < dout) {
-          const float* src = g.outside + ((size_t)(oz * dout + oy) * dout + ox) * g.ld_out + n0 + rq;
-          if ((g.ld_out & 3) == 0 && n0 + rq + 4 <= N) {
-            const float4 q = *reinterpret_cast<const float4*>(src);
-            b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (n0 + rq + j < N) b[j] = src[j];
-          }
-        }
-      }
-      *reinterpret_cast<float4*>(Bs + kr * kTileStride + rq) = make_float4(b[0], b[1], b[2], b[3]);
+      tile_mma<false, A_RK, B_RK>(as, bs, warp, lane, acc);
     }
-    __syncthreads();
-    tile_fma(As, Bs, ty, tx, acc);
-    __syncthreads();
   }
 
-  // ---- epilogue
+  // ---- epilogue: fragment f, element e of this lane -> (row, col) of the tile
+  const int wm = warp >> 1, wn = warp & 1, fg = lane >> 2, ft = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
+  for (int i = 0; i < 4; ++i) {                       // i = fragment
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= N) continue;
+    for (int j = 0; j < 4; ++j) {                     // j = element of the fragment
+      const int m = m0 + wm * 16 + fg + 8 * (j >> 1);
+      const int n = n0 + wn * 32 + i * 8 + 2 * ft + (j & 1);
+      if (m >= M || n >= N) continue;
       float v = acc[i][j];
       if (MODE == 0) {
         const int mz = m / (din * din), my = (m / din) % din, mx = m % din;
@@ -226,10 +274,23 @@ deconv_gemm_kernel(const DeconvArgs g) {
           g.dst[(size_t)m * g.cin + n] = v;
         }
       } else {
-        g.dst[((size_t)m * 64 + blockIdx.y) * g.cout + n] = v;
+        // k_splits > 1: partial[split] has the layout of dW itself
+        g.dst[(size_t)blockIdx.z * g.cin * 64 * g.cout + ((size_t)m * 64 + blockIdx.y) * g.cout + n] = v;
       }
     }
   }
+}
+
+// dst[i] = sum_s partial[s][i] (weight gradients of the layers whose K = voxel count was split)
+__global__ void sum_partials_kernel(const float4* __restrict__ partial, int splits, int64_t n4, float4* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = partial[i];
+  for (int k = 1; k < splits; ++k) {
+    const float4 p = partial[(size_t)k * n4 + i];
+    s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+  }
+  dst[i] = s;
 }
 
 // out[row][col] = f(sum_s partial[s][row][col]): forward (bias + optional LeakyReLU) or data gradient (LeakyReLU' mask)
@@ -270,14 +331,23 @@ __global__ void linear_wgrad_kernel(int n_out, int n_in, const float* __restrict
   d_w[idx] = dpre[j] * __ldg(e + i);
   if (i == 0) d_b[j] = dpre[j];
 }
-// d_e[i] = sum_j W[j][i] dpre[j]: one thread per input, fixed order
-__global__ void linear_dgrad_kernel(int n_out, int n_in, const float* __restrict__ w, const float* __restrict__ dpre,
-                                    float* __restrict__ d_e) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_in) return;
+// d_e[i] = sum_j W[j][i] dpre[j]: block = 32 inputs x 8 slices of j, slices added in a fixed order
+__global__ void __launch_bounds__(256) linear_dgrad_kernel(int n_out, int n_in, const float* __restrict__ w, const float* __restrict__ dpre,
+                                                           float* __restrict__ d_e) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int j = 0; j < n_out; ++j) s = fmaf(__ldg(w + (size_t)j * n_in + i), dpre[j], s);
-  d_e[i] = s;
+  if (i < n_in)
+    for (int j = sl; j < n_out; j += 8) s = fmaf(__ldg(w + (size_t)j * n_in + i), dpre[j], s);
+  red[sl][lane] = s;
+  __syncthreads();
+  if (sl == 0 && i < n_in) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    d_e[i] = t;
+  }
 }
 // d_b[c] = sum_rows g[row][c]: one block of 256 threads per column, fixed-order tree
 __global__ void __launch_bounds__(256) column_sum_kernel(int64_t rows, int ld, const float* __restrict__ g, float* __restrict__ out) {
@@ -336,7 +406,7 @@ struct DecPlan {
   int ch[kDecMaxConv + 1];
   int din[kDecMaxConv];
   int ld_logits;
-  int fwd_splits[kDecMaxConv], dgrad_splits[kDecMaxConv];                 // K splits of the forward / data-gradient GEMMs
+  int fwd_splits[kDecMaxConv], dgrad_splits[kDecMaxConv], wgrad_splits[kDecMaxConv];   // K splits of the three GEMMs per layer
   size_t off_h, off_act[kDecMaxConv + 1], off_logits, ws_floats;          // saved for backward
   size_t off_partial, off_g[2], off_dlogits, scratch_floats;
 };
@@ -344,7 +414,7 @@ struct DecPlan {
 // K-splits for a GEMM with `rows` rows: the low layers are weight-bandwidth bound and need many CTAs
 static int pick_splits(int64_t tiles, int k_total) {
   int splits = 1;
-  while (tiles * splits < 296 && splits < 16 && k_total / (splits * 2) >= 64) splits *= 2;
+  while (tiles * splits < 592 && splits < 16 && k_total / (splits * 2) >= 64) splits *= 2;
   return splits;
 }
 
@@ -376,6 +446,9 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
     p.fwd_splits[l] = pick_splits(ft, (p.din[l] == 1 ? 1 : 8) * p.ch[l]);
     const int64_t dt = (int64_t)ceil_div<int64_t>((int64_t)d3, kTile) * ceil_div(p.ch[l], kTile);
     p.dgrad_splits[l] = pick_splits(dt, (p.din[l] == 1 ? 8 : 64) * (ceil_div(p.ch[l + 1], kTileK) * kTileK));
+    const int64_t wt = (int64_t)ceil_div(p.ch[l], kTile) * ceil_div(p.ch[l + 1], kTile) * 64;
+    p.wgrad_splits[l] = pick_splits(wt, (int)d3);
+    if (p.wgrad_splits[l] > 1) part = std::max(part, (size_t)p.wgrad_splits[l] * p.ch[l] * 64 * p.ch[l + 1]);
     if (p.fwd_splits[l] > 1) part = std::max(part, (size_t)p.fwd_splits[l] * 8 * d3 * p.ch[l + 1]);
     if (p.dgrad_splits[l] > 1) part = std::max(part, (size_t)p.dgrad_splits[l] * d3 * p.ch[l]);
     gmax = std::max(gmax, std::max(d3 * p.ch[l], 8 * d3 * (size_t)std::max(p.ch[l + 1], l == n_conv - 1 ? p.ld_logits : 0)));
@@ -390,7 +463,7 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
 }
 
 static int run_forward_layer(const DecPlan& p, int l, const float* in, const float* w, const float* b, float* out, int ld_out,
-                             bool leaky, float* partial, cudaStream_t st) {
+                             bool leaky, float* partial, bool x3, cudaStream_t st) {
   DeconvArgs g;
   memset(&g, 0, sizeof(g));
   const int din = p.din[l], d3 = din * din * din;
@@ -402,7 +475,8 @@ static int run_forward_layer(const DecPlan& p, int l, const float* in, const flo
   g.k_per_split = ceil_div(ceil_div(k_total, splits), kTileK) * kTileK;
   g.dst = splits > 1 ? partial : out;
   dim3 grid((unsigned)tiles, 8, (unsigned)splits);
-  deconv_gemm_kernel<0><<<grid, 256, 0, st>>>(g);
+  if (x3) deconv_gemm_kernel<0, true><<<grid, 256, 0, st>>>(g);
+  else deconv_gemm_kernel<0, false><<<grid, 256, 0, st>>>(g);
   HN_TRY(launched("hn_vol_decoder_fwd/deconv"));
   if (splits > 1) {
     const int64_t rows = (int64_t)8 * d3;
@@ -432,7 +506,8 @@ int64_t hn_vol_decoder_scratch_bytes(int embed, int hidden, int n_conv, const in
 
 int hn_vol_decoder_fwd(int embed, int hidden, int n_conv, const int* channels, const float* embedding, const float* lin_w,
                        const float* lin_b, const float* const* conv_w, const float* const* conv_b, const float* prior,
-                       float* vol, void* workspace, int64_t workspace_bytes, void* scratch, int64_t scratch_bytes, void* stream) {
+                       float* vol, void* workspace, int64_t workspace_bytes, void* scratch, int64_t scratch_bytes, int precision,
+                       void* stream) {
   DecPlan p;
   HN_TRY(make_dec_plan(embed, hidden, n_conv, channels, p));
   if (!embedding || !lin_w || !lin_b || !conv_w || !conv_b || !prior || !vol || !workspace || !scratch)
@@ -450,7 +525,7 @@ int hn_vol_decoder_fwd(int embed, int hidden, int n_conv, const int* channels, c
     const bool last = l == n_conv - 1;
     float* out = last ? ws + p.off_logits : ws + p.off_act[l + 1];
     HN_TRY(run_forward_layer(p, l, ws + p.off_act[l], conv_w[l], conv_b[l], out, last ? p.ld_logits : p.ch[l + 1], !last,
-                             sc + p.off_partial, st));
+                             sc + p.off_partial, precision == HN_PRECISION_FP32, st));
   }
   const int side = 2 * p.din[n_conv - 1], n_vox = side * side * side;
   softmax_prior_fwd_kernel<<<ceil_div(n_vox, 128), 128, 0, st>>>(n_vox, p.ch[n_conv], p.ld_logits, ws + p.off_logits, prior, vol);
@@ -460,7 +535,8 @@ int hn_vol_decoder_fwd(int embed, int hidden, int n_conv, const int* channels, c
 int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, const float* embedding, const float* lin_w,
                        const float* const* conv_w, const float* vol, const float* d_vol, const void* workspace,
                        int64_t workspace_bytes, void* scratch, int64_t scratch_bytes, float* d_embedding, float* d_lin_w,
-                       float* d_lin_b, float* const* d_conv_w, float* const* d_conv_b, void* stream) {
+                       float* d_lin_b, float* const* d_conv_w, float* const* d_conv_b, int precision, void* stream) {
+  const bool x3 = precision == HN_PRECISION_FP32;
   DecPlan p;
   HN_TRY(make_dec_plan(embed, hidden, n_conv, channels, p));
   if (!embedding || !lin_w || !conv_w || !vol || !d_vol || !workspace || !scratch || !d_embedding || !d_lin_w || !d_lin_b ||
@@ -488,10 +564,20 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     DeconvArgs g;
     memset(&g, 0, sizeof(g));
     g.din = din; g.cin = cin; g.cout = cout; g.ld_out = ld_g; g.in = ws + p.off_act[l]; g.outside = g_out; g.dst = d_conv_w[l];
-    g.k_splits = 1;
-    dim3 wgrid((unsigned)(ceil_div(cin, kTile) * ceil_div(cout, kTile)), 64, 1);
-    deconv_gemm_kernel<2><<<wgrid, 256, 0, st>>>(g);
+    const int wsp = p.wgrad_splits[l];
+    g.k_splits = wsp;
+    g.k_per_split = ceil_div(ceil_div(d3, wsp), kTileK) * kTileK;
+    if (wsp > 1) g.dst = sc + p.off_partial;
+    dim3 wgrid((unsigned)(ceil_div(cin, kTile) * ceil_div(cout, kTile)), 64, (unsigned)wsp);
+    if (x3) deconv_gemm_kernel<2, true><<<wgrid, 256, 0, st>>>(g);
+    else deconv_gemm_kernel<2, false><<<wgrid, 256, 0, st>>>(g);
     HN_TRY(launched("hn_vol_decoder_bwd/wgrad"));
+    if (wsp > 1) {
+      const int64_t n4 = (int64_t)cin * 64 * cout / 4;
+      sum_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sc + p.off_partial), wsp, n4,
+                                                                              reinterpret_cast<float4*>(d_conv_w[l]));
+      HN_TRY(launched("hn_vol_decoder_bwd/wgrad sum"));
+    }
     // data gradient -> gradient of the pre-activation of the previous layer (LeakyReLU' from its stored output)
     float* g_in = sc + p.off_g[l & 1];
     g.w = conv_w[l]; g.act_in = ws + p.off_act[l];
@@ -502,7 +588,8 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     g.k_per_split = ceil_div(ceil_div(k_total, splits), kTileK) * kTileK;
     g.dst = splits > 1 ? sc + p.off_partial : g_in;
     dim3 dgrid((unsigned)tiles, 1, (unsigned)splits);
-    deconv_gemm_kernel<1><<<dgrid, 256, 0, st>>>(g);
+    if (x3) deconv_gemm_kernel<1, true><<<dgrid, 256, 0, st>>>(g);
+    else deconv_gemm_kernel<1, false><<<dgrid, 256, 0, st>>>(g);
     HN_TRY(launched("hn_vol_decoder_bwd/dgrad"));
     if (splits > 1) {
       deconv_finish_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)d3 * cin, 256), 256, 0, st>>>(sc + p.off_partial, splits, d3, cin, cin, nullptr, 0,
@@ -515,7 +602,7 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
   // linear layer: g_out = d(pre-activation of h) (hidden)
   linear_wgrad_kernel<<<ceil_div(hidden * embed, 256), 256, 0, st>>>(hidden, embed, g_out, embedding, d_lin_w, d_lin_b);
   HN_TRY(launched("hn_vol_decoder_bwd/linear wgrad"));
-  linear_dgrad_kernel<<<ceil_div(embed, 128), 128, 0, st>>>(hidden, embed, lin_w, g_out, d_embedding);
+  linear_dgrad_kernel<<<ceil_div(embed, 32), 256, 0, st>>>(hidden, embed, lin_w, g_out, d_embedding);
   return launched("hn_vol_decoder_bwd/linear dgrad");
 }
 

@@ -1,10 +1,12 @@
 """Motion-weight volume decoder, plugin-compatible with reference
 `core/nets/human_nerf/mweight_vol_decoders/deconv_vol_decoder.py:8-33`:
 softmax(decoder(const_embedding) + log(prior)) over the 25 channels.  On a CUDA device the whole module - linear
-layer, the five transposed convolutions, LeakyReLUs, softmax with the prior, and their backward - runs on the
-hand-written kernels of csrc/vol_decoder.cu (`ops.vol_decoder`, fp32, deterministic); `cfg.b200.decoder = 'cudnn'`
-keeps the PyTorch / cuDNN path (TF32 on the bf16 path) as an A/B arm.  CPU tensors (construction-time tests, the
-oracle arm) always take the PyTorch path."""
+layer, the five transposed convolutions, LeakyReLUs, softmax with the prior, and their backward - can run on the
+hand-written kernels of csrc/vol_decoder.cu (`ops.vol_decoder`: fp32 storage, tensor-core products, deterministic).
+`cfg.b200.decoder`: 'hn' = those kernels, 'cudnn' = PyTorch / cuDNN, 'auto' (default) = 'hn' on the fp32 parity path
+(3xTF32 products, bit-reproducible gradients) and 'cudnn' with TF32 on the bf16 path, where cuDNN's implicit-GEMM
+engines are still ~0.6 ms per training step faster than the mma.sync kernels here (measured: 7.00 against 7.58 ms per
+step).  CPU tensors (construction-time tests, the oracle arm) always take the PyTorch path."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -26,8 +28,7 @@ class MotionWeightVolumeDecoder(nn.Module):
 
     def _use_kernels(self, prior) -> bool:
         from humannerf_b200.config import get_cfg
-        mode = str(get_cfg().get('b200', {}).get('decoder', 'hn')).lower()
-        return prior.is_cuda and mode != 'cudnn'
+XX
 
     def forward(self, motion_weights_priors, **_):
         if self._use_kernels(motion_weights_priors):
@@ -35,8 +36,12 @@ class MotionWeightVolumeDecoder(nn.Module):
             convs = [m for m in self.decoder.block_conv if isinstance(m, nn.ConvTranspose3d)]
             lin = self.decoder.block_mlp[0]
             prior = motion_weights_priors[0] if motion_weights_priors.dim() == 5 else motion_weights_priors
+            from humannerf_b200 import _lib
+            # allow_tf32 (set by Network: True on the bf16 tensor-core path) selects plain TF32 products; the fp32
+            # parity path multiplies as 3xTF32 (fp32-level accuracy)
             vol = ops.vol_decoder(self.const_embedding, lin.weight, lin.bias, prior, [c.weight for c in convs],
-                                  [c.bias for c in convs])
+                                  [c.bias for c in convs],
+                                  precision=_lib.PRECISION_BF16 if self.allow_tf32 else _lib.PRECISION_FP32)
             return vol[None, ...]
         # on the fp32 parity path TF32 is off: its 10-bit mantissa moves the sampled blend weights by 1e-4
         # and breaks the 1e-4 output parity with the reference

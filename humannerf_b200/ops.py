@@ -268,7 +268,7 @@ class _VolDecoder(torch.autograd.Function):
     [w0, b0, w1, b1, ...] - weights (C_in, C_out, 4, 4, 4) in channels_last_3d strides."""
 
     @staticmethod
-    def forward(ctx, embedding, lin_w, lin_b, prior, *wb):
+    def forward(ctx, precision, embedding, lin_w, lin_b, prior, *wb):
         lib = _lib.load()
         ws_, bs_ = list(wb[0::2]), list(wb[1::2])
         n_conv = len(ws_)
@@ -295,8 +295,9 @@ class _VolDecoder(torch.autograd.Function):
         bp = (C.c_void_p * n_conv)(*[b.data_ptr() for b in bs_])
         with torch.cuda.device(dev), _timed('vol_decoder_fwd'):
             check(lib.hn_vol_decoder_fwd(E, H, n_conv, ch, ptr(embedding), ptr(lin_w), ptr(lin_b), wp, bp, ptr(prior), ptr(vol),
-                                         ptr(ws), wbytes, ptr(scratch), sbytes, stream_ptr()), 'vol_decoder_fwd')
+                                         ptr(ws), wbytes, ptr(scratch), sbytes, int(precision), stream_ptr()), 'vol_decoder_fwd')
         ctx.geom = (E, H, n_conv, channels)
+        ctx.precision = int(precision)
         ctx.ws = ws
         ctx.save_for_backward(embedding, lin_w, vol, *ws_)
         return vol
@@ -321,21 +322,22 @@ class _VolDecoder(torch.autograd.Function):
         with torch.cuda.device(dev), _timed('vol_decoder_bwd'):
             check(lib.hn_vol_decoder_bwd(E, H, n_conv, ch, ptr(embedding), ptr(lin_w), wp, ptr(vol), ptr(g_vol), ptr(ctx.ws),
                                          ctx.ws.numel(), ptr(scratch), sbytes, ptr(d_e), ptr(d_lw), ptr(d_lb), dwp, dbp,
-                                         stream_ptr()), 'vol_decoder_bwd')
+                                         ctx.precision, stream_ptr()), 'vol_decoder_bwd')
         ctx.ws = None
-        out = [d_e, d_lw, d_lb, None]
+        out = [None, d_e, d_lw, d_lb, None]
         for w, b in zip(d_w, d_b):
             out += [w, b]
         return tuple(out)
 
 
-def vol_decoder(embedding, lin_w, lin_b, prior, conv_weights, conv_biases):
+def vol_decoder(embedding, lin_w, lin_b, prior, conv_weights, conv_biases, precision=_lib.PRECISION_FP32):
     """softmax_c(ConvDecoder3D(embedding) + log prior) -> (C, V, V, V) (deconv_vol_decoder.py:25-33, network_util.py:12-50)
-    on the hand-written kernels of csrc/vol_decoder.cu; differentiable in everything but the prior."""
+    on the hand-written kernels of csrc/vol_decoder.cu; differentiable in everything but the prior.
+    precision: PRECISION_FP32 = 3xTF32 products (fp32-level accuracy), PRECISION_BF16 = plain TF32 products."""
     wb = []
     for w, b in zip(conv_weights, conv_biases):
         wb += [w, b]
-    return _VolDecoder.apply(embedding, lin_w, lin_b, prior, *wb)
+    return _VolDecoder.apply(int(precision), embedding, lin_w, lin_b, prior, *wb)
 
 
 # ---------------------------------------------------------------------------

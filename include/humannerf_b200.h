@@ -235,7 +235,8 @@ int hn_gather_rows(int64_t n_rows, int n_cols, const float* src, const int64_t* 
  * a7  core/nets/human_nerf/mweight_vol_decoders/deconv_vol_decoder.py:25-33 + core/utils/network_util.py:12-50
  * vol = softmax_c(ConvDecoder3D(const_embedding) + log(prior)): Linear(embed, hidden) + LeakyReLU(0.2), then n_conv
  * ConvTranspose3d(k4, s2, p1) layers with channels[0] = hidden -> ... -> channels[n_conv] (LeakyReLU(0.2) between
- * them), volume side 2^n_conv.  fp32, deterministic (no atomics).  lin_w (hidden, embed) row-major; conv_w[l] is the
+ * them), volume side 2^n_conv.  fp32 storage, deterministic (no atomics); precision = HN_PRECISION_FP32: products as
+ * 3xTF32 (fp32-level accuracy, the 1e-4 parity path), HN_PRECISION_BF16: plain TF32 tensor-core products.  lin_w (hidden, embed) row-major; conv_w[l] is the
  * ConvTranspose3d weight (C_in, C_out, 4, 4, 4) in NDHWC (torch.channels_last_3d) strides, i.e. memory order
  * [C_in][kz][ky][kx][C_out]; d_conv_w[l] is written in the same order.  prior / vol / d_vol: (channels[n_conv], V, V, V)
  * contiguous.  workspace (hn_vol_decoder_workspace_bytes) keeps the activations between forward and backward;
@@ -246,11 +247,11 @@ int64_t hn_vol_decoder_scratch_bytes(int embed, int hidden, int n_conv, const in
 int hn_vol_decoder_fwd(int embed, int hidden, int n_conv, const int* channels, const float* embedding, const float* lin_w,
                        const float* lin_b, const float* const* conv_w, const float* const* conv_b, const float* prior,
                        float* vol, void* workspace, int64_t workspace_bytes, void* scratch, int64_t scratch_bytes,
-                       void* stream);
+                       int precision, void* stream);
 int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, const float* embedding, const float* lin_w,
                        const float* const* conv_w, const float* vol, const float* d_vol, const void* workspace,
                        int64_t workspace_bytes, void* scratch, int64_t scratch_bytes, float* d_embedding, float* d_lin_w,
-                       float* d_lin_b, float* const* d_conv_w, float* const* d_conv_b, void* stream);
+                       float* d_lin_b, float* const* d_conv_w, float* const* d_conv_b, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a3  core/data/human_nerf/train.py:235-340 get_patch_ray_indices / _get_patch_ray_indices,
