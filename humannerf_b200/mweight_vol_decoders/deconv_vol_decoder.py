@@ -28,7 +28,10 @@ class MotionWeightVolumeDecoder(nn.Module):
 
     def _use_kernels(self, prior) -> bool:
         from humannerf_b200.config import get_cfg
-XX
+        mode = str(get_cfg().get('b200', {}).get('decoder', 'auto')).lower()
+        if mode == 'auto':
+            mode = 'cudnn' if self.allow_tf32 else 'hn'          # allow_tf32: set by Network on the bf16 path
+        return prior.is_cuda and mode != 'cudnn'
 
     def forward(self, motion_weights_priors, **_):
         if self._use_kernels(motion_weights_priors):

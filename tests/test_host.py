@@ -71,7 +71,9 @@ def test_field_plan_sizes():
     # backward-data image: W^T windows, K = out features (16 for the output layers), N = width / pe_pad
     nr_bwd = 16 * 128 + 5 * 128 * 128 + 2 * 128 * 48
     cn_bwd = 16 * 256 + 7 * 256 * 256 + 2 * 256 * 64
-    elems = nr + cn + nr_bwd + cn_bwd
+    # the forward weights appear twice: the chunks of the SS kernel (mlp_tc_2sm.cu) and, with the same K rows grouped
+    # per (layer, accumulator half), the chunks of the TS kernel (mlp_tc_ts.cu)
+    elems = 2 * (nr + cn) + nr_bwd + cn_bwd
     assert 2 * elems < packed < 2 * elems + 64 * 1024
 
 
