@@ -475,6 +475,17 @@ class GraphedTrainStep:
             g['lr'] = cfg.train[f"lr_{g['name']}"] if f"lr_{g['name']}" in cfg.train else cfg.train.lr
         # the warm-up iterations below are real optimizer steps on the loaded batch; undo them afterwards
         # so that capture has no side effect on the training state
+        # Autograd caches one AccumulateGrad node per parameter for as long as ANY graph that uses the parameter is alive,
+        # and runs it on the stream it was created on.  If an earlier eager step ran on the legacy default stream and
+        # something still references its graph (the network keeps the last boundary tensors, a reducer too), the
+        # captured backward would have to synchronise with that stream - illegal during capture.  Drop what we can reach.
+        for holder in (self.net, getattr(self.net, 'module', None)):
+            if holder is not None and hasattr(holder, 'boundary_tensors'):
+                holder.boundary_tensors = {}
+                holder.motion_weights_vol = None
+        if self.reducer is not None:
+            self.reducer.boundary = {}
+        self.opt.zero_grad(set_to_none=True)
         snap_p = [p.detach().clone() for p in self.opt._ps]
         snap = (self.opt._flat_m.clone(), self.opt._flat_v.clone(), self.opt.step_dev.clone())
         side = torch.cuda.Stream()

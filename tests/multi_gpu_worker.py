@@ -80,6 +80,8 @@ def main():
     for k, v in rows.items():
         worst[k.split('.')[0]] = max(worst.get(k.split('.')[0], 0.0), v)
 
+    loss_single, loss_split = float(loss1), float(lossN)
+    del out, rgb, lossN, loss1          # the eager graphs above must not outlive this point (see GraphedTrainStep._capture)
     # ---- replicas stay identical through optimizer steps (bf16 tensor-core path, strong split)
     cfg.b200.mlp_precision = 'bf16'
     cfg.b200.jitter_rng = 'device'
@@ -120,7 +122,7 @@ def main():
     if rank == 0:
         print('MULTI ' + json.dumps({
             'world': world, 'backend': 'nccl' if nccl else 'gloo', 'devices': world if nccl else 1,
-            'loss_single': float(loss1), 'loss_split': float(lossN), 'floats_exchanged': n_floats,
+            'loss_single': loss_single, 'loss_split': loss_split, 'floats_exchanged': n_floats,
             'grad_rel_l2_worst_by_group': worst, 'grad_rel_l2_worst': max(rows.values()),
             'steps_mode': mode, 'step_losses': losses, 'param_divergence_after_3_steps': div,
             'params_moved_max_abs': moved}), flush=True)
