@@ -3,8 +3,8 @@
 softmax(decoder(const_embedding) + log(prior)) over the 25 channels.  On a CUDA device the whole module - linear
 layer, the five transposed convolutions, LeakyReLUs, softmax with the prior, and their backward - can run on the
 hand-written kernels of csrc/vol_decoder.cu (`ops.vol_decoder`: fp32 storage, tensor-core products, deterministic).
-`cfg.b200.decoder`: 'hn' = those kernels, 'cudnn' = PyTorch / cuDNN, 'auto' (default) = 'hn' on the fp32 parity path
-(3xTF32 products, bit-reproducible gradients) and 'cudnn' with TF32 on the bf16 path, where cuDNN's implicit-GEMM
+`cfg.b200.decoder`: 'hn' = those kernels, 'cudnn' = PyTorch / cuDNN, 'auto' (default) = 'hn' everywhere (fp32 parity path:
+3xTF32 products, bit-reproducible gradients; rendering) except bf16-path training steps, where cuDNN's TF32 implicit-GEMM
 engines are still ~0.6 ms per training step faster than the mma.sync kernels here (measured: 7.00 against 7.58 ms per
 step).  CPU tensors (construction-time tests, the oracle arm) always take the PyTorch path."""
 import torch
@@ -30,7 +30,8 @@ class MotionWeightVolumeDecoder(nn.Module):
         from humannerf_b200.config import get_cfg
         mode = str(get_cfg().get('b200', {}).get('decoder', 'auto')).lower()
         if mode == 'auto':
-            mode = 'cudnn' if self.allow_tf32 else 'hn'          # allow_tf32: set by Network on the bf16 path
+            # cuDNN only where it is faster: bf16-path TRAINING steps (allow_tf32 is set by Network on the bf16 path)
+            mode = 'cudnn' if (self.allow_tf32 and torch.is_grad_enabled()) else 'hn'
         return prior.is_cuda and mode != 'cudnn'
 
     def forward(self, motion_weights_priors, **_):
