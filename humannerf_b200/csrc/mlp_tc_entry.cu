@@ -65,6 +65,10 @@ int launch_field_ts(const TcPlan& plan, const uint8_t* packed, int64_t n_samples
                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets,
                     const TrainBufs* bufs, int sms, cudaStream_t st);
 
+// mlp_tc_ts2.cu
+int launch_field_ts2(const TcPlan& plan, const uint8_t* packed, int64_t n_samples, const int64_t* n_samples_dev, const float* x_skel,
+                     const float* hann_w, int ignore_non_rigid, float* raw, float* xyz, float* offsets, int sms, cudaStream_t st);
+
 // Forward kernel selection, read once per process.  Default ("auto"): rendering (nothing saved for backward) runs the TS
 // kernel (hidden activations in tensor memory, mlp_tc_ts.cu: 28.7 instead of 33.5 ms per 512 x 512 frame), training the
 // SS kernel of mlp_tc_2sm.cu (activations in shared memory, image stores through the TMA: 1.40 against 1.45 ms per
@@ -172,6 +176,12 @@ int hn_field_fwd(const hn_field_params* p, int64_t n_samples, const float* x_ske
     if (!workspace || workspace_bytes < need) return fail_arg("hn_field_fwd: bf16 training workspace too small");
     if (!use_relu_bits()) memset(bufs.bits, 0, sizeof(bufs.bits));
   }
+  // rendering with the reference widths: the two-tile TS kernel (HN_TC_TS2=0 keeps the one-tile kernel)
+  static const bool ts2_on = [] { const char* v = getenv("HN_TC_TS2"); return v == nullptr || atoi(v) != 0; }();
+  if (use_ts_forward(save_for_backward != 0) && !save_for_backward && ts2_on && !plan.ts_chunks.empty() && plan.width[0] == 128 &&
+      plan.width[1] == 256)
+    return launch_field_ts2(plan, static_cast<const uint8_t*>(packed), n_samples, n_samples_dev, x_skel, hann_w,
+                            ignore_non_rigid ? 1 : 0, raw, xyz, offsets, sms, as_stream(stream));
   if (use_ts_forward(save_for_backward != 0) && !plan.ts_chunks.empty())
     return launch_field_ts(plan, static_cast<const uint8_t*>(packed), n_samples, n_samples_dev, x_skel, hann_w,
                            ignore_non_rigid ? 1 : 0, raw, xyz, offsets, save_for_backward ? &bufs : nullptr, sms,
