@@ -702,15 +702,18 @@ def main():
 
     # =========================== render leg (forward, bf16 tcgen05) ================================
     if not args.no_render:
+        # the frame goes through the network in ONE chunk (cfg.chunk raised from the reference's 32768 rays: 180 GB of HBM
+        # hold every per-sample tensor of a frame; chunking changes no value - tests/test_gpu_parity.py - only adds 8 x
+        # the launches and a concatenation of the per-sample outputs)
         for _ in range(3):
-            render_frame(sharded=True)
+            render_frame(sharded=True, one_chunk=True)
         barrier()
         ops.timing_start()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
         r0.record()
         for _ in range(reps):
-            render_frame(sharded=True)
+            render_frame(sharded=True, one_chunk=True)
         r1.record()
         barrier()
         rop = ops.timing_stop()
@@ -724,8 +727,8 @@ def main():
         rt, mt = (traffic or {}).get('render_field'), (traffic or {}).get('render_motion_field')
         result['render'] = {
             'rays_per_sec': n_valid / (rms * 1e-3), 'samples_per_sec': n_valid * N_SAMPLES / (rms * 1e-3), 'ms_per_frame': rms,
-            'rays': int(n_valid), 'scaling': 'strong (one frame, rays sharded over ranks + all_gather of 20 B/ray)', 'ops_ms_per_frame': {k: round(v[0] / reps, 3) for k, v in sorted(rop.items())},
-            'roofline_mlp': {'kernel': 'field_tc2_kernel (tcgen05 cta_group::2 / TMEM, fused PE + MLPs on CTA pairs)', 'bound': 'tensor', 'achieved': tc_tf,
+            'rays': int(n_valid), 'chunk': 'whole frame in one chunk', 'scaling': 'strong (one frame, rays sharded over ranks + all_gather of 20 B/ray)', 'ops_ms_per_frame': {k: round(v[0] / reps, 3) for k, v in sorted(rop.items())},
+            'roofline_mlp': {'kernel': 'field_ts2_kernel (tcgen05 cta_group::2, TS form: hidden activations in tensor memory; fused PE + both MLPs on CTA pairs)', 'bound': 'tensor', 'achieved': tc_tf,
                              'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': tc_tf / peaks['tf'],
                              'traffic': rt['dram_bytes'] if rt else None, 'traffic_source': rt['source'] if rt else None,
                              'peak_source': peaks['source'] + ' (burst bf16)'},
@@ -738,7 +741,7 @@ def main():
 
         # opt-in empty-space skipping (cfg.b200.cull_mask_eps = 1e-7: outputs within 2.6e-5 of the dense
         # render) with the frame in one chunk; reported next to the dense leg, never instead of it
-        dense_ref = render_frame(sharded=True)
+        dense_ref = render_frame(sharded=True, one_chunk=True)
         for _ in range(2):
             culled = render_frame(sharded=True, cull_eps=1e-7, one_chunk=True)
         barrier()
