@@ -29,6 +29,7 @@ constexpr uint32_t kWgOperandBytes = 256 * kWgStageSamples * 2;       // 32 KB: 
 constexpr uint32_t kWgStageBytes = 2 * kWgOperandBytes;               // A (dZ) + B (X)
 constexpr uint32_t kWgBarOff = kWgStages * kWgStageBytes;
 constexpr uint32_t kWgSmem = kWgBarOff + 128;
+constexpr int kWgItemsPerSm = 3;
 constexpr int kWgThreads = 6 * 32;                                    // producer, MMA, 4 epilogue warps
 
 // MN-major for both operands: bits 15 / 16 of the instruction descriptor
@@ -38,17 +39,32 @@ __device__ __forceinline__ uint32_t make_idesc_mn(uint32_t n) { return make_ides
 // captured in a CUDA graph.
 struct WgradJobTable {
   WgradJob jobs[kMaxWgradJobs];
+  int slab0[kMaxWgradJobs + 1];      // work items of job j: [slab0[j], slab0[j + 1]) - one item = one slab of samples
 };
 
+// Work decomposition: job j is cut into n_slabs_j = slab0[j + 1] - slab0[j] slabs of samples, n_slabs_j proportional to
+// the bytes the job streams per sample (f_dz + n features), so every (job, slab) item costs about the same and the
+// item count is a whole multiple of the grid: the static round-robin over the CTAs is balanced (a common slab count
+// for all jobs left the slowest CTA 16 % above the mean with the 144 ... 512-byte jobs of the training step).
+struct WgradItem { int job, slab, n_slabs; };
+// even split of the tiles over a job's slabs (slabs differ by at most one tile; empty when n_tiles < n_slabs)
+__device__ __forceinline__ int slab_begin(int n_tiles, int slab, int n_slabs) {
+  return (int)((int64_t)slab * n_tiles / n_slabs);
+}
+__device__ __forceinline__ WgradItem find_item(const WgradJobTable& tab, int n_jobs, int item) {
+  int j = 0;
+  while (j + 1 < n_jobs && item >= tab.slab0[j + 1]) ++j;
+  return {j, item - tab.slab0[j], tab.slab0[j + 1] - tab.slab0[j]};
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1)
-tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles_cap, int n_slabs_cap,
-                  const int64_t* __restrict__ n_dev, int slab_major) {
+tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_tiles_cap,
+                  const int64_t* __restrict__ n_dev) {
   const WgradJob* jobs = tab.jobs;
   // n_dev (nullable): number of samples actually present (device-side count, see field_tc_kernel); the slab
-  // decomposition keeps the host's slab COUNT and shrinks the slabs
+  // decomposition keeps the host's slab COUNTS and shrinks the slabs
   int n_tiles = n_tiles_cap;
   if (n_dev) n_tiles = (int)min((max(__ldg(n_dev), (int64_t)0) + 127) / 128, (int64_t)n_tiles_cap);
-  const int tiles_per_slab = max((n_tiles + n_slabs_cap - 1) / n_slabs_cap, 1);
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_full = s_base + kWgBarOff;
@@ -58,8 +74,7 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
   const uint32_t s_tmem_slot = s_drained + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWgBarOff + (2 * kWgStages + 2) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_slabs = n_slabs_cap;
-  const int n_items = n_jobs * n_slabs;
+  const int n_items = tab.slab0[n_jobs];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) {
@@ -84,12 +99,9 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        // slab-major order: CTAs that run at the same time work on the SAME slab of samples for
-        // neighbouring jobs, so a dZ image that two jobs of a layer read (weights + bias column)
-        // comes from HBM once and from L2 the second time
-        const int ji = slab_major ? item % n_jobs : item / n_slabs, si = slab_major ? item / n_jobs : item % n_slabs;
-        const WgradJob job = jobs[ji];
-        const int t0 = si * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        const WgradItem it = find_item(tab, n_jobs, item);
+        const WgradJob job = jobs[it.job];
+        const int t0 = slab_begin(n_tiles, it.slab, it.n_slabs), t1 = slab_begin(n_tiles, it.slab + 1, it.n_slabs);
         const uint32_t a_blk = (uint32_t)job.f_dz * 32u;       // bytes per 16-sample block of the dZ image
         const uint32_t x_blk = (uint32_t)job.f_x * 32u;
         const uint32_t b_blk = (uint32_t)job.n * 32u;          // bytes of the X window per 16-sample block
@@ -121,9 +133,9 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
       const uint32_t lo_const = ((128u >> 4) << 16);          // LBO = 128 B (next 8 samples)
       bool first_item = true;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ji = slab_major ? item % n_jobs : item / n_slabs, si = slab_major ? item / n_jobs : item % n_slabs;
-        const WgradJob job = jobs[ji];
-        const int t0 = si * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
+        const WgradItem it = find_item(tab, n_jobs, item);
+        const WgradJob job = jobs[it.job];
+        const int t0 = slab_begin(n_tiles, it.slab, it.n_slabs), t1 = slab_begin(n_tiles, it.slab + 1, it.n_slabs);
         const int m_tiles = (job.m + 127) / 128;
         const uint32_t idesc = make_idesc_mn((uint32_t)job.n);
         const uint32_t a_blk = (uint32_t)job.f_dz * 32u, b_blk = (uint32_t)job.n * 32u;
@@ -164,16 +176,16 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
     uint32_t acc_phase = 0;
     uint32_t e_stage = 0, e_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const WgradJob job = jobs[slab_major ? item % n_jobs : item / n_slabs];
+      const WgradItem it = find_item(tab, n_jobs, item);
+      const WgradJob job = jobs[it.job];
       const int m_tiles = (job.m + 127) / 128;
-      const int e_si = slab_major ? item / n_jobs : item % n_slabs;
-      const bool has_tiles = e_si * tiles_per_slab < n_tiles;      // an empty slab left the accumulators undefined
+      const int t0 = slab_begin(n_tiles, it.slab, it.n_slabs), t1 = slab_begin(n_tiles, it.slab + 1, it.n_slabs);
+      const bool has_tiles = t1 > t0;                              // an empty slab left the accumulators undefined
       // While the MMA warp works through the stages, these four otherwise idle warps read the dZ operand of
       // every stage from shared memory and keep its column sums = the bias gradient (bias_col == -2), so no
       // second job has to stream dZ from HBM again just for db.  Thread (warp w, lane l) owns the 8 features
       // of 16-byte chunk l and the 16 samples of block w of the 64-sample stage.
       {
-        const int t0 = e_si * tiles_per_slab, t1 = min(n_tiles, t0 + tiles_per_slab);
         const bool direct = job.bias_col == -2 && job.db != nullptr;
         const int ew = warp - 2;
         const bool own = direct && lane * 8 < job.m;
@@ -190,7 +202,11 @@ tile_wgrad_kernel(const __grid_constant__ WgradJobTable tab, int n_jobs, int n_t
 #pragma unroll 4
                 for (int r = 0; r < 16; ++r) {
                   uint32_t w0, w1, w2, w3;
-                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(src + r * 16u));
+                  // lane l starts at sample l: the 8 lanes of a quarter warp (256 bytes apart) hit 8 different 16-byte bank
+                  // groups instead of one (the straight order made every load a 32-way conflict, 2048 shared-memory
+                  // wavefronts per 64 KB stage - more than the MMAs and the TMA writes of the stage together)
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                               : "r"(src + (((uint32_t)(r + lane) & 15u) << 4)));
                   bsum[0] += __uint_as_float(w0 << 16); bsum[1] += __uint_as_float(w0 & 0xFFFF0000u);
                   bsum[2] += __uint_as_float(w1 << 16); bsum[3] += __uint_as_float(w1 & 0xFFFF0000u);
                   bsum[4] += __uint_as_float(w2 << 16); bsum[5] += __uint_as_float(w2 & 0xFFFF0000u);
@@ -289,13 +305,34 @@ int launch_tile_wgrad(const WgradJob* jobs_host, int n_jobs, int64_t n_samples, 
   HN_TRY(check_cuda(cudaFuncSetAttribute(tile_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kWgSmem), "tile_wgrad/smem attr"));
   const int n_tiles = (int)ceil_div<int64_t>(n_samples, 128);
-  // ~3 work items per SM: enough to balance, few enough to keep the atomic traffic small
-  int n_slabs = std::max(1, std::min(n_tiles, (3 * sms + n_jobs - 1) / n_jobs));
-  const int tiles_per_slab = (n_tiles + n_slabs - 1) / n_slabs;
-  n_slabs = (n_tiles + tiles_per_slab - 1) / tiles_per_slab;
-  const int grid = std::min(n_jobs * n_slabs, sms);
-  const char* ord = getenv("HN_WGRAD_SLAB_MAJOR");       // measurement aid (A/B of the item order)
-  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, n_slabs, n_samples_dev, ord ? atoi(ord) : 0);
+  // ~kWgItemsPerSm equal-cost work items per SM (few enough to keep the atomic traffic of the epilogues small): slabs per job
+  // proportional to the bytes per sample it streams, then the largest jobs take up the rounding slack so that the
+  // item count is a multiple of the grid
+  const int want = kWgItemsPerSm * sms;
+  double cost_sum = 0.0;
+  for (int j = 0; j < n_jobs; ++j) cost_sum += jobs_host[j].f_dz + jobs_host[j].n;
+  int slabs[kMaxWgradJobs], total = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    const double share = (jobs_host[j].f_dz + jobs_host[j].n) / cost_sum * want;
+    slabs[j] = std::max(1, std::min(n_tiles, (int)(share + 0.5)));
+    total += slabs[j];
+  }
+  const int grid = std::min(total, sms);
+  for (int guard = 0; total % grid != 0 && guard < 4 * kMaxWgradJobs; ++guard) {
+    // add slabs to the jobs with the most samples per slab until the count is a multiple of the grid
+    int best = -1;
+    double best_load = 0.0;
+    for (int j = 0; j < n_jobs; ++j) {
+      const double load = (double)(jobs_host[j].f_dz + jobs_host[j].n) / slabs[j];
+      if (slabs[j] < n_tiles && load > best_load) { best_load = load; best = j; }
+    }
+    if (best < 0) break;
+    ++slabs[best];
+    ++total;
+  }
+  tab.slab0[0] = 0;
+  for (int j = 0; j < n_jobs; ++j) tab.slab0[j + 1] = tab.slab0[j] + slabs[j];
+  tile_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(tab, n_jobs, n_tiles, n_samples_dev);
   return launched("tile_wgrad");
 }
 

@@ -31,7 +31,8 @@ constexpr float kLeaky = 0.2f;
 constexpr int kTile = 64, kTileK = 16;
 
 struct DeconvArgs {
-  int din;                 // input volume side (output side = 2 din)
+  int din;                 // input volume side (output side = 2 din), a power of two
+  int log2_din;
   int cin, cout;           // channels
   int ld_out;              // row stride (floats) of the output-side activation / gradient buffer (>= cout)
   const float* in;         // input-side activation [din^3][cin]            (forward A, wgrad A)
@@ -49,31 +50,35 @@ __device__ __forceinline__ int tap_k(int p, int t) { return p == 0 ? (t == 0 ? 1
 __device__ __forceinline__ int tap_off(int p, int t) { return t == 0 ? 0 : (p == 0 ? -1 : 1); }
 
 // Tensor-core tile product (warp-level mma.sync m16n8k8, TF32 operands, fp32 accumulate).  8 warps = 4 (rows) x 2 (cols):
-// warp (wm, wn) owns rows [16 wm, +16) x cols [32 wn, +32) of the 64 x 64 tile = 4 fragments of 16 x 8;
+// warp (wm, wn) owns rows [16 wm, +16) x cols [kTN/2 wn, +kTN/2) of the 64 x kTN tile = kTN/16 fragments of 16 x 8;
 // acc[f][i]: fragment f, i = 0..3 -> (row g + 8 (i >> 1), col 2 t + (i & 1)) with g = lane >> 2, t = lane & 3.
 // kX3 = true: every operand is split into two TF32 values (hi + lo) and the product is hi*hi + hi*lo + lo*hi ("3xTF32"):
 // fp32-level accuracy for the 1e-4 parity path; kX3 = false: plain TF32 (the bf16 path, like cuDNN's TF32 engines).
 // Operand tiles sit in shared memory in the layout their source is contiguous in, so every global -> shared copy is a
-// 16-byte cp.async: "row-major in k" tiles [64 rows][16 k] with a row stride of 20 floats, "k-major" tiles [16 k][64]
-// with a row stride of 72 floats - both strides make the fragment loads bank-conflict free.
+// 16-byte cp.async: "row-major in k" tiles [rows][16 k] with a row stride of 20 floats, "k-major" tiles [16 k][cols]
+// with a row stride of cols + 8 floats - both strides make the fragment loads bank-conflict free.
 constexpr int kStrideRK = kTileK + 4;      // 20
-constexpr int kStrideKM = kTile + 8;       // 72
+constexpr int kStrideKM = kTile + 8;       // 72 (a 32-column k-major tile uses 40)
 constexpr int kTileFloats = kTile * kStrideRK > kTileK * kStrideKM ? kTile * kStrideRK : kTileK * kStrideKM;   // 1280
 constexpr int kDecStages = 4;
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> TF32 operand bits.  sm_100a has no native cvt.rna.tf32.f32 (ptxas expands it into ~8 integer / compare
+// instructions per element, which made the tile product instruction-issue bound: 150 M warp instructions for the last
+// layer's forward, 2.8 % of them MMAs).  The tensor core reads only the upper 19 bits of a TF32 operand, so adding half
+// an ulp of the 10-bit mantissa to the bit pattern rounds to nearest (ties away from zero, like .rna) in one integer add.
+__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
+// the same value with the ignored bits cleared: what the tensor core multiplies with (needed to form the 3xTF32 residual)
+__device__ __forceinline__ uint32_t to_tf32_exact(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// A_RK / B_RK: the tile is row-major in k ([row][k], stride 20) instead of k-major ([k][row], stride 72)
-template <bool kX3, bool A_RK, bool B_RK>
-__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Bs, int warp, int lane, float (&acc)[4][4]) {
+// A_RK / B_RK: the tile is row-major in k ([row][k], stride 20) instead of k-major ([k][row], stride 72 / kTN + 8)
+template <bool kX3, bool A_RK, bool B_RK, int kTN>
+__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Bs, int warp, int lane,
+                                         float (&acc)[kTN / 16][4]) {
+  constexpr int kSB = kTN + 8, kWN = kTN / 2;
   const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int k8 = 0; k8 < kTileK; k8 += 8) {
@@ -88,21 +93,21 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ As, const flo
     uint32_t a_hi[4], a_lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      a_hi[i] = to_tf32(af[i]);
+      a_hi[i] = kX3 ? to_tf32_exact(af[i]) : to_tf32(af[i]);
       if (kX3) a_lo[i] = to_tf32(af[i] - __uint_as_float(a_hi[i]));
     }
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
+    for (int f = 0; f < kTN / 16; ++f) {
       float bf[2];
       if (B_RK) {
-        bf[0] = Bs[(wn * 32 + f * 8 + g) * kStrideRK + k8 + t]; bf[1] = Bs[(wn * 32 + f * 8 + g) * kStrideRK + k8 + t + 4];
+        bf[0] = Bs[(wn * kWN + f * 8 + g) * kStrideRK + k8 + t]; bf[1] = Bs[(wn * kWN + f * 8 + g) * kStrideRK + k8 + t + 4];
       } else {
-        bf[0] = Bs[(k8 + t) * kStrideKM + wn * 32 + f * 8 + g]; bf[1] = Bs[(k8 + t + 4) * kStrideKM + wn * 32 + f * 8 + g];
+        bf[0] = Bs[(k8 + t) * kSB + wn * kWN + f * 8 + g]; bf[1] = Bs[(k8 + t + 4) * kSB + wn * kWN + f * 8 + g];
       }
       uint32_t b_hi[2], b_lo[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        b_hi[i] = to_tf32(bf[i]);
+        b_hi[i] = kX3 ? to_tf32_exact(bf[i]) : to_tf32(bf[i]);
         if (kX3) b_lo[i] = to_tf32(bf[i] - __uint_as_float(b_hi[i]));
       }
       if (kX3) {
@@ -129,23 +134,30 @@ __device__ __forceinline__ void cp_async4x4(float* dst, const float* src, int n_
 // MODE 0: forward.  grid = (m_tiles * n_tiles, 8 parity classes, k_splits); GEMM rows m = input-grid voxel, cols = cout.
 // MODE 1: data gradient.  grid = (m_tiles * n_tiles, 1, k_splits); rows = input voxel i, cols = cin, K = (tap, cout).
 // MODE 2: weight gradient.  grid = (m_tiles * n_tiles, 64 taps, k_splits); rows = cin, cols = cout, K = input voxel.
-// Four-stage cp.async pipeline: the copies of tile k + 3 are issued before the MMAs of tile k.
-template <int MODE, bool kX3>
+// Tiles are 64 rows x kTN columns (kTN = 32 for the 25-channel output layer) x 16 k.  Four-stage cp.async pipeline: the
+// copies of tile k + 3 are issued before the MMAs of tile k.  The K axis of MODE 0 / 1 is (tap, channel) with the channel
+// count a multiple of 16, so a k-tile lies inside ONE tap: everything that depends on the tap (neighbour voxel, bounds
+// test, weight slice) is recomputed only when the tap advances and a step costs two pointer additions; volume sides are
+// powers of two (the decoder doubles from 1^3), so voxel <-> (z, y, x) is shifts and masks.
+template <int MODE, bool kX3, int kTN>
 __global__ void __launch_bounds__(256)
 deconv_gemm_kernel(const DeconvArgs g) {
   __shared__ __align__(16) float As[kDecStages][kTileFloats];
   __shared__ __align__(16) float Bs[kDecStages][kTileFloats];
   constexpr bool A_RK = MODE != 2, B_RK = MODE == 1;
+  constexpr int kSB = kTN + 8;                       // row stride of a k-major B tile
+  static_assert(MODE != 1 || kTN == 64, "the data gradient always has >= 64 columns (cin)");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int din = g.din, din3 = din * din * din, dout = 2 * din;
+  const int sh = g.log2_din, din = 1 << sh, dmask = din - 1, din3 = 1 << (3 * sh), dout = 2 * din;
   const int M = MODE == 2 ? g.cin : din3;
   const int N = MODE == 0 ? g.cout : (MODE == 1 ? g.cin : g.cout);
-  const int n_tiles = (N + kTile - 1) / kTile;
-  const int m0 = (int)(blockIdx.x / n_tiles) * kTile, n0 = (int)(blockIdx.x % n_tiles) * kTile;
+  const int n_tiles = (N + kTN - 1) / kTN;
+  const int m0 = (int)(blockIdx.x / n_tiles) * kTile, n0 = (int)(blockIdx.x % n_tiles) * kTN;
   // K geometry
   const int cout_pad = (g.cout + kTileK - 1) / kTileK * kTileK;          // dgrad: K per tap, zero padded
   const int n_taps = MODE == 0 ? (din == 1 ? 1 : 8) : (din == 1 ? 8 : 64);
-  const int k_total = MODE == 0 ? n_taps * g.cin : (MODE == 1 ? n_taps * cout_pad : din3);
+  const int kpt = MODE == 0 ? g.cin : cout_pad;                          // K per tap (MODE 0 / 1)
+  const int k_total = MODE == 2 ? din3 : n_taps * kpt;
   int k_begin = 0, k_end = k_total;
   if (g.k_splits > 1) {
     k_begin = (int)blockIdx.z * g.k_per_split;
@@ -153,114 +165,144 @@ deconv_gemm_kernel(const DeconvArgs g) {
   }
   const int pz = (blockIdx.y >> 2) & 1, py = (blockIdx.y >> 1) & 1, px = blockIdx.y & 1;      // MODE 0: parity class
   const int wz = blockIdx.y >> 4, wy = (blockIdx.y >> 2) & 3, wx = blockIdx.y & 3;           // MODE 2: tap
-  // copy roles: row-major-in-k tiles: thread = (row tid >> 2, k quad (tid & 3) * 4); k-major tiles: (k tid >> 4, quad (tid & 15) * 4)
+  // copy roles.  row-major-in-k tiles: thread = (row tid >> 2, k quad (tid & 3) * 4); k-major A tile (64 columns):
+  // (k tid >> 4, quad (tid & 15) * 4); k-major B tile: the same for 64 columns, (k tid >> 3, quad (tid & 7) * 4) of the
+  // first 128 threads for 32 columns
   const int r4 = tid >> 2, kq = (tid & 3) * 4, kr = tid >> 4, q16 = (tid & 15) * 4;
-  int vz = 0, vy = 0, vx = 0;                       // MODE 0 / 1: voxel of this thread's A row
-  if (MODE != 2) {
-    const int m = m0 + r4;
-    vz = m / (din * din); vy = (m / din) % din; vx = m % din;
-  }
+  const int krb = kTN == 64 ? kr : tid >> 3, qb = kTN == 64 ? q16 : (tid & 7) * 4;
+  const bool b_thread = kTN == 64 || tid < 128;
   const bool w_rows_aligned = (g.cout & 3) == 0;
+  const int vm = m0 + r4;                            // MODE 0 / 1: voxel of this thread's A row
+  const int vz = vm >> (2 * sh), vy = (vm >> sh) & dmask, vx = vm & dmask;
+  const bool row_ok = vm < din3;
 
-  auto issue = [&](int k0, int stage) {
+  // issue cursor (uniform over the block): tap and channel offset of the next k-tile to copy
+  int tap_i = 0, c_i = 0, k_i = k_begin;
+  if (MODE != 2) { tap_i = k_begin / kpt; c_i = k_begin - tap_i * kpt; }
+  const float* a_tap = nullptr;                      // A row of this thread for the current tap (+ its k quad)
+  const float* b_tap = nullptr;
+  bool a_ok = false;
+  int b_cols = 0;                                    // MODE 0 / 2: valid columns of this thread's B quad
+  if (MODE != 1) b_cols = b_thread ? max(0, min(4, N - (n0 + qb))) : 0;
+  const bool b_row_ok = MODE == 1 && n0 + r4 < N;
+  auto set_tap = [&](int tap) {
+    if (MODE == 0) {
+      const int iz = vz + tap_off(pz, (tap >> 2) & 1), iy = vy + tap_off(py, (tap >> 1) & 1), ix = vx + tap_off(px, tap & 1);
+      a_ok = row_ok && (unsigned)iz < (unsigned)din && (unsigned)iy < (unsigned)din && (unsigned)ix < (unsigned)din;
+      a_tap = g.in + (size_t)((((iz << sh) + iy) << sh) + ix) * g.cin + kq;
+      const int kidx = (tap_k(pz, (tap >> 2) & 1) * 4 + tap_k(py, (tap >> 1) & 1)) * 4 + tap_k(px, tap & 1);
+      b_tap = g.w + ((size_t)krb * 64 + kidx) * g.cout + n0 + qb;
+    } else if (MODE == 1) {
+      // tap list: all 64 taps, or (din == 1) the 8 taps with k in {1, 2} per axis - the only ones that reach the 2^3 output
+      const int kz = din == 1 ? 1 + ((tap >> 2) & 1) : tap >> 4, ky = din == 1 ? 1 + ((tap >> 1) & 1) : (tap >> 2) & 3,
+                kx = din == 1 ? 1 + (tap & 1) : tap & 3;
+      const int oz = 2 * vz - 1 + kz, oy = 2 * vy - 1 + ky, ox = 2 * vx - 1 + kx;
+      a_ok = row_ok && (unsigned)oz < (unsigned)dout && (unsigned)oy < (unsigned)dout && (unsigned)ox < (unsigned)dout;
+      a_tap = g.outside + (size_t)((((oz << (sh + 1)) + oy) << (sh + 1)) + ox) * g.ld_out + kq;
+      b_tap = g.w + ((size_t)(n0 + r4) * 64 + (kz * 4 + ky) * 4 + kx) * g.cout + kq;
+    }
+  };
+  if (MODE != 2) set_tap(tap_i);
+
+  auto issue = [&](int stage) {
     float* as = As[stage];
     float* bs = Bs[stage];
     if (MODE == 0) {
-      // A(m, kk) = in[i(m, tap)][ci .. ci + 3]
-      const int kk = k0 + kq, tap = kk / g.cin, ci = kk - tap * g.cin;
-      const int iz = vz + tap_off(pz, (tap >> 2) & 1), iy = vy + tap_off(py, (tap >> 1) & 1), ix = vx + tap_off(px, tap & 1);
-      const bool ok = m0 + r4 < din3 && kk < k_end && iz >= 0 && iz < din && iy >= 0 && iy < din && ix >= 0 && ix < din;
-      cp_async16(as + r4 * kStrideRK + kq, ok ? g.in + ((size_t)(iz * din + iy) * din + ix) * g.cin + ci : g.in, ok);
-      // B(kk, n) = w[ci][k(p, tap)][n .. n + 3]
-      const int kb = k0 + kr, tapb = kb / g.cin, cib = kb - tapb * g.cin;
-      const int kidx = (tap_k(pz, (tapb >> 2) & 1) * 4 + tap_k(py, (tapb >> 1) & 1)) * 4 + tap_k(px, tapb & 1);
-      const float* src = g.w + ((size_t)cib * 64 + kidx) * g.cout + n0 + q16;
-      const int nv = kb < k_end ? max(0, min(4, N - (n0 + q16))) : 0;
-      if (w_rows_aligned) cp_async16(bs + kr * kStrideKM + q16, nv == 4 ? src : g.w, nv == 4);
-      else cp_async4x4(bs + kr * kStrideKM + q16, nv > 0 ? src : g.w, nv);
+      // A(m, kk) = in[i(m, tap)][ci .. ci + 3];  B(kk, n) = w[ci][k(p, tap)][n .. n + 3]
+      cp_async16(as + r4 * kStrideRK + kq, a_ok ? a_tap + c_i : g.in, a_ok);
+      if (b_thread) {
+        const float* src = b_tap + (size_t)c_i * 64 * g.cout;
+        if (w_rows_aligned) cp_async16(bs + krb * kSB + qb, b_cols == 4 ? src : g.w, b_cols == 4);
+        else cp_async4x4(bs + krb * kSB + qb, b_cols > 0 ? src : g.w, b_cols);
+      }
     } else if (MODE == 1) {
       // A(i, kk) = outside[o(i, tap)][co .. co + 3], kk = tap * cout_pad + co;  B(ci, kk) = w[ci][tap][co .. co + 3]
-      const int kk = k0 + kq, tl = kk / cout_pad, co = kk - tl * cout_pad;
-      // tap list: all 64 taps, or (din == 1) the 8 taps with k in {1, 2} per axis - the only ones that reach the 2^3 output
-      const int kz = din == 1 ? 1 + ((tl >> 2) & 1) : tl >> 4, ky = din == 1 ? 1 + ((tl >> 1) & 1) : (tl >> 2) & 3,
-                kx = din == 1 ? 1 + (tl & 1) : tl & 3;
-      const int oz = 2 * vz - 1 + kz, oy = 2 * vy - 1 + ky, ox = 2 * vx - 1 + kx;
-      const bool ok = kk < k_end && m0 + r4 < din3 && oz >= 0 && oz < dout && oy >= 0 && oy < dout && ox >= 0 && ox < dout;
-      const float* asrc = g.outside + ((size_t)(oz * dout + oy) * dout + ox) * g.ld_out + co;
       // ld_out is a multiple of 4 and columns [cout, ld_out) of the gradient buffers are zero
-      const int av = ok ? max(0, min(4, g.ld_out - co)) : 0;
-      cp_async16(as + r4 * kStrideRK + kq, av == 4 ? asrc : g.outside, av == 4);
-      const int ci = n0 + r4;
-      const int bv = (kk < k_end && ci < N) ? max(0, min(4, g.cout - co)) : 0;
-      const float* bsrc = g.w + ((size_t)ci * 64 + (kz * 4 + ky) * 4 + kx) * g.cout + co;
-      if (w_rows_aligned) cp_async16(bs + r4 * kStrideRK + kq, bv == 4 ? bsrc : g.w, bv == 4);
-      else cp_async4x4(bs + r4 * kStrideRK + kq, bv > 0 ? bsrc : g.w, bv);
+      const int co = c_i + kq;
+      const bool av = a_ok && co + 4 <= g.ld_out;
+      cp_async16(as + r4 * kStrideRK + kq, av ? a_tap + c_i : g.outside, av);
+      const int bv = b_row_ok ? max(0, min(4, g.cout - co)) : 0;
+      if (w_rows_aligned) cp_async16(bs + r4 * kStrideRK + kq, bv == 4 ? b_tap + c_i : g.w, bv == 4);
+      else cp_async4x4(bs + r4 * kStrideRK + kq, bv > 0 ? b_tap + c_i : g.w, bv);
     } else {
       // A(ci, i) = in[i][ci .. ci + 3];  B(i, co) = outside[o(i, tap)][co .. co + 3]
-      const int i = k0 + kr;
-      const bool aok = i < k_end && m0 + q16 + 4 <= M;
-      cp_async16(as + kr * kStrideKM + q16, aok ? g.in + (size_t)i * g.cin + m0 + q16 : g.in, aok);
-      const int iz = i / (din * din), iy = (i / din) % din, ix = i % din;
-      const int oz = 2 * iz - 1 + wz, oy = 2 * iy - 1 + wy, ox = 2 * ix - 1 + wx;
-      const bool bok = i < k_end && oz >= 0 && oz < dout && oy >= 0 && oy < dout && ox >= 0 && ox < dout && n0 + q16 + 4 <= g.ld_out;
-      cp_async16(bs + kr * kStrideKM + q16, bok ? g.outside + ((size_t)(oz * dout + oy) * dout + ox) * g.ld_out + n0 + q16 : g.outside, bok);
+      const int ia = k_i + kr;
+      const bool aok = ia < k_end && m0 + q16 + 4 <= M;
+      cp_async16(as + kr * kStrideKM + q16, aok ? g.in + (size_t)ia * g.cin + m0 + q16 : g.in, aok);
+      if (b_thread) {
+        const int i = k_i + krb;
+        const int oz = 2 * (i >> (2 * sh)) - 1 + wz, oy = 2 * ((i >> sh) & dmask) - 1 + wy, ox = 2 * (i & dmask) - 1 + wx;
+        const bool bok = i < k_end && (unsigned)oz < (unsigned)dout && (unsigned)oy < (unsigned)dout && (unsigned)ox < (unsigned)dout &&
+                         n0 + qb + 4 <= g.ld_out;
+        cp_async16(bs + krb * kSB + qb, bok ? g.outside + (size_t)((((oz << (sh + 1)) + oy) << (sh + 1)) + ox) * g.ld_out + n0 + qb : g.outside,
+                   bok);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    k_i += kTileK;
+    if (MODE != 2) {
+      c_i += kTileK;
+      if (c_i == kpt) {
+        c_i = 0;
+        if (++tap_i < n_taps) set_tap(tap_i);
+      }
+    }
   };
 
-  float acc[4][4];
+  float acc[kTN / 16][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kTN / 16; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int n_steps = (k_end - k_begin + kTileK - 1) / kTileK;
 #pragma unroll
   for (int s = 0; s < kDecStages - 1; ++s) {
-    if (s < n_steps) issue(k_begin + s * kTileK, s);
+    if (s < n_steps) issue(s);
     else asm volatile("cp.async.commit_group;" ::: "memory");
   }
+#pragma unroll 1
   for (int step = 0; step < n_steps; ++step) {
     asm volatile("cp.async.wait_group %0;" ::"n"(kDecStages - 2) : "memory");
     __syncthreads();                                   // tile `step` has landed for every thread; tile step - 1 is no longer read
     const int nxt = step + kDecStages - 1;
-    if (nxt < n_steps) issue(k_begin + nxt * kTileK, nxt % kDecStages);
+    if (nxt < n_steps) issue(nxt % kDecStages);
     else asm volatile("cp.async.commit_group;" ::: "memory");
     const float* as = As[step % kDecStages];
     const float* bs = Bs[step % kDecStages];
     if (kX3) {
       // tensor-core accumulation truncates: keep its error inside one 16-long partial sum and add the tiles up in
       // round-to-nearest fp32
-      float part[4][4];
+      float part[kTN / 16][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kTN / 16; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
-      tile_mma<true, A_RK, B_RK>(as, bs, warp, lane, part);
+      tile_mma<true, A_RK, B_RK, kTN>(as, bs, warp, lane, part);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kTN / 16; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     } else {
-      tile_mma<false, A_RK, B_RK>(as, bs, warp, lane, acc);
+      tile_mma<false, A_RK, B_RK, kTN>(as, bs, warp, lane, acc);
     }
   }
 
   // ---- epilogue: fragment f, element e of this lane -> (row, col) of the tile
   const int wm = warp >> 1, wn = warp & 1, fg = lane >> 2, ft = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {                       // i = fragment
+  for (int i = 0; i < kTN / 16; ++i) {                // i = fragment
 #pragma unroll
     for (int j = 0; j < 4; ++j) {                     // j = element of the fragment
       const int m = m0 + wm * 16 + fg + 8 * (j >> 1);
-      const int n = n0 + wn * 32 + i * 8 + 2 * ft + (j & 1);
+      const int n = n0 + wn * (kTN / 2) + i * 8 + 2 * ft + (j & 1);
       if (m >= M || n >= N) continue;
       float v = acc[i][j];
       if (MODE == 0) {
-        const int mz = m / (din * din), my = (m / din) % din, mx = m % din;
-        const size_t o = ((size_t)((2 * mz + pz) * dout + 2 * my + py)) * dout + 2 * mx + px;
+        const int mz = m >> (2 * sh), my = (m >> sh) & dmask, mx = m & dmask;
+        const size_t o = (size_t)(((((2 * mz + pz) << (sh + 1)) + 2 * my + py) << (sh + 1)) + 2 * mx + px);
         if (g.k_splits > 1) {
-          g.dst[((size_t)blockIdx.z * dout * dout * dout + o) * g.cout + n] = v;
+          g.dst[((size_t)blockIdx.z * 8 * din3 + o) * g.cout + n] = v;
         } else {
           v += __ldg(g.bias + n);
           if (g.leaky) v = v > 0.f ? v : kLeaky * v;
@@ -280,6 +322,20 @@ deconv_gemm_kernel(const DeconvArgs g) {
     }
   }
 }
+
+template <int MODE>
+static int launch_deconv_gemm(const DeconvArgs& g, dim3 grid, bool x3, int tn, cudaStream_t st, const char* what) {
+  if (MODE != 1 && tn == 32) {
+    if (x3) deconv_gemm_kernel<MODE == 1 ? 0 : MODE, true, 32><<<grid, 256, 0, st>>>(g);
+    else deconv_gemm_kernel<MODE == 1 ? 0 : MODE, false, 32><<<grid, 256, 0, st>>>(g);
+  } else {
+    if (x3) deconv_gemm_kernel<MODE, true, 64><<<grid, 256, 0, st>>>(g);
+    else deconv_gemm_kernel<MODE, false, 64><<<grid, 256, 0, st>>>(g);
+  }
+  return launched(what);
+}
+// column tile of a GEMM with `n` columns
+static int tile_n(int n) { return n <= 32 ? 32 : 64; }
 
 // dst[i] = sum_s partial[s][i] (weight gradients of the layers whose K = voxel count was split)
 __global__ void sum_partials_kernel(const float4* __restrict__ partial, int splits, int64_t n4, float4* __restrict__ dst) {
@@ -331,73 +387,120 @@ __global__ void linear_wgrad_kernel(int n_out, int n_in, const float* __restrict
   d_w[idx] = dpre[j] * __ldg(e + i);
   if (i == 0) d_b[j] = dpre[j];
 }
-// d_e[i] = sum_j W[j][i] dpre[j]: block = 32 inputs x 8 slices of j, slices added in a fixed order
-__global__ void __launch_bounds__(256) linear_dgrad_kernel(int n_out, int n_in, const float* __restrict__ w, const float* __restrict__ dpre,
-                                                           float* __restrict__ d_e) {
-  __shared__ float red[8][33];
+// d_e[i] = sum_j W[j][i] dpre[j]: block = 32 inputs x 32 slices of j (coalesced rows of W), slices added in a fixed order
+__global__ void __launch_bounds__(1024) linear_dgrad_kernel(int n_out, int n_in, const float* __restrict__ w, const float* __restrict__ dpre,
+                                                            float* __restrict__ d_e) {
+  __shared__ float red[32][33];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
-  if (i < n_in)
-    for (int j = sl; j < n_out; j += 8) s = fmaf(__ldg(w + (size_t)j * n_in + i), dpre[j], s);
+  if (i < n_in) {
+#pragma unroll 4
+    for (int j = sl; j < n_out; j += 32) s = fmaf(__ldg(w + (size_t)j * n_in + i), dpre[j], s);
+  }
   red[sl][lane] = s;
   __syncthreads();
   if (sl == 0 && i < n_in) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    for (int k = 0; k < 32; ++k) t += red[k][lane];
     d_e[i] = t;
   }
 }
-// d_b[c] = sum_rows g[row][c]: one block of 256 threads per column, fixed-order tree
-__global__ void __launch_bounds__(256) column_sum_kernel(int64_t rows, int ld, const float* __restrict__ g, float* __restrict__ out) {
-  __shared__ float red[256];
-  const int c = blockIdx.x;
-  float s = 0.f;
-  for (int64_t r = threadIdx.x; r < rows; r += 256) s += g[r * ld + c];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
+// d_b[c] = sum_rows g[row][c] for c < n_cols.  grid = (row slabs, chunks of 128 columns).  Block (b, y) sums its slab of
+// rows with coalesced row reads (thread = column lane x row lane), writes partial[b][.]; the block of a chunk that finishes
+// last adds the partials in slab order: no floating-point atomics, bit-reproducible.  `counter[y]` must be zero at launch
+// (cleared by the caller once per backward pass).
+constexpr int kColSumMaxLd = 128;          // columns per chunk
+constexpr int kColSumMaxChunks = 4;        // => at most 512 channels on the output side of a convolution
+__global__ void __launch_bounds__(256) column_sum_kernel(int64_t rows, int ld, int n_cols, const float* __restrict__ g,
+                                                         float* __restrict__ partial, unsigned int* __restrict__ counter,
+                                                         float* __restrict__ out) {
+  __shared__ float red[8][kColSumMaxLd];
+  __shared__ bool is_last;
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5, n_slabs = gridDim.x, c0 = blockIdx.y * kColSumMaxLd;
+  const int64_t r0 = rows * blockIdx.x / n_slabs, r1 = rows * (blockIdx.x + 1) / n_slabs;
+  float s[kColSumMaxLd / 32] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = r0 + rl; r < r1; r += 8) {
+#pragma unroll
+    for (int q = 0; q < kColSumMaxLd / 32; ++q)
+      if (c0 + cl + 32 * q < ld) s[q] += g[r * ld + c0 + cl + 32 * q];
   }
-  if (threadIdx.x == 0) out[c] = red[0];
+#pragma unroll
+  for (int q = 0; q < kColSumMaxLd / 32; ++q) red[rl][cl + 32 * q] = s[q];
+  __syncthreads();
+  const int c = c0 + (int)threadIdx.x;
+  if (threadIdx.x < kColSumMaxLd && c < ld) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    partial[(size_t)blockIdx.x * ld + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter + blockIdx.y, 1u) == (unsigned)(n_slabs - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < kColSumMaxLd && c < n_cols) {
+      float t = 0.f;
+      for (int b = 0; b < n_slabs; ++b) t += __ldcg(partial + (size_t)b * ld + c);
+      out[c] = t;
+    }
+  }
 }
 
-// vol[c][voxel] = softmax_c(logits[voxel][c] + log prior[c][voxel]); one thread per voxel
-__global__ void softmax_prior_fwd_kernel(int n_vox, int C, int ld, const float* __restrict__ logits, const float* __restrict__ prior,
-                                         float* __restrict__ vol) {
+// vol[c][voxel] = softmax_c(logits[voxel][c] + log prior[c][voxel]); one thread per voxel, logits rows of kLdLogits = 32
+// floats read as 8 x 16 bytes, everything in registers
+constexpr int kLdLogits = 32;
+__global__ void __launch_bounds__(128) softmax_prior_fwd_kernel(int n_vox, int C, const float* __restrict__ logits,
+                                                                const float* __restrict__ prior, float* __restrict__ vol) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vox) return;
-  float x[32];
+  float x[kLdLogits];
+  const float4* row = reinterpret_cast<const float4*>(logits + (size_t)v * kLdLogits);
+#pragma unroll
+  for (int q = 0; q < kLdLogits / 4; ++q) {
+    const float4 t = row[q];
+    x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+  }
   float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < C; ++c) {
-    x[c] = logits[(size_t)v * ld + c] + logf(prior[(size_t)c * n_vox + v]);
-    mx = fmaxf(mx, x[c]);
-  }
+#pragma unroll
+  for (int c = 0; c < kLdLogits; ++c)
+    if (c < C) {
+      x[c] += logf(prior[(size_t)c * n_vox + v]);
+      mx = fmaxf(mx, x[c]);
+    }
   float s = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < C; ++c) { x[c] = expf(x[c] - mx); s += x[c]; }
+#pragma unroll
+  for (int c = 0; c < kLdLogits; ++c)
+    if (c < C) { x[c] = expf(x[c] - mx); s += x[c]; }
   const float inv = 1.0f / s;
-#pragma unroll 1
-  for (int c = 0; c < C; ++c) vol[(size_t)c * n_vox + v] = x[c] * inv;
+#pragma unroll
+  for (int c = 0; c < kLdLogits; ++c)
+    if (c < C) vol[(size_t)c * n_vox + v] = x[c] * inv;
 }
-// d_logits[voxel][c] = y_c (g_c - sum_k g_k y_k)
-__global__ void softmax_prior_bwd_kernel(int n_vox, int C, int ld, const float* __restrict__ vol, const float* __restrict__ d_vol,
-                                         float* __restrict__ d_logits) {
+// d_logits[voxel][c] = y_c (g_c - sum_k g_k y_k); columns [C, 32) are written as zeros
+__global__ void __launch_bounds__(128) softmax_prior_bwd_kernel(int n_vox, int C, const float* __restrict__ vol,
+                                                                const float* __restrict__ d_vol, float* __restrict__ d_logits) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vox) return;
+  float y[kLdLogits], gy[kLdLogits];
   float dot = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < C; ++c) dot = fmaf(d_vol[(size_t)c * n_vox + v], vol[(size_t)c * n_vox + v], dot);
-#pragma unroll 1
-  for (int c = 0; c < C; ++c) {
-    const float y = vol[(size_t)c * n_vox + v];
-    d_logits[(size_t)v * ld + c] = y * (d_vol[(size_t)c * n_vox + v] - dot);
+#pragma unroll
+  for (int c = 0; c < kLdLogits; ++c) {
+    y[c] = 0.f; gy[c] = 0.f;
+    if (c < C) {
+      y[c] = vol[(size_t)c * n_vox + v];
+      gy[c] = d_vol[(size_t)c * n_vox + v];
+      dot = fmaf(gy[c], y[c], dot);
+    }
   }
-#pragma unroll 1
-  for (int c = C; c < ld; ++c) d_logits[(size_t)v * ld + c] = 0.f;
+  float4* row = reinterpret_cast<float4*>(d_logits + (size_t)v * kLdLogits);
+#pragma unroll
+  for (int q = 0; q < kLdLogits / 4; ++q)
+    row[q] = make_float4(y[4 * q] * (gy[4 * q] - dot), y[4 * q + 1] * (gy[4 * q + 1] - dot), y[4 * q + 2] * (gy[4 * q + 2] - dot),
+                         y[4 * q + 3] * (gy[4 * q + 3] - dot));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -408,10 +511,11 @@ struct DecPlan {
   int ld_logits;
   int fwd_splits[kDecMaxConv], dgrad_splits[kDecMaxConv], wgrad_splits[kDecMaxConv];   // K splits of the three GEMMs per layer
   size_t off_h, off_act[kDecMaxConv + 1], off_logits, ws_floats;          // saved for backward
-  size_t off_partial, off_g[2], off_dlogits, scratch_floats;
+  size_t off_partial, off_g[2], off_dlogits, off_colsum, off_counters, scratch_floats;
 };
 
 // K-splits for a GEMM with `rows` rows: the low layers are weight-bandwidth bound and need many CTAs
+constexpr int kColSumSlabs = 64;
 static int pick_splits(int64_t tiles, int k_total) {
   int splits = 1;
   while (tiles * splits < 592 && splits < 16 && k_total / (splits * 2) >= 64) splits *= 2;
@@ -426,10 +530,12 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
   for (int l = 0; l <= n_conv; ++l) {
     p.ch[l] = channels[l];
     if (channels[l] <= 0 || (l < n_conv && (channels[l] % 16))) return fail_arg("hn_vol_decoder: channel counts must be multiples of 16 (except the output)");
+    if (l > 0 && channels[l] > kColSumMaxLd * kColSumMaxChunks)
+      return fail_arg("hn_vol_decoder: at most %d output channels per convolution", kColSumMaxLd * kColSumMaxChunks);
   }
   if (p.ch[n_conv] > 32) return fail_arg("hn_vol_decoder: at most 32 output channels");
   for (int l = 0; l < n_conv; ++l) p.din[l] = 1 << l;
-  p.ld_logits = 32;
+  p.ld_logits = kLdLogits;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
   p.off_h = 0;
@@ -442,11 +548,11 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
   size_t part = 0, gmax = 0;
   for (int l = 0; l < n_conv; ++l) {
     const size_t d3 = (size_t)p.din[l] * p.din[l] * p.din[l];
-    const int64_t ft = (int64_t)ceil_div<int64_t>((int64_t)d3, kTile) * ceil_div(p.ch[l + 1], kTile) * 8;
+    const int64_t ft = (int64_t)ceil_div<int64_t>((int64_t)d3, kTile) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 8;
     p.fwd_splits[l] = pick_splits(ft, (p.din[l] == 1 ? 1 : 8) * p.ch[l]);
     const int64_t dt = (int64_t)ceil_div<int64_t>((int64_t)d3, kTile) * ceil_div(p.ch[l], kTile);
     p.dgrad_splits[l] = pick_splits(dt, (p.din[l] == 1 ? 8 : 64) * (ceil_div(p.ch[l + 1], kTileK) * kTileK));
-    const int64_t wt = (int64_t)ceil_div(p.ch[l], kTile) * ceil_div(p.ch[l + 1], kTile) * 64;
+    const int64_t wt = (int64_t)ceil_div(p.ch[l], kTile) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 64;
     p.wgrad_splits[l] = pick_splits(wt, (int)d3);
     if (p.wgrad_splits[l] > 1) part = std::max(part, (size_t)p.wgrad_splits[l] * p.ch[l] * 64 * p.ch[l + 1]);
     if (p.fwd_splits[l] > 1) part = std::max(part, (size_t)p.fwd_splits[l] * 8 * d3 * p.ch[l + 1]);
@@ -458,6 +564,8 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
   p.off_g[0] = take(gmax);
   p.off_g[1] = take(gmax);
   p.off_dlogits = take(n_vox * p.ld_logits);
+  p.off_colsum = take((size_t)kColSumSlabs * kColSumMaxLd * kColSumMaxChunks);
+  p.off_counters = take(kDecMaxConv * kColSumMaxChunks);
   p.scratch_floats = off;
   return 0;
 }
@@ -467,17 +575,16 @@ static int run_forward_layer(const DecPlan& p, int l, const float* in, const flo
   DeconvArgs g;
   memset(&g, 0, sizeof(g));
   const int din = p.din[l], d3 = din * din * din;
-  g.din = din; g.cin = p.ch[l]; g.cout = p.ch[l + 1]; g.ld_out = ld_out; g.in = in; g.w = w; g.bias = b; g.leaky = leaky ? 1 : 0;
+  g.din = din; g.log2_din = l; g.cin = p.ch[l]; g.cout = p.ch[l + 1]; g.ld_out = ld_out; g.in = in; g.w = w; g.bias = b; g.leaky = leaky ? 1 : 0;
   const int k_total = (din == 1 ? 1 : 8) * g.cin;
-  const int64_t tiles = (int64_t)ceil_div(d3, kTile) * ceil_div(g.cout, kTile);
+  const int tn = tile_n(g.cout);
+  const int64_t tiles = (int64_t)ceil_div(d3, kTile) * ceil_div(g.cout, tn);
   const int splits = p.fwd_splits[l];
   g.k_splits = splits;
   g.k_per_split = ceil_div(ceil_div(k_total, splits), kTileK) * kTileK;
   g.dst = splits > 1 ? partial : out;
   dim3 grid((unsigned)tiles, 8, (unsigned)splits);
-  if (x3) deconv_gemm_kernel<0, true><<<grid, 256, 0, st>>>(g);
-  else deconv_gemm_kernel<0, false><<<grid, 256, 0, st>>>(g);
-  HN_TRY(launched("hn_vol_decoder_fwd/deconv"));
+  HN_TRY(launch_deconv_gemm<0>(g, grid, x3, tn, st, "hn_vol_decoder_fwd/deconv"));
   if (splits > 1) {
     const int64_t rows = (int64_t)8 * d3;
     deconv_finish_kernel<<<(unsigned)ceil_div<int64_t>(rows * g.cout, 256), 256, 0, st>>>(partial, splits, rows, g.cout, ld_out, b,
@@ -528,7 +635,7 @@ int hn_vol_decoder_fwd(int embed, int hidden, int n_conv, const int* channels, c
                              sc + p.off_partial, precision == HN_PRECISION_FP32, st));
   }
   const int side = 2 * p.din[n_conv - 1], n_vox = side * side * side;
-  softmax_prior_fwd_kernel<<<ceil_div(n_vox, 128), 128, 0, st>>>(n_vox, p.ch[n_conv], p.ld_logits, ws + p.off_logits, prior, vol);
+  softmax_prior_fwd_kernel<<<ceil_div(n_vox, 128), 128, 0, st>>>(n_vox, p.ch[n_conv], ws + p.off_logits, prior, vol);
   return launched("hn_vol_decoder_fwd/softmax");
 }
 
@@ -552,26 +659,29 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
   const int side = 2 * p.din[n_conv - 1], n_vox = side * side * side;
   float* g_out = sc + p.off_dlogits;                       // gradient of the pre-activation on the output side of layer l
   int ld_g = p.ld_logits;
-  softmax_prior_bwd_kernel<<<ceil_div(n_vox, 128), 128, 0, st>>>(n_vox, p.ch[n_conv], p.ld_logits, vol, d_vol, g_out);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(sc + p.off_counters);
+  HN_TRY(check_cuda(cudaMemsetAsync(counters, 0, kDecMaxConv * kColSumMaxChunks * sizeof(unsigned int), st), "hn_vol_decoder_bwd/memset"));
+  softmax_prior_bwd_kernel<<<ceil_div(n_vox, 128), 128, 0, st>>>(n_vox, p.ch[n_conv], vol, d_vol, g_out);
   HN_TRY(launched("hn_vol_decoder_bwd/softmax"));
   for (int l = n_conv - 1; l >= 0; --l) {
     const int din = p.din[l], d3 = din * din * din, cin = p.ch[l], cout = p.ch[l + 1];
     const int64_t rows_out = (int64_t)8 * d3;
     // bias gradient
-    column_sum_kernel<<<cout, 256, 0, st>>>(rows_out, ld_g, g_out, d_conv_b[l]);
+    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(kColSumSlabs, rows_out / 64));
+    column_sum_kernel<<<dim3((unsigned)slabs, (unsigned)ceil_div(ld_g, kColSumMaxLd)), 256, 0, st>>>(rows_out, ld_g, cout, g_out, sc + p.off_colsum,
+                                                                                                  counters + l * kColSumMaxChunks, d_conv_b[l]);
     HN_TRY(launched("hn_vol_decoder_bwd/bias"));
     // weight gradient: one small GEMM per tap, written in the parameter's [cin][64][cout] layout
     DeconvArgs g;
     memset(&g, 0, sizeof(g));
-    g.din = din; g.cin = cin; g.cout = cout; g.ld_out = ld_g; g.in = ws + p.off_act[l]; g.outside = g_out; g.dst = d_conv_w[l];
+    g.din = din; g.log2_din = l; g.cin = cin; g.cout = cout; g.ld_out = ld_g; g.in = ws + p.off_act[l]; g.outside = g_out; g.dst = d_conv_w[l];
     const int wsp = p.wgrad_splits[l];
     g.k_splits = wsp;
     g.k_per_split = ceil_div(ceil_div(d3, wsp), kTileK) * kTileK;
     if (wsp > 1) g.dst = sc + p.off_partial;
-    dim3 wgrid((unsigned)(ceil_div(cin, kTile) * ceil_div(cout, kTile)), 64, (unsigned)wsp);
-    if (x3) deconv_gemm_kernel<2, true><<<wgrid, 256, 0, st>>>(g);
-    else deconv_gemm_kernel<2, false><<<wgrid, 256, 0, st>>>(g);
-    HN_TRY(launched("hn_vol_decoder_bwd/wgrad"));
+    const int tn = tile_n(cout);
+    dim3 wgrid((unsigned)(ceil_div(cin, kTile) * ceil_div(cout, tn)), 64, (unsigned)wsp);
+    HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, st, "hn_vol_decoder_bwd/wgrad"));
     if (wsp > 1) {
       const int64_t n4 = (int64_t)cin * 64 * cout / 4;
       sum_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sc + p.off_partial), wsp, n4,
@@ -588,9 +698,7 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     g.k_per_split = ceil_div(ceil_div(k_total, splits), kTileK) * kTileK;
     g.dst = splits > 1 ? sc + p.off_partial : g_in;
     dim3 dgrid((unsigned)tiles, 1, (unsigned)splits);
-    if (x3) deconv_gemm_kernel<1, true><<<dgrid, 256, 0, st>>>(g);
-    else deconv_gemm_kernel<1, false><<<dgrid, 256, 0, st>>>(g);
-    HN_TRY(launched("hn_vol_decoder_bwd/dgrad"));
+    HN_TRY(launch_deconv_gemm<1>(g, dgrid, x3, 64, st, "hn_vol_decoder_bwd/dgrad"));
     if (splits > 1) {
       deconv_finish_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)d3 * cin, 256), 256, 0, st>>>(sc + p.off_partial, splits, d3, cin, cin, nullptr, 0,
                                                                                           ws + p.off_act[l], g_in);
@@ -602,7 +710,7 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
   // linear layer: g_out = d(pre-activation of h) (hidden)
   linear_wgrad_kernel<<<ceil_div(hidden * embed, 256), 256, 0, st>>>(hidden, embed, g_out, embedding, d_lin_w, d_lin_b);
   HN_TRY(launched("hn_vol_decoder_bwd/linear wgrad"));
-  linear_dgrad_kernel<<<ceil_div(embed, 32), 256, 0, st>>>(hidden, embed, lin_w, g_out, d_embedding);
+  linear_dgrad_kernel<<<ceil_div(embed, 32), 1024, 0, st>>>(hidden, embed, lin_w, g_out, d_embedding);
   return launched("hn_vol_decoder_bwd/linear dgrad");
 }
 

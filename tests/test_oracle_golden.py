@@ -248,7 +248,7 @@ def test_train_step_cfg2_p20_oracle_and_lpips_against_reference():
     loss = 0.2 * mse + 1.0 * lpips
     assert abs(float(loss) - st['loss']) <= 1e-5 * st['loss']
     loss.backward()
-    rows = sf.compare_grads(st, {k: v.grad for k, v in sd.items()}, 2e-3, pose_tol=1e-2, label='oracle p20')
+    rows = sf.compare_grads(st, {k: v.grad for k, v in sd.items()}, 2e-3, pose_tol=1e-2, label='oracle p20', f64_tag='p20')
     worst = max(rows, key=lambda r: r[1])
     print(f'[parity] oracle vs reference train step p20: loss {float(loss):.6f} vs {st["loss"]:.6f}, '
           f'worst gradient rel L2 {worst[1]:.2e} ({worst[0]})')
