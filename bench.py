@@ -408,7 +408,9 @@ def main():
     cfg.b200.heavy_outputs = False
     cfg.N_samples = N_SAMPLES
     if os.environ.get('HN_DECODER'):
-        cfg.b200.decoder = os.environ['HN_DECODER']          # A/B switch: 'hn' (default) or 'cudnn'
+        cfg.b200.decoder = os.environ['HN_DECODER']          # A/B switch: 'hn' or 'cudnn' (default: cfg.b200.decoder = 'auto')
+    if os.environ.get('HN_FRONT_STREAMS'):
+        cfg.b200.front_streams = os.environ['HN_FRONT_STREAMS'] != '0'      # A/B switch of the decoder side stream
     torch.manual_seed(0)
     net = Network()
     net.load_state_dict(syn.fixture_state_dict(syn.REFERENCE_PARAM_SHAPES, dense=True))

@@ -159,6 +159,9 @@ _DEFAULTS: Dict[str, Any] = {
         # motion-weight volume decoder: 'hn' = hand-written kernels (csrc/vol_decoder.cu), 'cudnn' = PyTorch / cuDNN
         # transposed convolutions, 'auto' = 'hn' on the fp32 parity path, 'cudnn' (TF32) on the bf16 path
         'decoder': 'auto',
+        # run the volume decoder on a side stream, concurrently with the pose decoder / forward kinematics (and their
+        # backward passes with each other)
+        'front_streams': True,
         # cache the decoded motion-weight volume across eval frames
         'cache_eval_volume': False,
         # stratified-jitter noise: 'reference' = CPU default generator like network.py:468

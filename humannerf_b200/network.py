@@ -83,6 +83,7 @@ class Network(nn.Module):
                     f'that the B200 hot path does not implement (SURVEY.md section 2, row 22)')
 
         self.motion_basis_computer = MotionBasisComputer(total_bones=cfg.total_bones)
+        self._side_streams = {}           # device index -> stream of the volume decoder branch (forward)
 
         self.mweight_vol_decoder = _load_symbol(cfg.mweight_volume.module, 'MotionWeightVolumeDecoder')(
             embedding_size=cfg.mweight_volume.embedding_size,
@@ -204,6 +205,25 @@ class Network(nn.Module):
         cnl_gtfms = cnl_gtfms[None, ...].float()
         priors = motion_weights_priors[None, ...] if motion_weights_priors.dim() == 4 else motion_weights_priors
 
+        # 0. the blend-weight volume depends on neither the pose nor the rays: its decoder (35 launches, ~0.3 ms) starts
+        #    on a side stream and runs under the pose decoder / forward kinematics / weight re-pack below.  Autograd runs
+        #    a node's backward on the stream of its forward, so the decoder's backward overlaps the pose branch's too.
+        precision = _lib.PRECISION_BF16 if str(b200.get('mlp_precision', 'fp32')).lower() == 'bf16' \
+            else _lib.PRECISION_FP32
+        if hasattr(self.mweight_vol_decoder, 'allow_tf32'):
+            tf32 = b200.get('decoder_tf32', 'auto')
+            self.mweight_vol_decoder.allow_tf32 = (precision == _lib.PRECISION_BF16) if tf32 == 'auto' else bool(tf32)
+        side = None
+        if bool(b200.get('front_streams', True)):
+            main = torch.cuda.current_stream(dev)
+            side = self._side_streams.get(dev.index)
+            if side is None:
+                side = self._side_streams[dev.index] = torch.cuda.Stream(dev)
+            pri = priors.float()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                vol = self._decode_volume(pri)[0]
+
         # 1. pose refinement (network.py:667-695)
         refine = (not cfg.pose_decoder_off) and it >= cfg.pose_decoder.get('kick_in_iter', 0)
         fused_front = bool(b200.get('fused_front_end', True))
@@ -230,11 +250,6 @@ class Network(nn.Module):
             hann = hann_window_weights(it, nr_cfg.multires, nr_cfg.kick_in_iter, nr_cfg.full_band_iter).to(dev)
 
         # 3. motion bases and blend-weight volume (network.py:757-763)
-        precision = _lib.PRECISION_BF16 if str(b200.get('mlp_precision', 'fp32')).lower() == 'bf16' \
-            else _lib.PRECISION_FP32
-        if hasattr(self.mweight_vol_decoder, 'allow_tf32'):
-            tf32 = b200.get('decoder_tf32', 'auto')
-            self.mweight_vol_decoder.allow_tf32 = (precision == _lib.PRECISION_BF16) if tf32 == 'auto' else bool(tf32)
         if fused_front:
             # Rodrigues + corrected rotations + the forward-kinematics chain in one launch (csrc/pose_fk.cu);
             # the LU inverse (the reference's torch.inverse without its host-side check) and the product
@@ -245,7 +260,11 @@ class Network(nn.Module):
             scale_Rs, Ts = f[None, :, :3, :3], f[None, :, :3, 3]
         else:
             scale_Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts, cnl_gtfms)
-        vol = self._decode_volume(priors.float())[0]
+        if side is not None:
+            main.wait_stream(side)
+            vol.record_stream(main)             # allocated on the side stream, consumed (and later freed) on this one
+        else:
+            vol = self._decode_volume(priors.float())[0]
         self.motion_weights_vol = vol
         # outputs of the replicated per-frame front end; the multi-GPU train step exchanges the
         # gradients of these instead of the 63.6 M decoder parameters (parallel.CutBReducer)

@@ -2,7 +2,7 @@
 # A/B of training-kernel variants: per-op times of the eager roofline re-run in bench.py
 mkdir -p gpurun_out
 for v in "$@"; do
-  env $v HN_DECODER=cudnn timeout 600 python bench.py --no-cpu-baseline --no-eager-gpu-baseline --no-skip-leg --no-render --steps 10 > gpurun_out/bench_exp.log 2> gpurun_out/bench_exp.err
+  env $v timeout 600 python bench.py --no-cpu-baseline --no-eager-gpu-baseline --no-skip-leg --no-render --steps 10 > gpurun_out/bench_exp.log 2> gpurun_out/bench_exp.err
   python - "$v" <<P
 import json, sys
 d = json.loads(open('gpurun_out/bench_exp.log').read().strip().splitlines()[-1])
