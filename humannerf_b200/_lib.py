@@ -12,10 +12,12 @@ from typing import Optional
 
 import torch
 
-HN_ABI_VERSION = 5
+HN_ABI_VERSION = 6
 HN_MAX_LAYERS = 16
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+BWD_DATA = 1          # phases of hn_field_bwd_bf16_phases
+BWD_WEIGHTS = 2
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libhumannerf_b200.so')
 _lib: Optional[C.CDLL] = None
@@ -71,6 +73,8 @@ SIGNATURES = {
     'hn_field_bwd_bf16_scratch_bytes': (_i64, [C.POINTER(FieldParams), _i64]),
     'hn_field_bwd_bf16': (_int, [C.POINTER(FieldParams), C.POINTER(FieldGrads), _i64, _p, _p, _p, _p, _int, _p, _p, _p,
                                  _p, _p, _i64, _p, _p, _i64, _p, _p]),
+    'hn_field_bwd_bf16_phases': (_int, [C.POINTER(FieldParams), C.POINTER(FieldGrads), _i64, _p, _p, _p, _p, _int, _p, _p, _p,
+                                 _p, _p, _i64, _p, _p, _i64, _p, _int, _p]),
     'hn_field_packed_bytes': (_i64, [C.POINTER(FieldParams)]),
     'hn_field_pack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),
     'hn_field_repack_bf16': (_int, [C.POINTER(FieldParams), _p, _p, _p]),

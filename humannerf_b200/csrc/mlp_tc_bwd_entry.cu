@@ -56,9 +56,20 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
                       const float* d_raw, const float* d_xyz, const float* d_offsets, float* d_x_skel,
                       void* workspace, int64_t workspace_bytes, const void* packed, void* scratch,
                       int64_t scratch_bytes, const int64_t* n_samples_dev, void* stream) {
+  return hn_field_bwd_bf16_phases(p, g, n_samples, x_skel, xyz, cond, hann_w, ignore_non_rigid, d_raw, d_xyz, d_offsets, d_x_skel,
+                                  workspace, workspace_bytes, packed, scratch, scratch_bytes, n_samples_dev,
+                                  HN_BWD_DATA | HN_BWD_WEIGHTS, stream);
+}
+
+int hn_field_bwd_bf16_phases(const hn_field_params* p, const hn_field_grads* g, int64_t n_samples, const float* x_skel,
+                             const float* xyz, const float* cond, const float* hann_w, int ignore_non_rigid,
+                             const float* d_raw, const float* d_xyz, const float* d_offsets, float* d_x_skel,
+                             void* workspace, int64_t workspace_bytes, const void* packed, void* scratch,
+                             int64_t scratch_bytes, const int64_t* n_samples_dev, int phases, void* stream) {
   TcPlan plan;
   HN_TRY(make_tc_plan(p, plan));
   if (n_samples == 0) return 0;
+  if ((phases & ~(HN_BWD_DATA | HN_BWD_WEIGHTS)) || !phases) return fail_arg("hn_field_bwd_bf16_phases: phases = %d", phases);
   if (!g || n_samples < 0 || !x_skel || !xyz || !d_raw || !d_x_skel || !workspace || !packed || !scratch)
     return fail_arg("hn_field_bwd_bf16: null pointer or negative size");
   if (!ignore_non_rigid && ((p->cond_dim > 0 && !cond) || !hann_w)) return fail_arg("hn_field_bwd_bf16: cond / hann_w missing");
@@ -78,6 +89,7 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
   HN_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "hn_field_bwd_bf16/attr"));
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
 
+  if (phases & HN_BWD_DATA) {
   // 1. canonical MLP: d_raw -> dZ images; d_xyz_tot = upstream d_xyz + PE'(xyz) . d(encoding), accumulated
   //    by the chain's epilogue (both encoding reads: skip layer and layer 0)
   if (d_xyz) HN_TRY(copy_cols(n, 3, d_xyz, 3, d_xyz_tot, 4, st));
@@ -91,6 +103,8 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
     HN_TRY(add3(n, d_xyz_tot, 4, d_offsets, 3, dz_nr, 4, st));
     HN_TRY(launch_field_tc2_bwd(plan, pk, n, n_samples_dev, 0, dz_nr, 4, 3, bufs, x_skel, hann_w, d_x_skel, 3, sms, st));
   }
+  }
+  if (!(phases & HN_BWD_WEIGHTS)) return 0;
   // 3. weight / bias gradients from the images
   std::vector<WgradJob> jobs;
   auto add_job = [&](const uint8_t* dz, int f_dz, int m, const uint8_t* x, int f_x, int x_f0, int nn, int n_valid,

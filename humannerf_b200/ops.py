@@ -405,6 +405,39 @@ class PackedField:
         return self.image
 
 
+# Deferred weight gradients (bf16 path).  Between the loss and the optimizer nothing reads the MLPs' weight gradients, but
+# the data gradients feed the motion field's backward and - on several GPUs - the all-reduce of the boundary gradients.
+# Inside `deferred_weight_gradients()` the field's backward launches only its data phase and returns gradient tensors
+# whose CONTENT arrives when `flush_weight_gradients()` launches the weight phase (on the then-current stream, which must
+# be ordered after the backward - the same stream in practice).  The context manager flushes on exit, so no code outside
+# it can observe unfinished gradients.
+_DEFERRED = {'on': False, 'jobs': []}
+
+
+class deferred_weight_gradients:
+    def __enter__(self):
+        if _DEFERRED['on']:
+            raise RuntimeError('humannerf_b200: deferred_weight_gradients() does not nest')
+        _DEFERRED['on'], _DEFERRED['jobs'] = True, []
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            if exc[0] is None:
+                flush_weight_gradients()
+        finally:
+            _DEFERRED['on'], _DEFERRED['jobs'] = False, []
+        return False
+
+
+def flush_weight_gradients() -> int:
+    """Launch the weight phases queued since the context was entered; returns how many."""
+    jobs, _DEFERRED['jobs'] = _DEFERRED['jobs'], []
+    for job in jobs:
+        job()
+    return len(jobs)
+
+
 class _CanonicalField(torch.autograd.Function):
     """inputs: x_skel (P,3), cond (cond_dim), hann_w (nr_freqs), then the flat parameter list
     [nr_w..., nr_b..., cn_w..., cn_b...]."""
@@ -468,11 +501,22 @@ class _CanonicalField(torch.autograd.Function):
         if ctx.precision == _lib.PRECISION_BF16:
             sbytes = int(lib.hn_field_bwd_bf16_scratch_bytes(C.byref(fp), P))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev), _timed('field_bwd_bf16'):
-                check(lib.hn_field_bwd_bf16(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(xyz), ptr(cond), ptr(hann_w),
-                                            1 if ctx.ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off), ptr(d_x),
-                                            ptr(ctx.ws), ctx.ws.numel(), ptr(ctx.packed), ptr(scratch), sbytes,
-                                            ptr(ctx.count), stream_ptr()), 'field_bwd_bf16')
+            ws, packed, count, ignore = ctx.ws, ctx.packed, ctx.count, ctx.ignore
+            keep = (flat, grads, gbuf)      # the queued weight phase keeps every buffer of the call alive until it ran
+
+            def run(phases: int) -> None:
+                with torch.cuda.device(dev), _timed('field_bwd_bf16'):
+                    check(lib.hn_field_bwd_bf16_phases(C.byref(fp), C.byref(fg), P, ptr(x_skel), ptr(xyz), ptr(cond),
+                                                       ptr(hann_w), 1 if ignore else 0, ptr(g_raw), ptr(g_xyz), ptr(g_off),
+                                                       ptr(d_x), ptr(ws), ws.numel(), ptr(packed), ptr(scratch), sbytes,
+                                                       ptr(count), phases, stream_ptr()), 'field_bwd_bf16')
+
+            if _DEFERRED['on']:
+                # data phase now; the weight-gradient kernel when `flush_weight_gradients` says so (same stream)
+                run(_lib.BWD_DATA)
+                _DEFERRED['jobs'].append(lambda _keep=keep: run(_lib.BWD_WEIGHTS))
+            else:
+                run(_lib.BWD_DATA | _lib.BWD_WEIGHTS)
         else:
             sbytes = int(lib.hn_field_bwd_scratch_bytes(C.byref(fp), P))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)

@@ -201,16 +201,23 @@ class CutBReducer:
         Returns the number of floats exchanged."""
         if os.environ.get('HN_CHECK_SAME_FRAME', '0') == '1' and not torch.cuda.is_current_stream_capturing():
             self.check_same_frame(group)
+        from humannerf_b200 import ops
         leaves = self.leaf_inputs()
-        grads = torch.autograd.grad(loss, leaves, retain_graph=True, allow_unused=True)
-        grads = [torch.zeros_like(t) if g is None else g.contiguous() for g, t in zip(grads, leaves)]
         n_mlp = len(self.mlp_params)
         b_tensors = list(self.boundary.values())
-        b_grads = grads[n_mlp:]
-        # critical path first: the boundary gradients feed the replicated backward below.  The MLP bucket is
-        # issued behind it on the communicator's stream and only joined before the parameters' .grad is set, so
-        # it overlaps the decoder / FK / pose-decoder backward.
-        allreduce_bucket(b_grads, group=group)
+        # The field's backward runs only its DATA phase here (ops.deferred_weight_gradients): the boundary gradients
+        # are complete after the motion field's backward, their all-reduce is enqueued on the communicator's stream,
+        # and only then the 1.7 ms weight-gradient kernel is launched - the collective on the critical path hides
+        # under it.  The MLP bucket (which that kernel fills) follows on the communicator's stream and is joined
+        # before the parameters' .grad is set, so it overlaps the decoder / FK / pose-decoder backward.
+        with ops.deferred_weight_gradients():
+            grads = torch.autograd.grad(loss, leaves, retain_graph=True, allow_unused=True)
+            grads = [torch.zeros_like(t) if g is None else g.contiguous() for g, t in zip(grads, leaves)]
+            b_grads = grads[n_mlp:]
+            finish_boundary = allreduce_bucket(b_grads, group=group, async_op=overlap)
+            ops.flush_weight_gradients()
+        if finish_boundary is not None:
+            finish_boundary()
         finish_mlp = allreduce_bucket(grads[:n_mlp], group=group, async_op=overlap)
         live = [(t, g) for t, g in zip(b_tensors, b_grads) if t.requires_grad]
         if live:

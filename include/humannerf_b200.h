@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 5
+#define HN_ABI_VERSION 6
 #define HN_MAX_LAYERS 16
 
 /* ABI version of the loaded library (compare with HN_ABI_VERSION). */
@@ -191,6 +191,19 @@ int hn_field_bwd_bf16(const hn_field_params* p, const hn_field_grads* g, int64_t
                       float* d_x_skel, void* workspace, int64_t workspace_bytes, const void* packed,
                       void* scratch, int64_t scratch_bytes, const int64_t* n_samples_dev /*nullable, as in
                       hn_field_fwd*/, void* stream);
+
+/* The same in two calls: HN_BWD_DATA runs the backward-data chains (writes d_x_skel and the dZ images into `workspace`),
+ * HN_BWD_WEIGHTS the weight / bias gradient kernel that reads those images (same arguments, any later time on a stream
+ * ordered after the first call).  Nothing between the loss and the optimizer needs the MLPs' weight gradients, so a
+ * multi-GPU trainer issues the all-reduce of the boundary gradients (which the data phase feeds) before the 1.7 ms
+ * weight phase and hides it there (parallel.CutBReducer); autograd of mlp_offset.py:74-114 / mlp_rgb_sigma.py:132-206. */
+#define HN_BWD_DATA 1
+#define HN_BWD_WEIGHTS 2
+int hn_field_bwd_bf16_phases(const hn_field_params* p, const hn_field_grads* g, int64_t n_samples,
+                             const float* x_skel, const float* xyz, const float* cond, const float* hann_w,
+                             int ignore_non_rigid, const float* d_raw, const float* d_xyz, const float* d_offsets,
+                             float* d_x_skel, void* workspace, int64_t workspace_bytes, const void* packed,
+                             void* scratch, int64_t scratch_bytes, const int64_t* n_samples_dev, int phases, void* stream);
 
 /* bf16 weight image for the tcgen05 kernel: weights re-tiled into the UMMA shared-memory
  * core-matrix layout, in consumption order, with the condition code folded into the first
