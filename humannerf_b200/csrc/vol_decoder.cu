@@ -323,11 +323,315 @@ deconv_gemm_kernel(const DeconvArgs g) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same three GEMMs with 128 x kTN x 32 tiles for the layers with >= 512 rows / K (the 8^3 -> 16^3 and 16^3 -> 32^3
+// layers hold 85 % of the decoder's FLOPs).  8 warps = 4 (rows) x 2 (cols), warp tile 32 x kTN/2 = 2 x kTN/16 fragments:
+// per 8-wide k step a warp issues 8 + kTN/8 shared loads for 2 kTN/16 MMAs (the 64 x 64 x 16 kernel above: 12 for 4),
+// a k-tile is 32 deep (half the barriers), three stages of 27 KB in dynamic shared memory, two blocks per SM.
+// Operand layouts, tap handling and epilogues are those of deconv_gemm_kernel.
+constexpr int kBM = 128, kBK = 32, kBStages = 3;
+constexpr int kBStrideRK = kBK + 4;        // 36: rows of a row-major-in-k tile
+constexpr int kBStrideAKM = kBM + 8;       // 136: rows of the k-major A tile of the weight gradient
+constexpr int kBAFloats = kBM * kBStrideRK;                        // 4608 >= 32 * 136
+__host__ __device__ constexpr int big_b_floats(int tn) { return tn == 64 ? 64 * kBStrideRK : kBK * (tn + 8); }   // 2304 (= 32 * 72) / 1280
+__host__ __device__ constexpr int big_smem_bytes(int tn) { return kBStages * (kBAFloats + big_b_floats(tn)) * 4; }
+
+template <int MODE, bool kX3, int kTN>
+__global__ void __launch_bounds__(256, 2)
+deconv_gemm_big_kernel(const DeconvArgs g) {
+  extern __shared__ __align__(16) float big_smem[];
+  constexpr bool A_RK = MODE != 2, B_RK = MODE == 1;
+  constexpr int kSB = kTN + 8, kNF = kTN / 16, kBF = big_b_floats(kTN);
+  static_assert(MODE != 1 || kTN == 64, "the data gradient always has >= 64 columns (cin)");
+  float* const As = big_smem;
+  float* const Bs = big_smem + kBStages * kBAFloats;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sh = g.log2_din, din = 1 << sh, dmask = din - 1, din3 = 1 << (3 * sh), dout = 2 * din;
+  const int M = MODE == 2 ? g.cin : din3;
+  const int N = MODE == 0 ? g.cout : (MODE == 1 ? g.cin : g.cout);
+  const int n_tiles = (N + kTN - 1) / kTN;
+  const int m0 = (int)(blockIdx.x / n_tiles) * kBM, n0 = (int)(blockIdx.x % n_tiles) * kTN;
+  const int cout_pad = (g.cout + kBK - 1) / kBK * kBK;                    // dgrad: K per tap, zero padded
+  const int n_taps = MODE == 0 ? (din == 1 ? 1 : 8) : (din == 1 ? 8 : 64);
+  const int kpt = MODE == 0 ? g.cin : cout_pad;                          // K per tap (MODE 0 / 1), a multiple of 32
+  const int k_total = MODE == 2 ? din3 : n_taps * kpt;
+  int k_begin = 0, k_end = k_total;
+  if (g.k_splits > 1) {
+    k_begin = (int)blockIdx.z * g.k_per_split;
+    k_end = min(k_total, k_begin + g.k_per_split);
+  }
+  const int pz = (blockIdx.y >> 2) & 1, py = (blockIdx.y >> 1) & 1, px = blockIdx.y & 1;      // MODE 0: parity class
+  const int wz = blockIdx.y >> 4, wy = (blockIdx.y >> 2) & 3, wx = blockIdx.y & 3;           // MODE 2: tap
+  // copy roles.  Row-major-in-k tiles (8 quads per row): thread = (row (tid >> 3) + 32 j, quad (tid & 7) * 4);
+  // k-major A tile (32 quads per k row): (k (tid >> 5) + 8 j, quad (tid & 31) * 4); k-major B tile: 64 columns (k (tid >> 4)
+  // + 16 j, quad (tid & 15) * 4), 32 columns (k tid >> 3, quad (tid & 7) * 4)
+  const int r8 = tid >> 3, kq = (tid & 7) * 4;
+  const int krb = kTN == 64 ? tid >> 4 : tid >> 3, qb = kTN == 64 ? (tid & 15) * 4 : (tid & 7) * 4;
+  constexpr int kBJ = kTN == 64 ? 2 : 1;                                  // k rows of the k-major B tile per thread
+  const bool w_rows_aligned = (g.cout & 3) == 0;
+
+  int tap_i = 0, c_i = 0, k_i = k_begin;
+  if (MODE != 2) { tap_i = k_begin / kpt; c_i = k_begin - tap_i * kpt; }
+  const float* a_tap[4] = {nullptr, nullptr, nullptr, nullptr};          // A rows of this thread for the current tap (+ k quad)
+  const float* b_tap[2] = {nullptr, nullptr};
+  uint32_t a_ok = 0u;                                                    // bit j: row j of this thread is inside the volume
+  int b_cols = 0;                                                        // MODE 0 / 2: valid columns of this thread's B quad
+  if (MODE != 1) b_cols = max(0, min(4, N - (n0 + qb)));
+  auto set_tap = [&](int tap) {
+    if (MODE == 2) return;
+    a_ok = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int vm = m0 + r8 + 32 * j;
+      const int vz = vm >> (2 * sh), vy = (vm >> sh) & dmask, vx = vm & dmask;
+      if (MODE == 0) {
+        const int iz = vz + tap_off(pz, (tap >> 2) & 1), iy = vy + tap_off(py, (tap >> 1) & 1), ix = vx + tap_off(px, tap & 1);
+        if (vm < din3 && (unsigned)iz < (unsigned)din && (unsigned)iy < (unsigned)din && (unsigned)ix < (unsigned)din) a_ok |= 1u << j;
+        a_tap[j] = g.in + (size_t)((((iz << sh) + iy) << sh) + ix) * g.cin + kq;
+      } else {
+        const int kz = din == 1 ? 1 + ((tap >> 2) & 1) : tap >> 4, ky = din == 1 ? 1 + ((tap >> 1) & 1) : (tap >> 2) & 3,
+                  kx = din == 1 ? 1 + (tap & 1) : tap & 3;
+        const int oz = 2 * vz - 1 + kz, oy = 2 * vy - 1 + ky, ox = 2 * vx - 1 + kx;
+        if (vm < din3 && (unsigned)oz < (unsigned)dout && (unsigned)oy < (unsigned)dout && (unsigned)ox < (unsigned)dout) a_ok |= 1u << j;
+        a_tap[j] = g.outside + (size_t)((((oz << (sh + 1)) + oy) << (sh + 1)) + ox) * g.ld_out + kq;
+      }
+    }
+    if (MODE == 0) {
+      const int kidx = (tap_k(pz, (tap >> 2) & 1) * 4 + tap_k(py, (tap >> 1) & 1)) * 4 + tap_k(px, tap & 1);
+#pragma unroll
+      for (int j = 0; j < kBJ; ++j) b_tap[j] = g.w + ((size_t)(krb + 16 * j) * 64 + kidx) * g.cout + n0 + qb;
+    } else {
+      const int kz = din == 1 ? 1 + ((tap >> 2) & 1) : tap >> 4, ky = din == 1 ? 1 + ((tap >> 1) & 1) : (tap >> 2) & 3,
+                kx = din == 1 ? 1 + (tap & 1) : tap & 3;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b_tap[j] = g.w + ((size_t)(n0 + r8 + 32 * j) * 64 + (kz * 4 + ky) * 4 + kx) * g.cout + kq;
+    }
+  };
+  if (MODE != 2) set_tap(tap_i);
+
+  auto issue = [&](int stage) {
+    float* as = As + stage * kBAFloats;
+    float* bs = Bs + stage * kBF;
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (a_ok >> j) & 1u;
+        cp_async16(as + (r8 + 32 * j) * kBStrideRK + kq, ok ? a_tap[j] + c_i : g.in, ok);
+      }
+#pragma unroll
+      for (int j = 0; j < kBJ; ++j) {
+        const float* src = b_tap[j] + (size_t)c_i * 64 * g.cout;
+        float* dst = bs + (krb + 16 * j) * kSB + qb;
+        if (w_rows_aligned) cp_async16(dst, b_cols == 4 ? src : g.w, b_cols == 4);
+        else cp_async4x4(dst, b_cols > 0 ? src : g.w, b_cols);
+      }
+    } else if (MODE == 1) {
+      const int co = c_i + kq;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool av = ((a_ok >> j) & 1u) && co + 4 <= g.ld_out;
+        cp_async16(as + (r8 + 32 * j) * kBStrideRK + kq, av ? a_tap[j] + c_i : g.outside, av);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int bv = (n0 + r8 + 32 * j < N) ? max(0, min(4, g.cout - co)) : 0;
+        float* dst = bs + (r8 + 32 * j) * kBStrideRK + kq;
+        if (w_rows_aligned) cp_async16(dst, bv == 4 ? b_tap[j] + c_i : g.w, bv == 4);
+        else cp_async4x4(dst, bv > 0 ? b_tap[j] + c_i : g.w, bv);
+      }
+    } else {
+      // A(ci, i) = in[i][ci .. ci + 3];  B(i, co) = outside[o(i, tap)][co .. co + 3]
+      const int ka = tid >> 5, qa = (tid & 31) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ia = k_i + ka + 8 * j;
+        const bool aok = ia < k_end && m0 + qa + 4 <= M;
+        cp_async16(as + (ka + 8 * j) * kBStrideAKM + qa, aok ? g.in + (size_t)ia * g.cin + m0 + qa : g.in, aok);
+      }
+#pragma unroll
+      for (int j = 0; j < kBJ; ++j) {
+        const int i = k_i + krb + 16 * j;
+        const int oz = 2 * (i >> (2 * sh)) - 1 + wz, oy = 2 * ((i >> sh) & dmask) - 1 + wy, ox = 2 * (i & dmask) - 1 + wx;
+        const bool bok = i < k_end && (unsigned)oz < (unsigned)dout && (unsigned)oy < (unsigned)dout && (unsigned)ox < (unsigned)dout &&
+                         n0 + qb + 4 <= g.ld_out;
+        cp_async16(bs + (krb + 16 * j) * kSB + qb,
+                   bok ? g.outside + (size_t)((((oz << (sh + 1)) + oy) << (sh + 1)) + ox) * g.ld_out + n0 + qb : g.outside, bok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    k_i += kBK;
+    if (MODE != 2) {
+      c_i += kBK;
+      if (c_i == kpt) {
+        c_i = 0;
+        if (++tap_i < n_taps) set_tap(tap_i);
+      }
+    }
+  };
+
+  float acc[2][kNF][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < kNF; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[a][i][j] = 0.f;
+
+  const int wm = warp >> 1, wn = warp & 1, fg = lane >> 2, ft = lane & 3;
+  const int n_steps = (k_end - k_begin + kBK - 1) / kBK;
+#pragma unroll
+  for (int s = 0; s < kBStages - 1; ++s) {
+    if (s < n_steps) issue(s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+#pragma unroll 1
+  for (int step = 0; step < n_steps; ++step) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kBStages - 2) : "memory");
+    __syncthreads();
+    const int nxt = step + kBStages - 1;
+    if (nxt < n_steps) issue(nxt % kBStages);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* as = As + (step % kBStages) * kBAFloats;
+    const float* bs = Bs + (step % kBStages) * kBF;
+    float part[2][kNF][4];
+    if (kX3) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < kNF; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) part[a][i][j] = 0.f;
+    }
+#pragma unroll
+    for (int k8 = 0; k8 < kBK; k8 += 8) {
+      uint32_t a_hi[2][4], a_lo[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int r = wm * 32 + a * 16 + fg;
+        float af[4];
+        if (A_RK) {
+          af[0] = as[r * kBStrideRK + k8 + ft];     af[1] = as[(r + 8) * kBStrideRK + k8 + ft];
+          af[2] = as[r * kBStrideRK + k8 + ft + 4]; af[3] = as[(r + 8) * kBStrideRK + k8 + ft + 4];
+        } else {
+          af[0] = as[(k8 + ft) * kBStrideAKM + r];     af[1] = as[(k8 + ft) * kBStrideAKM + r + 8];
+          af[2] = as[(k8 + ft + 4) * kBStrideAKM + r]; af[3] = as[(k8 + ft + 4) * kBStrideAKM + r + 8];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a_hi[a][i] = kX3 ? to_tf32_exact(af[i]) : to_tf32(af[i]);
+          if (kX3) a_lo[a][i] = to_tf32(af[i] - __uint_as_float(a_hi[a][i]));
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < kNF; ++f) {
+        const int c = wn * (kTN / 2) + f * 8 + fg;
+        float bf[2];
+        if (B_RK) { bf[0] = bs[c * kBStrideRK + k8 + ft]; bf[1] = bs[c * kBStrideRK + k8 + ft + 4]; }
+        else { bf[0] = bs[(k8 + ft) * kSB + c]; bf[1] = bs[(k8 + ft + 4) * kSB + c]; }
+        uint32_t b_hi[2], b_lo[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          b_hi[i] = kX3 ? to_tf32_exact(bf[i]) : to_tf32(bf[i]);
+          if (kX3) b_lo[i] = to_tf32(bf[i] - __uint_as_float(b_hi[i]));
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (kX3) {
+            mma_tf32(part[a][f], a_lo[a], b_hi);
+            mma_tf32(part[a][f], a_hi[a], b_lo);
+            mma_tf32(part[a][f], a_hi[a], b_hi);
+          } else {
+            mma_tf32(acc[a][f], a_hi[a], b_hi);
+          }
+        }
+      }
+    }
+    if (kX3) {
+      // tensor-core accumulation truncates: its error stays inside one 32-long partial sum, the tiles add up in fp32
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < kNF; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[a][i][j] += part[a][i][j];
+    }
+  }
+
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int i = 0; i < kNF; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + wm * 32 + a * 16 + fg + 8 * (j >> 1);
+        const int n = n0 + wn * (kTN / 2) + i * 8 + 2 * ft + (j & 1);
+        if (m >= M || n >= N) continue;
+        float v = acc[a][i][j];
+        if (MODE == 0) {
+          const int mz = m >> (2 * sh), my = (m >> sh) & dmask, mx = m & dmask;
+          const size_t o = (size_t)(((((2 * mz + pz) << (sh + 1)) + 2 * my + py) << (sh + 1)) + 2 * mx + px);
+          if (g.k_splits > 1) {
+            g.dst[((size_t)blockIdx.z * 8 * din3 + o) * g.cout + n] = v;
+          } else {
+            v += __ldg(g.bias + n);
+            if (g.leaky) v = v > 0.f ? v : kLeaky * v;
+            g.dst[o * g.ld_out + n] = v;
+          }
+        } else if (MODE == 1) {
+          if (g.k_splits > 1) {
+            g.dst[((size_t)blockIdx.z * din3 + m) * g.cin + n] = v;
+          } else {
+            if (g.act_in) v *= g.act_in[(size_t)m * g.cin + n] > 0.f ? 1.0f : kLeaky;
+            g.dst[(size_t)m * g.cin + n] = v;
+          }
+        } else {
+          g.dst[(size_t)blockIdx.z * g.cin * 64 * g.cout + ((size_t)m * 64 + blockIdx.y) * g.cout + n] = v;
+        }
+      }
+    }
+  }
+}
+
+// rows of a GEMM tile: the 128-row kernel for GEMMs with >= 512 rows (forward / data gradient: input voxels) or a K of
+// >= 512 voxels and >= 128 rows (weight gradient), when the K extent per tap is a multiple of its 32-deep k-tile
+static bool use_big_tiles(int mode, int din, int cin, int cout) {
+  const int d3 = din * din * din;
+  if (d3 < 512) return false;
+  if (mode == 0) return cin % kBK == 0;
+  if (mode == 1) return true;                 // K per tap is padded to 32 by the kernel itself
+  return cin >= kBM;
+}
+static int tile_m_rows(bool big) { return big ? kBM : kTile; }
+static int tile_k(bool big) { return big ? kBK : kTileK; }
+
+template <int MODE, bool kX3, int kTN>
+static int launch_big(const DeconvArgs& g, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HN_TRY(check_cuda(cudaFuncSetAttribute(deconv_gemm_big_kernel<MODE, kX3, kTN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           big_smem_bytes(kTN)), "hn_vol_decoder/smem attr"));
+    attr_set = true;
+  }
+  deconv_gemm_big_kernel<MODE, kX3, kTN><<<grid, 256, big_smem_bytes(kTN), st>>>(g);
+  return 0;
+}
+
 template <int MODE>
-static int launch_deconv_gemm(const DeconvArgs& g, dim3 grid, bool x3, int tn, cudaStream_t st, const char* what) {
+static int launch_deconv_gemm(const DeconvArgs& g, dim3 grid, bool x3, int tn, bool big, cudaStream_t st, const char* what) {
+  constexpr int M32 = MODE == 1 ? 0 : MODE;          // the data gradient has no 32-column variant
+  if (big) {
+    if (MODE != 1 && tn == 32) {
+      if (x3) HN_TRY((launch_big<M32, true, 32>(g, grid, st)));
+      else HN_TRY((launch_big<M32, false, 32>(g, grid, st)));
+    } else {
+      if (x3) HN_TRY((launch_big<MODE, true, 64>(g, grid, st)));
+      else HN_TRY((launch_big<MODE, false, 64>(g, grid, st)));
+    }
+    return launched(what);
+  }
   if (MODE != 1 && tn == 32) {
-    if (x3) deconv_gemm_kernel<MODE == 1 ? 0 : MODE, true, 32><<<grid, 256, 0, st>>>(g);
-    else deconv_gemm_kernel<MODE == 1 ? 0 : MODE, false, 32><<<grid, 256, 0, st>>>(g);
+    if (x3) deconv_gemm_kernel<M32, true, 32><<<grid, 256, 0, st>>>(g);
+    else deconv_gemm_kernel<M32, false, 32><<<grid, 256, 0, st>>>(g);
   } else {
     if (x3) deconv_gemm_kernel<MODE, true, 64><<<grid, 256, 0, st>>>(g);
     else deconv_gemm_kernel<MODE, false, 64><<<grid, 256, 0, st>>>(g);
@@ -514,8 +818,9 @@ struct DecPlan {
   size_t off_partial, off_g[2], off_dlogits, off_colsum, off_counters, scratch_floats;
 };
 
-// K-splits for a GEMM with `rows` rows: the low layers are weight-bandwidth bound and need many CTAs
 constexpr int kColSumSlabs = 64;
+// K-splits for a GEMM with `tiles` output tiles: the low layers are weight-bandwidth bound and need many CTAs; the large
+// layers also run faster in ~4 blocks per SM than in one wave (measured: 74 against 83 us for the last layer's forward)
 static int pick_splits(int64_t tiles, int k_total) {
   int splits = 1;
   while (tiles * splits < 592 && splits < 16 && k_total / (splits * 2) >= 64) splits *= 2;
@@ -548,11 +853,13 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
   size_t part = 0, gmax = 0;
   for (int l = 0; l < n_conv; ++l) {
     const size_t d3 = (size_t)p.din[l] * p.din[l] * p.din[l];
-    const int64_t ft = (int64_t)ceil_div<int64_t>((int64_t)d3, kTile) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 8;
+    const bool fb = use_big_tiles(0, p.din[l], p.ch[l], p.ch[l + 1]), db = use_big_tiles(1, p.din[l], p.ch[l], p.ch[l + 1]),
+               wb = use_big_tiles(2, p.din[l], p.ch[l], p.ch[l + 1]);
+    const int64_t ft = (int64_t)ceil_div<int64_t>((int64_t)d3, tile_m_rows(fb)) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 8;
     p.fwd_splits[l] = pick_splits(ft, (p.din[l] == 1 ? 1 : 8) * p.ch[l]);
-    const int64_t dt = (int64_t)ceil_div<int64_t>((int64_t)d3, kTile) * ceil_div(p.ch[l], kTile);
-    p.dgrad_splits[l] = pick_splits(dt, (p.din[l] == 1 ? 8 : 64) * (ceil_div(p.ch[l + 1], kTileK) * kTileK));
-    const int64_t wt = (int64_t)ceil_div(p.ch[l], kTile) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 64;
+    const int64_t dt = (int64_t)ceil_div<int64_t>((int64_t)d3, tile_m_rows(db)) * ceil_div(p.ch[l], kTile);
+    p.dgrad_splits[l] = pick_splits(dt, (p.din[l] == 1 ? 8 : 64) * (ceil_div(p.ch[l + 1], tile_k(db)) * tile_k(db)));
+    const int64_t wt = (int64_t)ceil_div(p.ch[l], tile_m_rows(wb)) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 64;
     p.wgrad_splits[l] = pick_splits(wt, (int)d3);
     if (p.wgrad_splits[l] > 1) part = std::max(part, (size_t)p.wgrad_splits[l] * p.ch[l] * 64 * p.ch[l + 1]);
     if (p.fwd_splits[l] > 1) part = std::max(part, (size_t)p.fwd_splits[l] * 8 * d3 * p.ch[l + 1]);
@@ -578,13 +885,14 @@ static int run_forward_layer(const DecPlan& p, int l, const float* in, const flo
   g.din = din; g.log2_din = l; g.cin = p.ch[l]; g.cout = p.ch[l + 1]; g.ld_out = ld_out; g.in = in; g.w = w; g.bias = b; g.leaky = leaky ? 1 : 0;
   const int k_total = (din == 1 ? 1 : 8) * g.cin;
   const int tn = tile_n(g.cout);
-  const int64_t tiles = (int64_t)ceil_div(d3, kTile) * ceil_div(g.cout, tn);
+  const bool big = use_big_tiles(0, din, g.cin, g.cout);
+  const int64_t tiles = (int64_t)ceil_div(d3, tile_m_rows(big)) * ceil_div(g.cout, tn);
   const int splits = p.fwd_splits[l];
   g.k_splits = splits;
-  g.k_per_split = ceil_div(ceil_div(k_total, splits), kTileK) * kTileK;
+  g.k_per_split = ceil_div(ceil_div(k_total, splits), tile_k(big)) * tile_k(big);
   g.dst = splits > 1 ? partial : out;
   dim3 grid((unsigned)tiles, 8, (unsigned)splits);
-  HN_TRY(launch_deconv_gemm<0>(g, grid, x3, tn, st, "hn_vol_decoder_fwd/deconv"));
+  HN_TRY(launch_deconv_gemm<0>(g, grid, x3, tn, big, st, "hn_vol_decoder_fwd/deconv"));
   if (splits > 1) {
     const int64_t rows = (int64_t)8 * d3;
     deconv_finish_kernel<<<(unsigned)ceil_div<int64_t>(rows * g.cout, 256), 256, 0, st>>>(partial, splits, rows, g.cout, ld_out, b,
@@ -677,11 +985,12 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     g.din = din; g.log2_din = l; g.cin = cin; g.cout = cout; g.ld_out = ld_g; g.in = ws + p.off_act[l]; g.outside = g_out; g.dst = d_conv_w[l];
     const int wsp = p.wgrad_splits[l];
     g.k_splits = wsp;
-    g.k_per_split = ceil_div(ceil_div(d3, wsp), kTileK) * kTileK;
+    const bool wbig = use_big_tiles(2, din, cin, cout), dbig = use_big_tiles(1, din, cin, cout);
+    g.k_per_split = ceil_div(ceil_div(d3, wsp), tile_k(wbig)) * tile_k(wbig);
     if (wsp > 1) g.dst = sc + p.off_partial;
     const int tn = tile_n(cout);
-    dim3 wgrid((unsigned)(ceil_div(cin, kTile) * ceil_div(cout, tn)), 64, (unsigned)wsp);
-    HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, st, "hn_vol_decoder_bwd/wgrad"));
+    dim3 wgrid((unsigned)(ceil_div(cin, tile_m_rows(wbig)) * ceil_div(cout, tn)), 64, (unsigned)wsp);
+    HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, wbig, st, "hn_vol_decoder_bwd/wgrad"));
     if (wsp > 1) {
       const int64_t n4 = (int64_t)cin * 64 * cout / 4;
       sum_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sc + p.off_partial), wsp, n4,
@@ -691,14 +1000,14 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     // data gradient -> gradient of the pre-activation of the previous layer (LeakyReLU' from its stored output)
     float* g_in = sc + p.off_g[l & 1];
     g.w = conv_w[l]; g.act_in = ws + p.off_act[l];
-    const int k_total = (din == 1 ? 8 : 64) * ceil_div(cout, kTileK) * kTileK;
-    const int64_t tiles = (int64_t)ceil_div(d3, kTile) * ceil_div(cin, kTile);
+    const int k_total = (din == 1 ? 8 : 64) * ceil_div(cout, tile_k(dbig)) * tile_k(dbig);
+    const int64_t tiles = (int64_t)ceil_div(d3, tile_m_rows(dbig)) * ceil_div(cin, kTile);
     const int splits = p.dgrad_splits[l];
     g.k_splits = splits;
-    g.k_per_split = ceil_div(ceil_div(k_total, splits), kTileK) * kTileK;
+    g.k_per_split = ceil_div(ceil_div(k_total, splits), tile_k(dbig)) * tile_k(dbig);
     g.dst = splits > 1 ? sc + p.off_partial : g_in;
     dim3 dgrid((unsigned)tiles, 1, (unsigned)splits);
-    HN_TRY(launch_deconv_gemm<1>(g, dgrid, x3, 64, st, "hn_vol_decoder_bwd/dgrad"));
+    HN_TRY(launch_deconv_gemm<1>(g, dgrid, x3, 64, dbig, st, "hn_vol_decoder_bwd/dgrad"));
     if (splits > 1) {
       deconv_finish_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)d3 * cin, 256), 256, 0, st>>>(sc + p.off_partial, splits, d3, cin, cin, nullptr, 0,
                                                                                           ws + p.off_act[l], g_in);

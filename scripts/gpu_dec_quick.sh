@@ -18,11 +18,4 @@ for nm, t in names[-n:]:
     print(f"{t/1000:9.1f} us  {nm[:70]}")
 print("total", round(tot / 1000, 1), "us")
 P
-for dec in hn cudnn; do
-  HN_DECODER=$dec timeout 600 python bench.py --no-cpu-baseline --no-eager-gpu-baseline --no-skip-leg --no-render > gpurun_out/bench_dec_$dec.log 2> gpurun_out/bench_dec_$dec.err
-  python - <<P
-import json
-d = json.loads(open('gpurun_out/bench_dec_$dec.log').read().strip().splitlines()[-1])
-print('$dec', 'ms/step', round(d['ms_per_step'], 3), {k: round(v['ms_total'] / v['calls'], 3) for k, v in d['ops_ms'].items() if 'decoder' in k or k.startswith('field')})
-P
-done
+bash scripts/gpu_exp.sh HN_DECODER=hn HN_DECODER=cudnn
