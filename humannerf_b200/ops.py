@@ -502,7 +502,6 @@ class _CanonicalField(torch.autograd.Function):
             sbytes = int(lib.hn_field_bwd_bf16_scratch_bytes(C.byref(fp), P))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
             ws, packed, count, ignore = ctx.ws, ctx.packed, ctx.count, ctx.ignore
-            keep = (flat, grads, gbuf)      # the queued weight phase keeps every buffer of the call alive until it ran
 
             def run(phases: int) -> None:
                 with torch.cuda.device(dev), _timed('field_bwd_bf16'):
@@ -514,7 +513,23 @@ class _CanonicalField(torch.autograd.Function):
             if _DEFERRED['on']:
                 # data phase now; the weight-gradient kernel when `flush_weight_gradients` says so (same stream)
                 run(_lib.BWD_DATA)
-                _DEFERRED['jobs'].append(lambda _keep=keep: run(_lib.BWD_WEIGHTS))
+                shapes = [t.shape for t in flat]
+                before = [(None, 0) if t.grad is None else (t.grad, t.grad._version) for t in flat]
+
+                def weight_phase():
+                    run(_lib.BWD_WEIGHTS)
+                    # What autograd did with the (then still empty) gradient tensors after this backward returned:
+                    # handed them on (torch.autograd.grad: .grad untouched), let AccumulateGrad take them over (.grad
+                    # IS the view of gbuf: complete now), or cloned / accumulated them into .grad - which then holds
+                    # a copy taken before the weight phase ran and gets the content now.
+                    for t, o, shp, (g0, v0) in zip(flat, offs, shapes, before):
+                        view = gbuf[o:o + t.numel()].view(shp)
+                        g1 = t.grad
+                        if g1 is None or g1.data_ptr() == view.data_ptr():
+                            continue
+                        if g1 is not g0 or g1._version != v0:
+                            g1.add_(view)
+                _DEFERRED['jobs'].append(weight_phase)
             else:
                 run(_lib.BWD_DATA | _lib.BWD_WEIGHTS)
         else:
