@@ -12,11 +12,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3500 --
 echo "ncu launches exit $?"
 python scripts/profile_render.py --rays 6144 --train > gpurun_out/prof_plain_train.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k "regex:field_tc|field_ts|tile_wgrad_kernel|adam_kernel|motion_field|pose_fk|pack_corners|composite|lpips_head|unpack_corners|select_patches|deconv_gemm" -s 0 -c 44 \
+    -k "regex:field_tc|field_ts|tile_wgrad_kernel|adam_kernel|motion_field|pose_fk|pack_corners|composite|lpips_head|unpack_corners|select_patches|deconv_gemm" -s 0 -c 30 \
     -o gpurun_out/prof_train_${TAG} -f python scripts/profile_render.py --rays 6144 --train > gpurun_out/ncu_train.log 2>&1
 echo "ncu train exit $?"
 python scripts/profile_render.py --rays 32768 > gpurun_out/prof_plain_render.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:field_tc|field_ts|motion_field_fwd|composite_fwd" -s 0 -c 8 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:field_tc|field_ts|motion_field_fwd|composite_fwd" -s 0 -c 4 \
     -o gpurun_out/prof_render_${TAG} -f python scripts/profile_render.py --rays 32768 > gpurun_out/ncu_render.log 2>&1
 echo "ncu render exit $?"
 ls -la gpurun_out/*${TAG}*
