@@ -217,3 +217,26 @@ def test_first_deconv_function_matches_conv_transpose():
     outer = got['block_conv.0.weight'].clone()
     outer[:, :, 1:3, 1:3, 1:3] = 0
     assert float(outer.abs().max()) == 0.0
+
+
+def test_deferred_weight_gradients_context_logic():
+    """ops.deferred_weight_gradients(): queued weight phases run exactly once - at flush_weight_gradients() or at the
+    context's exit -, the context does not nest, and an exception inside it drops the queue instead of launching."""
+    from humannerf_b200 import ops
+    ran = []
+    assert ops.flush_weight_gradients() == 0
+    with ops.deferred_weight_gradients():
+        ops._DEFERRED['jobs'].append(lambda: ran.append('a'))
+        assert ops.flush_weight_gradients() == 1 and ran == ['a']
+        ops._DEFERRED['jobs'].append(lambda: ran.append('b'))
+    assert ran == ['a', 'b'] and not ops._DEFERRED['on'] and ops._DEFERRED['jobs'] == []
+    with pytest.raises(RuntimeError):
+        with ops.deferred_weight_gradients():
+            with ops.deferred_weight_gradients():
+                pass
+    assert not ops._DEFERRED['on']
+    with pytest.raises(ValueError):
+        with ops.deferred_weight_gradients():
+            ops._DEFERRED['jobs'].append(lambda: ran.append('never'))
+            raise ValueError('step failed')
+    assert ran == ['a', 'b'] and not ops._DEFERRED['on'] and ops._DEFERRED['jobs'] == []
