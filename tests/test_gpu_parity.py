@@ -877,3 +877,54 @@ def test_vol_decoder_against_reference_and_torch(ops, sd, frame):
     assert torch.equal(vol2.detach(), outs['hn'])
     for k, p in m.named_parameters():
         assert torch.equal(p.grad, grads['hn'][k]), k
+
+
+@pytest.mark.parametrize('volume_size,embedding', [(16, 256), (8, 64)])
+def test_vol_decoder_other_geometries(ops, volume_size, embedding):
+    """The decoder kernels on the reference module at other `cfg.mweight_volume` sizes (network_util.py:25-38 builds
+    log2(V) - 1 hidden transposed convolutions): V = 16 puts the 25-channel layer on the 128-row kernel with 8^3 inputs,
+    V = 8 runs every layer on the 64-row kernel.  Forward and all parameter gradients against PyTorch / cuDNN in fp32
+    (TF32 off): 1e-5 abs on the softmax volume, 1e-4 relative L2 per gradient tensor; plain-TF32 mode within 5e-2."""
+    from humannerf_b200.config import make_cfg
+    from humannerf_b200.mweight_vol_decoders.deconv_vol_decoder import MotionWeightVolumeDecoder
+    cfg = make_cfg()
+    torch.manual_seed(volume_size)
+    ref = MotionWeightVolumeDecoder(embedding_size=embedding, volume_size=volume_size, total_bones=24)
+    with torch.no_grad():
+        for p in ref.parameters():                       # the module's own init leaves the last layers tiny
+            p.copy_(torch.randn_like(p) * (0.5 / max(p.shape[0] if p.dim() > 1 else 1, 1) ** 0.5))
+    mods = {'cudnn': ref.to(DEV)}
+    mods['hn'] = MotionWeightVolumeDecoder(embedding_size=embedding, volume_size=volume_size, total_bones=24).to(DEV)
+    mods['hn'].load_state_dict(ref.state_dict())
+    V = volume_size
+    gen = torch.Generator().manual_seed(7)
+    prior = torch.rand(1, 25, V, V, V, generator=gen).to(DEV) + 0.05
+    prior = prior / prior.sum(1, keepdim=True)
+    g_vol = torch.randn(1, 25, V, V, V, generator=gen).to(DEV)
+    outs, grads = {}, {}
+    try:
+        for mode, m in mods.items():
+            cfg.b200.decoder = mode
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                vol = m(motion_weights_priors=prior)
+                (vol * g_vol).sum().backward()
+            outs[mode] = vol.detach()
+            grads[mode] = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        report(f'vol_decoder V={V} vs cuDNN fp32', outs['hn'], outs['cudnn'], 1e-5, 1e-5)
+        for k, g in grads['hn'].items():
+            r = grads['cudnn'][k]
+            rel = float((g.double() - r.double()).norm() / (r.double().norm() + 1e-30))
+            assert rel <= 1e-4, (k, rel)
+        cfg.b200.decoder = 'hn'
+        m = mods['hn']
+        m.zero_grad()
+        m.allow_tf32 = True
+        vol_t = m(motion_weights_priors=prior)
+        (vol_t * g_vol).sum().backward()
+        report(f'vol_decoder V={V} TF32 products vs fp32', vol_t.detach(), outs['cudnn'], 1e-3, 1e-2)
+        worst = max(float((p.grad.double() - grads['cudnn'][k].double()).norm() / grads['cudnn'][k].double().norm())
+                    for k, p in m.named_parameters())
+        print(f'[parity] vol_decoder V={V} TF32 products: worst gradient rel L2 vs fp32 {worst:.2e}')
+        assert worst <= 5e-2, worst
+    finally:
+        cfg.b200.decoder = 'auto'
