@@ -641,6 +641,28 @@ static int launch_deconv_gemm(const DeconvArgs& g, dim3 grid, bool x3, int tn, b
 // column tile of a GEMM with `n` columns
 static int tile_n(int n) { return n <= 32 ? 32 : 64; }
 
+// Weight gradient of the FIRST transposed convolution (1^3 input): dW[ci][k][co] = in[ci] * g[o(k)][co] for the 8 taps
+// k in {1, 2}^3 that reach the 2^3 output (o = k - 1 per axis) and 0 for the other 56 - an outer product written once,
+// 16 bytes per thread in the parameter's [cin][64][cout] order (the generic kernel ran 8192 blocks with K = 1 for it).
+__global__ void __launch_bounds__(256) deconv_wgrad_din1_kernel(int cin, int cout, int ld_g, const float* __restrict__ in,
+                                                                const float* __restrict__ g, float4* __restrict__ dw) {
+  const int q4 = cout >> 2;                                   // float4 per (ci, tap) row
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)cin * 64 * q4) return;
+  const int c4 = (int)(idx % q4);
+  const int tap = (int)((idx / q4) & 63);
+  const int ci = (int)(idx / ((int64_t)q4 * 64));
+  const int kz = tap >> 4, ky = (tap >> 2) & 3, kx = tap & 3;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (((kz - 1) | (ky - 1) | (kx - 1)) >= 0 && kz <= 2 && ky <= 2 && kx <= 2) {
+    const int o = ((kz - 1) * 2 + (ky - 1)) * 2 + (kx - 1);
+    const float a = __ldg(in + ci);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + (size_t)o * ld_g) + c4);
+    v = make_float4(a * gg.x, a * gg.y, a * gg.z, a * gg.w);
+  }
+  dw[idx] = v;
+}
+
 // dst[i] = sum_s partial[s][i] (weight gradients of the layers whose K = voxel count was split)
 __global__ void sum_partials_kernel(const float4* __restrict__ partial, int splits, int64_t n4, float4* __restrict__ dst) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -725,6 +747,7 @@ __global__ void __launch_bounds__(256) column_sum_kernel(int64_t rows, int ld, i
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5, n_slabs = gridDim.x, c0 = blockIdx.y * kColSumMaxLd;
   const int64_t r0 = rows * blockIdx.x / n_slabs, r1 = rows * (blockIdx.x + 1) / n_slabs;
   float s[kColSumMaxLd / 32] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
   for (int64_t r = r0 + rl; r < r1; r += 8) {
 #pragma unroll
     for (int q = 0; q < kColSumMaxLd / 32; ++q)
@@ -745,10 +768,24 @@ __global__ void __launch_bounds__(256) column_sum_kernel(int64_t rows, int ld, i
   if (threadIdx.x == 0) is_last = atomicAdd(counter + blockIdx.y, 1u) == (unsigned)(n_slabs - 1);
   __syncthreads();
   if (is_last) {
+    // the same two-level order for the partials: row lane rl takes slabs rl, rl + 8, ..., then the 8 lanes in order
     __threadfence();
+#pragma unroll
+    for (int q = 0; q < kColSumMaxLd / 32; ++q) s[q] = 0.f;
+#pragma unroll 4
+    for (int b = rl; b < n_slabs; b += 8) {
+#pragma unroll
+      for (int q = 0; q < kColSumMaxLd / 32; ++q)
+        if (c0 + cl + 32 * q < ld) s[q] += __ldcg(partial + (size_t)b * ld + c0 + cl + 32 * q);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kColSumMaxLd / 32; ++q) red[rl][cl + 32 * q] = s[q];
+    __syncthreads();
     if (threadIdx.x < kColSumMaxLd && c < n_cols) {
       float t = 0.f;
-      for (int b = 0; b < n_slabs; ++b) t += __ldcg(partial + (size_t)b * ld + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
       out[c] = t;
     }
   }
@@ -818,7 +855,7 @@ struct DecPlan {
   size_t off_partial, off_g[2], off_dlogits, off_colsum, off_counters, scratch_floats;
 };
 
-constexpr int kColSumSlabs = 64;
+constexpr int kColSumSlabs = 128;
 // K-splits for a GEMM with `tiles` output tiles: the low layers are weight-bandwidth bound and need many CTAs; the large
 // layers also run faster in ~4 blocks per SM than in one wave (measured: 74 against 83 us for the last layer's forward)
 static int pick_splits(int64_t tiles, int k_total) {
@@ -975,7 +1012,7 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     const int din = p.din[l], d3 = din * din * din, cin = p.ch[l], cout = p.ch[l + 1];
     const int64_t rows_out = (int64_t)8 * d3;
     // bias gradient
-    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(kColSumSlabs, rows_out / 64));
+    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(kColSumSlabs, rows_out / 32));
     column_sum_kernel<<<dim3((unsigned)slabs, (unsigned)ceil_div(ld_g, kColSumMaxLd)), 256, 0, st>>>(rows_out, ld_g, cout, g_out, sc + p.off_colsum,
                                                                                                   counters + l * kColSumMaxChunks, d_conv_b[l]);
     HN_TRY(launched("hn_vol_decoder_bwd/bias"));
@@ -983,15 +1020,22 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     DeconvArgs g;
     memset(&g, 0, sizeof(g));
     g.din = din; g.log2_din = l; g.cin = cin; g.cout = cout; g.ld_out = ld_g; g.in = ws + p.off_act[l]; g.outside = g_out; g.dst = d_conv_w[l];
+    const bool wbig = use_big_tiles(2, din, cin, cout), dbig = use_big_tiles(1, din, cin, cout);
+    const bool outer = din == 1 && (cout & 3) == 0 && (ld_g & 3) == 0;      // first layer: an outer product per tap
+    if (outer) {
+      const int64_t n4 = (int64_t)cin * 64 * cout / 4;
+      deconv_wgrad_din1_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(cin, cout, ld_g, ws + p.off_act[l], g_out,
+                                                                                   reinterpret_cast<float4*>(d_conv_w[l]));
+      HN_TRY(launched("hn_vol_decoder_bwd/wgrad outer"));
+    }
     const int wsp = p.wgrad_splits[l];
     g.k_splits = wsp;
-    const bool wbig = use_big_tiles(2, din, cin, cout), dbig = use_big_tiles(1, din, cin, cout);
     g.k_per_split = ceil_div(ceil_div(d3, wsp), tile_k(wbig)) * tile_k(wbig);
     if (wsp > 1) g.dst = sc + p.off_partial;
     const int tn = tile_n(cout);
     dim3 wgrid((unsigned)(ceil_div(cin, tile_m_rows(wbig)) * ceil_div(cout, tn)), 64, (unsigned)wsp);
-    HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, wbig, st, "hn_vol_decoder_bwd/wgrad"));
-    if (wsp > 1) {
+    if (!outer) HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, wbig, st, "hn_vol_decoder_bwd/wgrad"));
+    if (wsp > 1 && !outer) {
       const int64_t n4 = (int64_t)cin * 64 * cout / 4;
       sum_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sc + p.off_partial), wsp, n4,
                                                                               reinterpret_cast<float4*>(d_conv_w[l]));
