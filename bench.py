@@ -726,7 +726,7 @@ def main():
         barrier()
         ops.timing_start()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
+        reps = 10          # frames back to back: the host enqueues frame i + 1 while frame i runs (no sync in between)
         r0.record()
         for _ in range(reps):
             render_frame(sharded=True, one_chunk=True)

@@ -72,6 +72,10 @@ _UNSUPPORTED = (
 )
 
 
+# device index -> stream of the volume decoder branch (module level: streams are neither copied nor pickled with a Network)
+_SIDE_STREAMS: Dict[int, 'torch.cuda.Stream'] = {}
+
+
 class Network(nn.Module):
     def __init__(self):
         super().__init__()
@@ -83,7 +87,6 @@ class Network(nn.Module):
                     f'that the B200 hot path does not implement (SURVEY.md section 2, row 22)')
 
         self.motion_basis_computer = MotionBasisComputer(total_bones=cfg.total_bones)
-        self._side_streams = {}           # device index -> stream of the volume decoder branch (forward)
 
         self.mweight_vol_decoder = _load_symbol(cfg.mweight_volume.module, 'MotionWeightVolumeDecoder')(
             embedding_size=cfg.mweight_volume.embedding_size,
@@ -216,9 +219,9 @@ class Network(nn.Module):
         side = None
         if bool(b200.get('front_streams', True)):
             main = torch.cuda.current_stream(dev)
-            side = self._side_streams.get(dev.index)
+            side = _SIDE_STREAMS.get(dev.index)
             if side is None:
-                side = self._side_streams[dev.index] = torch.cuda.Stream(dev)
+                side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
             pri = priors.float()
             side.wait_stream(main)
             with torch.cuda.stream(side):
