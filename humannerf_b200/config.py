@@ -156,8 +156,8 @@ _DEFAULTS: Dict[str, Any] = {
         'mlp_precision': 'fp32',
         # keep the heavy per-sample outputs (weights (R,S,24) ...) in the dict
         'heavy_outputs': True,
-        # motion-weight volume decoder: 'hn' = hand-written kernels (csrc/vol_decoder.cu), 'cudnn' = PyTorch / cuDNN
-        # transposed convolutions, 'auto' = 'hn' on the fp32 parity path, 'cudnn' (TF32) on the bf16 path
+        # motion-weight volume decoder: 'hn' / 'auto' = hand-written kernels (csrc/vol_decoder.cu), 'cudnn' = PyTorch /
+        # cuDNN transposed convolutions (A/B)
         'decoder': 'auto',
         # run the volume decoder on a side stream, concurrently with the pose decoder / forward kinematics (and their
         # backward passes with each other)
@@ -179,8 +179,8 @@ _DEFAULTS: Dict[str, Any] = {
         'fused_front_end': True,
         # one-launch multi-tensor Adam (csrc/adam.cu) instead of torch.optim.Adam's per-group kernels
         'fused_adam': True,
-        # TF32 in the cuDNN transposed convolutions of the motion-weight volume decoder: 'auto' = on with the bf16
-        # MLP path (2e-2 parity bound), off with the fp32 path (TF32 moves the blend weights by 1e-4); True / False
+        # product precision of the motion-weight volume decoder: 'auto' = plain TF32 with the bf16 MLP path (2e-2
+        # parity bound), 3xTF32 (hn kernels) / fp32 (cuDNN) with the fp32 path - TF32 moves the blend weights by 1e-4; True / False
         'decoder_tf32': 'auto',
     },
 }

@@ -852,7 +852,7 @@ struct DecPlan {
   int ld_logits;
   int fwd_splits[kDecMaxConv], dgrad_splits[kDecMaxConv], wgrad_splits[kDecMaxConv];   // K splits of the three GEMMs per layer
   size_t off_h, off_act[kDecMaxConv + 1], off_logits, ws_floats;          // saved for backward
-  size_t off_partial, off_g[2], off_dlogits, off_colsum, off_counters, scratch_floats;
+  size_t off_partial, off_partial_w, off_g[3], off_dlogits, off_colsum, off_counters, scratch_floats;
 };
 
 constexpr int kColSumSlabs = 128;
@@ -887,7 +887,7 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
   p.off_logits = take(n_vox * p.ld_logits);
   p.ws_floats = off;
   // scratch: split-K partials (forward and data gradient), two gradient buffers, d_logits
-  size_t part = 0, gmax = 0;
+  size_t part = 0, part_w = 0, gmax = 0;
   for (int l = 0; l < n_conv; ++l) {
     const size_t d3 = (size_t)p.din[l] * p.din[l] * p.din[l];
     const bool fb = use_big_tiles(0, p.din[l], p.ch[l], p.ch[l + 1]), db = use_big_tiles(1, p.din[l], p.ch[l], p.ch[l + 1]),
@@ -898,15 +898,15 @@ static int make_dec_plan(int embed, int hidden, int n_conv, const int* channels,
     p.dgrad_splits[l] = pick_splits(dt, (p.din[l] == 1 ? 8 : 64) * (ceil_div(p.ch[l + 1], tile_k(db)) * tile_k(db)));
     const int64_t wt = (int64_t)ceil_div(p.ch[l], tile_m_rows(wb)) * ceil_div(p.ch[l + 1], tile_n(p.ch[l + 1])) * 64;
     p.wgrad_splits[l] = pick_splits(wt, (int)d3);
-    if (p.wgrad_splits[l] > 1) part = std::max(part, (size_t)p.wgrad_splits[l] * p.ch[l] * 64 * p.ch[l + 1]);
+    if (p.wgrad_splits[l] > 1) part_w = std::max(part_w, (size_t)p.wgrad_splits[l] * p.ch[l] * 64 * p.ch[l + 1]);
     if (p.fwd_splits[l] > 1) part = std::max(part, (size_t)p.fwd_splits[l] * 8 * d3 * p.ch[l + 1]);
     if (p.dgrad_splits[l] > 1) part = std::max(part, (size_t)p.dgrad_splits[l] * d3 * p.ch[l]);
     gmax = std::max(gmax, std::max(d3 * p.ch[l], 8 * d3 * (size_t)std::max(p.ch[l + 1], l == n_conv - 1 ? p.ld_logits : 0)));
   }
   off = 0;
   p.off_partial = take(std::max<size_t>(part, 64));
-  p.off_g[0] = take(gmax);
-  p.off_g[1] = take(gmax);
+  p.off_partial_w = take(std::max<size_t>(part_w, 64));        // the weight side runs next to the data side (own partials)
+  for (int k = 0; k < 3; ++k) p.off_g[k] = take(gmax);
   p.off_dlogits = take(n_vox * p.ld_logits);
   p.off_colsum = take((size_t)kColSumSlabs * kColSumMaxLd * kColSumMaxChunks);
   p.off_counters = take(kDecMaxConv * kColSumMaxChunks);
@@ -936,6 +936,28 @@ static int run_forward_layer(const DecPlan& p, int l, const float* in, const flo
                                                                                        leaky ? 1 : 0, nullptr, out);
     HN_TRY(launched("hn_vol_decoder_fwd/finish"));
   }
+  return 0;
+}
+
+// Library-owned stream and events of the backward's weight side, one set per device (created on first use, never freed)
+struct BwdStreams {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[kDecMaxConv], done[kDecMaxConv];
+};
+static int get_bwd_streams(BwdStreams** out) {
+  static BwdStreams per_device[64];
+  int dev = 0;
+  HN_TRY(check_cuda(cudaGetDevice(&dev), "hn_vol_decoder_bwd/device"));
+  if (dev < 0 || dev >= 64) return fail_arg("hn_vol_decoder_bwd: device index %d", dev);
+  BwdStreams& b = per_device[dev];
+  if (!b.side) {
+    HN_TRY(check_cuda(cudaStreamCreateWithFlags(&b.side, cudaStreamNonBlocking), "hn_vol_decoder_bwd/stream"));
+    for (int l = 0; l < kDecMaxConv; ++l) {
+      HN_TRY(check_cuda(cudaEventCreateWithFlags(&b.fork[l], cudaEventDisableTiming), "hn_vol_decoder_bwd/event"));
+      HN_TRY(check_cuda(cudaEventCreateWithFlags(&b.done[l], cudaEventDisableTiming), "hn_vol_decoder_bwd/event"));
+    }
+  }
+  *out = &b;
   return 0;
 }
 
@@ -999,6 +1021,13 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
   if (workspace_bytes < (int64_t)p.ws_floats * 4 || scratch_bytes < (int64_t)p.scratch_floats * 4)
     return fail_arg("hn_vol_decoder_bwd: workspace / scratch too small");
   cudaStream_t st = as_stream(stream);
+  // Two branches per layer, both fed by g_out: the DATA side (data gradient -> next layer's g_out) stays on `stream`, the
+  // WEIGHT side (bias sums, weight gradient) runs on a library-owned stream forked and joined with events - capturable
+  // (the side stream joins the capture through the fork event and leaves it through the join event).  The three g
+  // buffers rotate, and the data gradient that re-uses a buffer waits for the weight side that read it two layers up.
+  BwdStreams* bs = nullptr;
+  HN_TRY(get_bwd_streams(&bs));
+  cudaStream_t sw = bs->side;
   const float* ws = static_cast<const float*>(workspace);
   float* sc = static_cast<float*>(scratch);
   const int side = 2 * p.din[n_conv - 1], n_vox = side * side * side;
@@ -1011,9 +1040,12 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
   for (int l = n_conv - 1; l >= 0; --l) {
     const int din = p.din[l], d3 = din * din * din, cin = p.ch[l], cout = p.ch[l + 1];
     const int64_t rows_out = (int64_t)8 * d3;
+    // fork: g_out of this layer is complete on `st`
+    HN_TRY(check_cuda(cudaEventRecord(bs->fork[l], st), "hn_vol_decoder_bwd/fork"));
+    HN_TRY(check_cuda(cudaStreamWaitEvent(sw, bs->fork[l], 0), "hn_vol_decoder_bwd/fork wait"));
     // bias gradient
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(kColSumSlabs, rows_out / 32));
-    column_sum_kernel<<<dim3((unsigned)slabs, (unsigned)ceil_div(ld_g, kColSumMaxLd)), 256, 0, st>>>(rows_out, ld_g, cout, g_out, sc + p.off_colsum,
+    column_sum_kernel<<<dim3((unsigned)slabs, (unsigned)ceil_div(ld_g, kColSumMaxLd)), 256, 0, sw>>>(rows_out, ld_g, cout, g_out, sc + p.off_colsum,
                                                                                                   counters + l * kColSumMaxChunks, d_conv_b[l]);
     HN_TRY(launched("hn_vol_decoder_bwd/bias"));
     // weight gradient: one small GEMM per tap, written in the parameter's [cin][64][cout] layout
@@ -1024,25 +1056,28 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
     const bool outer = din == 1 && (cout & 3) == 0 && (ld_g & 3) == 0;      // first layer: an outer product per tap
     if (outer) {
       const int64_t n4 = (int64_t)cin * 64 * cout / 4;
-      deconv_wgrad_din1_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(cin, cout, ld_g, ws + p.off_act[l], g_out,
+      deconv_wgrad_din1_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, sw>>>(cin, cout, ld_g, ws + p.off_act[l], g_out,
                                                                                    reinterpret_cast<float4*>(d_conv_w[l]));
       HN_TRY(launched("hn_vol_decoder_bwd/wgrad outer"));
     }
     const int wsp = p.wgrad_splits[l];
     g.k_splits = wsp;
     g.k_per_split = ceil_div(ceil_div(d3, wsp), tile_k(wbig)) * tile_k(wbig);
-    if (wsp > 1) g.dst = sc + p.off_partial;
+    if (wsp > 1) g.dst = sc + p.off_partial_w;
     const int tn = tile_n(cout);
     dim3 wgrid((unsigned)(ceil_div(cin, tile_m_rows(wbig)) * ceil_div(cout, tn)), 64, (unsigned)wsp);
-    if (!outer) HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, wbig, st, "hn_vol_decoder_bwd/wgrad"));
+    if (!outer) HN_TRY(launch_deconv_gemm<2>(g, wgrid, x3, tn, wbig, sw, "hn_vol_decoder_bwd/wgrad"));
     if (wsp > 1 && !outer) {
       const int64_t n4 = (int64_t)cin * 64 * cout / 4;
-      sum_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sc + p.off_partial), wsp, n4,
+      sum_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, sw>>>(reinterpret_cast<const float4*>(sc + p.off_partial_w), wsp, n4,
                                                                               reinterpret_cast<float4*>(d_conv_w[l]));
       HN_TRY(launched("hn_vol_decoder_bwd/wgrad sum"));
     }
-    // data gradient -> gradient of the pre-activation of the previous layer (LeakyReLU' from its stored output)
-    float* g_in = sc + p.off_g[l & 1];
+    HN_TRY(check_cuda(cudaEventRecord(bs->done[l], sw), "hn_vol_decoder_bwd/weight side done"));
+    // data gradient -> gradient of the pre-activation of the previous layer (LeakyReLU' from its stored output).  Its
+    // output buffer was the g_out of layer l + 2: that layer's weight side must have finished reading it
+    float* g_in = sc + p.off_g[l % 3];
+    if (l + 2 < n_conv) HN_TRY(check_cuda(cudaStreamWaitEvent(st, bs->done[l + 2], 0), "hn_vol_decoder_bwd/buffer wait"));
     g.w = conv_w[l]; g.act_in = ws + p.off_act[l];
     const int k_total = (din == 1 ? 8 : 64) * ceil_div(cout, tile_k(dbig)) * tile_k(dbig);
     const int64_t tiles = (int64_t)ceil_div(d3, tile_m_rows(dbig)) * ceil_div(cin, kTile);
@@ -1064,7 +1099,11 @@ int hn_vol_decoder_bwd(int embed, int hidden, int n_conv, const int* channels, c
   linear_wgrad_kernel<<<ceil_div(hidden * embed, 256), 256, 0, st>>>(hidden, embed, g_out, embedding, d_lin_w, d_lin_b);
   HN_TRY(launched("hn_vol_decoder_bwd/linear wgrad"));
   linear_dgrad_kernel<<<ceil_div(embed, 32), 1024, 0, st>>>(hidden, embed, lin_w, g_out, d_embedding);
-  return launched("hn_vol_decoder_bwd/linear dgrad");
+  HN_TRY(launched("hn_vol_decoder_bwd/linear dgrad"));
+  // join: everything the weight side wrote is complete for whatever follows on `stream`
+  for (int l = std::min(n_conv - 1, 1); l >= 0; --l)
+    HN_TRY(check_cuda(cudaStreamWaitEvent(st, bs->done[l], 0), "hn_vol_decoder_bwd/join"));
+  return 0;
 }
 
 }  // extern "C"

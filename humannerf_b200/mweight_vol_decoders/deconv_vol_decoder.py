@@ -1,12 +1,11 @@
 """Motion-weight volume decoder, plugin-compatible with reference
 `core/nets/human_nerf/mweight_vol_decoders/deconv_vol_decoder.py:8-33`:
 softmax(decoder(const_embedding) + log(prior)) over the 25 channels.  On a CUDA device the whole module - linear
-layer, the five transposed convolutions, LeakyReLUs, softmax with the prior, and their backward - can run on the
+layer, the five transposed convolutions, LeakyReLUs, softmax with the prior, and their backward - runs on the
 hand-written kernels of csrc/vol_decoder.cu (`ops.vol_decoder`: fp32 storage, tensor-core products, deterministic).
-`cfg.b200.decoder`: 'hn' = those kernels, 'cudnn' = PyTorch / cuDNN, 'auto' (default) = 'hn' everywhere (fp32 parity path:
-3xTF32 products, bit-reproducible gradients; rendering) except bf16-path training steps, where cuDNN's TF32 implicit-GEMM
-engines are still ~0.6 ms per training step faster than the mma.sync kernels here (measured: 7.00 against 7.58 ms per
-step).  CPU tensors (construction-time tests, the oracle arm) always take the PyTorch path."""
+`cfg.b200.decoder`: 'hn' / 'auto' (default) = those kernels (fp32 parity path: 3xTF32 products; bf16 path: TF32 products
+like cuDNN's TF32 engines), 'cudnn' = PyTorch / cuDNN (kept for A/B: 6.67 against 6.71 ms per training step).
+CPU tensors (construction-time tests, the oracle arm) always take the PyTorch path."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -22,16 +21,12 @@ class MotionWeightVolumeDecoder(nn.Module):
         self.const_embedding = nn.Parameter(torch.randn(embedding_size), requires_grad=True)
         self.decoder = ConvDecoder3D(embedding_size=embedding_size, volume_size=volume_size,
                                      voxel_channels=total_bones + 1)
-        # set by humannerf_b200.Network: True on the bf16 tensor-core path (2e-2 parity bound), where the
-        # TF32 transposed convolutions are ~0.4 ms per training step faster than cuDNN's fp32 engine
+        # set by humannerf_b200.Network: True on the bf16 tensor-core path (2e-2 parity bound): plain TF32 products
         self.allow_tf32 = False
 
     def _use_kernels(self, prior) -> bool:
         from humannerf_b200.config import get_cfg
         mode = str(get_cfg().get('b200', {}).get('decoder', 'auto')).lower()
-        if mode == 'auto':
-            # cuDNN only where it is faster: bf16-path TRAINING steps (allow_tf32 is set by Network on the bf16 path)
-            mode = 'cudnn' if (self.allow_tf32 and torch.is_grad_enabled()) else 'hn'
         return prior.is_cuda and mode != 'cudnn'
 
     def forward(self, motion_weights_priors, **_):

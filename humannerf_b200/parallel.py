@@ -182,7 +182,7 @@ class CutBReducer:
 
     def check_same_frame(self, group=None) -> None:
         """Raise unless the boundary tensors (functions of the frame and the replicated parameters only) agree on
-        every rank: max and min over ranks of a per-tensor checksum within 1e-5 relative (the cuDNN decoder is not
+        every rank: max and min over ranks of a per-tensor checksum within 1e-5 relative (with `cfg.b200.decoder = 'cudnn'` the decoder is not
         bit-reproducible between processes; a different frame moves the checksums by orders of magnitude more)."""
         if not self.boundary or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return

@@ -119,7 +119,10 @@ def test_train_step_bf16_against_reference():
     Loss within 1e-3 of the reference's (measured 4e-5).  Gradients, per tensor (all 55), against the float64 gradient:
     relative L2 <= the group bound AND cosine similarity >= the group bound (a zero, random or sign-flipped gradient
     has cosine <= 0; independent noise of relative size e gives 1 / sqrt(1 + e^2)).  Measured on the B200 (printed):
-    canonical MLP 0.012-0.09 / cos >= 0.996, volume decoder 0.05-0.28, non-rigid MLP 0.30-0.55, pose decoder 0.32.
+    canonical MLP 0.012-0.09 / cos >= 0.996, volume decoder 0.06-0.29, non-rigid MLP 0.30-0.55, pose decoder 0.39-0.42 /
+    cos >= 0.909 with the TF32 products of the decoder kernels (0.32 with cuDNN's TF32 engines, `cfg.b200.decoder =
+    'cudnn'`: the pose gradient goes through the SPATIAL gradient of the blend-weight volume, i.e. differences of
+    neighbouring voxels, which see the 10-bit mantissa of either; the reference's own fp32 gradient is 0.11-0.14 away).
     The input-side groups are large because the bf16 forward flips ~2 % of the ReLU masks per layer and d(raw)/d(xyz)
     of a ReLU MLP behind a 2^9-frequency encoding changes by O(1) in every flipped region: the bf16 gradient is the
     exact gradient of the bf16 forward function (tests/bf16_emu.py agrees with the kernels to 0.12), not a noisy copy
@@ -141,7 +144,7 @@ def test_train_step_bf16_against_reference():
     assert abs(tot - st['loss']) <= 1e-3 * st['loss']
     rows = _grad_table(st, grads, tag)
     bounds = {'cnl_mlp': (0.12, 0.99), 'mweight_vol_decoder': (0.35, 0.93), 'non_rigid_mlp': (0.65, 0.80),
-              'pose_decoder': (0.42, 0.90)}
+              'pose_decoder': (0.48, 0.88)}
     f64 = np.load(F64, allow_pickle=False)
     bad = []
     for n, e_ref, e_f64, r_f64, nrm in rows:
