@@ -240,3 +240,35 @@ def test_deferred_weight_gradients_context_logic():
             ops._DEFERRED['jobs'].append(lambda: ran.append('never'))
             raise ValueError('step failed')
     assert ran == ['a', 'b'] and not ops._DEFERRED['on'] and ops._DEFERRED['jobs'] == []
+
+
+def test_decoder_plan_sizes_and_phase_argument_errors():
+    """Host-only entry points of the volume decoder and of the two-phase field backward (no device work): workspace =
+    the saved activations of the reference decoder (network_util.py:25-38: 1024 @ 1^3, 512 @ 2^3, 512 @ 4^3, 256 @ 8^3,
+    256 @ 16^3, 32-float logits rows @ 32^3), scratch at least the three rotating gradient buffers; bad geometries and a
+    bad `phases` mask are refused with a message."""
+    lib = _lib.load()
+    ch = (ctypes.c_int * 6)(1024, 512, 512, 256, 256, 25)
+    ws = lib.hn_vol_decoder_workspace_bytes(256, 1024, 5, ch)
+    acts = [1024 * 1, 512 * 8, 512 * 64, 256 * 512, 256 * 4096, 32 * 32768]
+    assert ws == 4 * sum((a + 63) // 64 * 64 for a in acts) + 256
+    sc = lib.hn_vol_decoder_scratch_bytes(256, 1024, 5, ch)
+    gmax = max(256 * 4096, 8 * 4096 * 32)                      # widest gradient buffer: d(logits) rows of 32 floats
+    assert sc >= 4 * 3 * gmax
+    small = (ctypes.c_int * 4)(1024, 512, 512, 25)
+    assert 0 < lib.hn_vol_decoder_workspace_bytes(64, 1024, 3, small) < ws
+    bad = (ctypes.c_int * 6)(1000, 512, 512, 256, 256, 25)
+    assert lib.hn_vol_decoder_workspace_bytes(256, 1024, 5, bad) == -1 and b'hn_vol_decoder' in lib.hn_last_error()
+    wide = (ctypes.c_int * 3)(1024, 1024, 25)
+    assert lib.hn_vol_decoder_scratch_bytes(256, 1024, 2, wide) == -1 and b'output channels' in lib.hn_last_error()
+    many = (ctypes.c_int * 6)(1024, 512, 512, 256, 256, 40)
+    assert lib.hn_vol_decoder_workspace_bytes(256, 1024, 5, many) == -1
+    # hn_field_bwd_bf16_phases: the phase mask is checked before anything touches the device
+    from humannerf_b200.ops import FieldSpec
+    fp = FieldSpec().params([None] * 7, [None] * 7, [None] * 9, [None] * 9)
+    fg = _lib.FieldGrads()
+    for phases in (0, 4, 7):
+        rc = lib.hn_field_bwd_bf16_phases(ctypes.byref(fp), ctypes.byref(fg), 128, *([None] * 3), None, 0, *([None] * 4), None, 0, None,
+                                          None, 0, None, phases, None)
+        assert rc < 0 and b'phases' in lib.hn_last_error(), phases
+    assert _lib.BWD_DATA == 1 and _lib.BWD_WEIGHTS == 2
